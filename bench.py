@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- walk-jump chain-steps/s (atoms x steps / s) of the B200-native hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (the reference algorithm on the host CPU: oracle port)
+
+A bench "step" is one pass of the hot path over one batch: `--inner` consecutive BAOAB walk-jump steps (radius graph,
+edge features, 6 conv blocks, head, fused integrator + jump) over all chains of the workload.  The workload at N=1 is
+BASELINE.json configs[1]: uncapped 2AA peptides, 1024 chains (per GPU; weak scaling at N>1), random-init default
+denoiser with output_gain=1, synthetic coordinates.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SIGMA = 0.04
+MCMC = dict(delta=0.04, friction=1.0, M=1.0, inverse_temperature=1.0, score_fn_clip=100.0)
+METRIC = "walkjump_atom_steps_per_s"
+UNIT = "atoms*steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="2AA", choices=["2AA", "4AA", "ala2_capped", "protein1000"])
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: 1024; protein1000: 64)")
+    ap.add_argument("--inner", type=int, default=4, help="walk-jump steps per bench step")
+    ap.add_argument("--cpu-sample-chains", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(args, rank: int):
+    from jamun_b200 import synthetic
+
+    chains = args.chains or (64 if args.workload == "protein1000" else 1024)
+    sizes_all = synthetic.workload_sizes(args.workload, chains * max(1, args.gpus))
+    sizes = sizes_all[rank * chains:(rank + 1) * chains]
+    n_res = {"2AA": 2, "4AA": 4, "ala2_capped": 2, "protein1000": 100}[args.workload]
+    t = synthetic.make_tensors(sizes, n_res=n_res, first_chain_id=rank * chains)
+    return t, sizes
+
+
+def oracle_model():
+    from oracle import jamun_oracle as O
+
+    torch.manual_seed(0)
+    o = O.Denoiser()
+    O.randomize_for_parity(o)
+    return o
+
+
+def cpu_reference_rate(args, sizes_sample, steps: int):
+    """The reference's formulation (oracle port) on the host cores: atoms x steps / s on a bounded sample."""
+    from jamun_b200 import synthetic
+    from oracle import jamun_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    o = oracle_model()
+    n_res = {"2AA": 2, "4AA": 4, "ala2_capped": 2, "protein1000": 100}[args.workload]
+    t = synthetic.make_tensors(sizes_sample, n_res=n_res)
+    ob = O.OracleBatch(pos=t["pos"], batch=t["batch"], num_graphs=t["num_graphs"], edge_index=t["edge_index"],
+                       atom_type_index=t["atom_type_index"], atom_code_index=t["atom_code_index"],
+                       residue_code_index=t["residue_code_index"], residue_sequence_index=t["residue_sequence_index"])
+    y0 = t["pos"] + SIGMA * torch.randn(t["pos"].shape)
+    with torch.no_grad():
+        O.walk_jump(o, ob, y0, SIGMA, mcmc=O.baoab, v_init="gaussian", steps=2, save_trajectory=True, redundant_jump=False, **MCMC)
+        t0 = time.perf_counter()
+        # steps+1 score evaluations advance `steps` Langevin updates; the reference's redundant jump pass doubles that
+        O.walk_jump(o, ob, y0, SIGMA, mcmc=O.baoab, v_init="gaussian", steps=steps + 1, save_trajectory=True,
+                    redundant_jump=True, **MCMC)
+        dt = time.perf_counter() - t0
+    atoms = int(t["pos"].shape[0])
+    return atoms * steps / dt, atoms, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from jamun_b200 import synthetic
+
+    chains = args.chains or (64 if args.workload == "protein1000" else 1024)
+    sizes = synthetic.workload_sizes(args.workload, chains)[: args.cpu_sample_chains]
+    inner = 1
+    rates, times = [], []
+    for k in range(args.warmup + args.steps):
+        rate, atoms, dt = cpu_reference_rate(args, sizes, inner)
+        if k >= args.warmup:
+            rates.append(rate)
+            times.append(dt)
+    value = sum(rates) / len(rates)
+    sample = f"first {len(sizes)} chains ({atoms} atoms) of the {args.workload} workload x {inner} walk-jump step(s) per bench step, " \
+             f"reference formulation incl. its redundant jump pass"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} uncapped peptides, {chains} chains/GPU, sigma=0.04, BAOAB", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch.distributed as dist
+
+    import jamun_b200 as J
+    from jamun_b200 import data, ops, utils
+    from jamun_b200.sampling.mcmc import BAOAB
+    from jamun_b200.sampling.mcmc.functional import fused_baoab
+    from jamun_b200.sampling.walkjump import SingleMeasurementSampler
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t, sizes = build_workload(args, rank)
+    atoms = int(t["pos"].shape[0])
+    # weights: seed-0 default init + parity re-draws (output_gain=1), identical on every rank -- product-side init
+    torch.manual_seed(0)
+    model = J.default_denoiser()
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        model.arch_module.output_gain.fill_(1.0)
+        from jamun_b200.model.noise_conditioning import NoiseConditionalScaling
+
+        for m in model.modules():
+            if isinstance(m, NoiseConditionalScaling):
+                last = m.scale_predictor[-1]
+                last.weight.copy_(torch.randn(last.weight.shape, generator=gen) * 0.1)
+                last.bias.copy_(1.0 + torch.randn(last.bias.shape, generator=gen) * 0.1)
+    model = model.to(dev).eval()
+    torch.manual_seed(1234 + rank)  # per-rank Philox stream (cmdline/sample.py:86-88)
+    batch = data.Batch.from_tensors(t).to(dev)
+    wrapped = utils.ModelSamplingWrapper(model, batch, SIGMA)
+    topo = wrapped.topology
+    sampler = SingleMeasurementSampler(BAOAB(steps=args.inner + 1, save_trajectory=False, **MCMC), SIGMA)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    y = wrapped.sample_initial_noisy_positions()
+    state = {"y": y, "v": "gaussian"}
+
+    def device_step():
+        out = fused_baoab(model, topo, state["y"], SIGMA, steps=args.inner + 1, v_init=state["v"], **MCMC)
+        state["y"], state["v"] = out["y"], out["v"]
+        return out
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = device_step()
+    if world > 1:  # the run's only collective: final gather of the denoised samples
+        gathered = [torch.empty_like(out["xhat"]) for _ in range(world)] if False else None
+        pad = torch.zeros(max(1, atoms), 3, device=dev)
+        sz = torch.tensor([atoms], device=dev)
+        szs = [torch.zeros_like(sz) for _ in range(world)]
+        dist.all_gather(szs, sz)
+        mx = int(max(int(s) for s in szs))
+        buf = torch.zeros(mx, 3, device=dev)
+        buf[:atoms] = out["xhat"]
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf)
+    ev1.record()
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    tt = torch.tensor([ms, float(atoms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, total_atoms = float(tmax[0]), float(tsum[1])
+    else:
+        total_atoms = float(atoms)
+    value = total_atoms * args.inner * args.steps / (ms * 1e-3)
+
+    # ---------------- end-to-end through the public sampler API with HOST buffers (`e2e`)
+    y_host = y.detach().cpu().pin_memory()
+    x_host = torch.empty_like(y_host).pin_memory()
+
+    def e2e_step():
+        y_dev = y_host.to(dev, non_blocking=True)
+        o = sampler.sample(wrapped, y_init=y_dev, v_init="gaussian")
+        x_host.copy_(o["sample"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        te = torch.tensor([ems], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ems = float(te[0])
+    e2e_value = total_atoms * args.inner * args.steps / (ems * 1e-3)
+    bytes_io = int(y_host.numel() * 4)
+
+    # ---------------- roofline of the dominant kernel: jamun_conv_fwd (hidden block), timed alone with CUDA events
+    pk, pk_src = peaks()
+    plan = model.arch_module.plan(model.sigma_context(SIGMA).c_noise, dev)
+    b = plan.blocks[1]
+    x_in = topo.xs[0]
+    reps = 5
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], topo.conv)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(reps):
+        ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], topo.conv)
+    c1.record()
+    torch.cuda.synchronize()
+    conv_ms = c0.elapsed_time(c1) / reps
+    E = int(topo.rowptr[-1].item())
+    deg = E / max(1, atoms)
+    flop_per_atom = 2 * 65 * (152 * 152 + 3 * 184 * 32) + 2 * deg * 65 * (152 + 3 * 184)  # contraction + aggregate build
+    achieved = atoms * flop_per_atom / (conv_ms * 1e-3) / 1e12
+    tf32_peak = pk["bf16_tflops"] / 2.0  # dense tf32 = half the bf16 rate; fp32 parity needs 3 tf32 passes -> /3 for 3xTF32
+    roofline = {"kernel": "jamun_conv_fwd (hidden ConvBlock, 120x0e+32x1e)", "bound": "tensor", "achieved": achieved,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                "peak_source": f"{pk_src} bf16 burst / 2 (tf32 dense)", "ms_per_launch": conv_ms,
+                "flop_per_atom": flop_per_atom, "mean_in_degree": deg}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload} uncapped peptides, {len(sizes)} chains/GPU ({atoms} atoms/GPU), "
+                                       f"{args.inner} BAOAB walk-jump steps per bench step, sigma=0.04, default e3conv denoiser "
+                                       f"(random init, output_gain=1)",
+                           "l2": "working set per step (weights 42 MB x2 + edge features) exceeds nothing special; "
+                                 "every step rewrites y/CSR/features, inputs are regenerated each step, no cached outputs",
+                           "parallelism": f"chains sharded x{world}, final NCCL all_gather of samples"},
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
+                        "ms_per_step": ems / args.steps},
+                "roofline": roofline}
+        if not args.no_cpu_baseline and world == 1:
+            from jamun_b200 import synthetic
+
+            chains = args.chains or (64 if args.workload == "protein1000" else 1024)
+            sample_sizes = synthetic.workload_sizes(args.workload, chains)[: args.cpu_sample_chains]
+            rate, a, dt = cpu_reference_rate(args, sample_sizes, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"first {len(sample_sizes)} chains ({a} atoms) x 1 walk-jump step, reference "
+                                              f"formulation incl. redundant jump pass, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

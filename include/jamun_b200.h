@@ -1,0 +1,149 @@
+/* jamun_b200 C ABI -- the drop-in boundary of the B200-native walk-jump hot path.
+ *
+ * The reference (prescient-design/jamun) is pure Python and has no native boundary of its own;
+ * every entry point below replaces one third-party kernel family the reference reaches through
+ * Python (file:line under /root/reference/src/jamun are cited per function).  A maintainer binds
+ * these with ctypes; jamun_b200/_lib.py is that binding.
+ *
+ * Conventions: the caller owns every buffer (device pointers unless noted); no entry point
+ * allocates or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ * the return value is 0 or a negative JAMUN_E* code (jamun_last_error() gives the text);
+ * nothing throws.  Thread-safe for distinct streams.  All floating point is fp32, indices int32.
+ *
+ * Internal node-feature layout ("SoA irreps"): for irreps `S x0e + V x1e` a row is
+ * [S scalars | V x-components | V y-components | V z-components]; jamun_layout_* convert from/to
+ * the e3nn layout [S scalars | V x (x,y,z)] used at module boundaries of the reference.
+ */
+#ifndef JAMUN_B200_H
+#define JAMUN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* jamun_stream_t;
+
+#define JAMUN_OK 0
+#define JAMUN_EINVAL (-1)   /* bad argument / unsupported irreps */
+#define JAMUN_ECUDA (-2)    /* CUDA launch error */
+
+/* hidden irreps the kernels are specialised for (e3conv.yaml:4): 120x0e + 32x1e */
+#define JAMUN_S 120
+#define JAMUN_V 32
+#define JAMUN_HID (JAMUN_S + 3 * JAMUN_V)          /* 216 */
+#define JAMUN_GATE_IN (JAMUN_S + JAMUN_V + 3 * JAMUN_V) /* 248 = 152x0e + 32x1e */
+#define JAMUN_S0 56                                  /* initial embedding scalars */
+#define JAMUN_EDGE_HID 64                            /* radial MLP hidden width (edge_attr_dim) */
+#define JAMUN_NBASIS 32                              /* radial Gaussians */
+
+int jamun_abi_version(void);
+const char* jamun_last_error(void);
+
+/* NoiseConditionalScaling.scale_predictor: out = W2 . SELU(W1*c + b1) + b2, optional sigmoid
+ * (model/noise_conditioning.py:33-38,50-54,69-73).  w1,b1:[n]  w2:[n,n] row-major (out,in)  b2:[n]. */
+int jamun_noise_mlp(const float* w1, const float* b1, const float* w2, const float* b2, float c_noise,
+                    int n, int apply_sigmoid, float* out, jamun_stream_t stream);
+
+/* AtomEmbeddingWithResidueInformation.forward fused with initial_noise_scaling
+ * (model/atom_embedding.py:58-76, arch/e3conv.py:129-130).  idx*: [N] int32, tab*: [rows, dim*],
+ * scale: [sum dims] or NULL, out: [N, sum dims]. */
+int jamun_atom_embed(const int* idx0, const int* idx1, const int* idx2, const int* idx3,
+                     const float* tab0, const float* tab1, const float* tab2, const float* tab3,
+                     int dim0, int dim1, int dim2, int dim3, const float* scale, int N, float* out,
+                     jamun_stream_t stream);
+
+/* mean_center + input scaling (utils/mean_center.py:7-12, model/denoiser.py:205-207,191-192):
+ * ybar = y - centroid_chain(y) (ybar = y when center == 0); p = c_in * ybar.  chain_ptr: [G+1].
+ * ybar/p may be NULL. */
+int jamun_center_scale(const float* y, const int* chain_ptr, int G, int center, float c_in, float* ybar, float* p,
+                       jamun_stream_t stream);
+
+/* radius_graph + bonded-edge concatenation as a receiver-sorted CSR
+ * (model/denoiser.py:138-166 -> torch_geometric.nn.radius_graph -> torch_cluster radius kernel).
+ * Pair (j->i) kept iff same chain, j != i, dx*dx+dy*dy+dz*dz < r2 (strict, unfused fp32), and j is
+ * among the first max_num_neighbors+1 hits (self included) scanning the chain in ascending index;
+ * max_num_neighbors < 0 disables the cap.  Row i = radial sources ascending, then the bonded
+ * in-edges of i in their original order (bond_rowptr:[N+1], bond_src: CSR of the template's bonded
+ * edge_index by receiver).  Outputs: rowptr:[N+1] (rowptr[N] = E on device), col/edst:[cap] source
+ * and receiver per edge, ebond:[cap] 0 radial / 1 bonded.  cap >= (max_num_neighbors+1)*N + E_bonded.
+ * scratch: [N+1] int32. */
+int jamun_radius_csr(const float* pos, const int* chain_of, const int* chain_ptr, int N, float r2,
+                     int max_num_neighbors, const int* bond_rowptr, const int* bond_src, int* scratch,
+                     int* rowptr, int* col, int* edst, unsigned char* ebond, jamun_stream_t stream);
+
+/* Edge featurisation (arch/e3conv.py:110-127): for each CSR edge, rhat = (p[src]-p[dst])/|.| (so
+ * sh = [1, sqrt3*rhat]) and the 32 Gaussian radial bases exp(-((d-mu_k)/step)^2)/1.12.
+ * rhat: [cap,4] (x,y,z,d)  rb: [cap, JAMUN_NBASIS]  mu: [JAMUN_NBASIS]. */
+int jamun_edge_geom(const float* p, const int* rowptr, const int* col, const int* edst, int N, int cap,
+                    const float* mu, float step, float* rhat, float* rb, jamun_stream_t stream);
+
+/* Radial MLP hidden layer (e3tools/nn/_conv.py:84-94, _mlp.py:21-34), bondedness embedding folded:
+ * h = SiLU(w0r . rb + b0eff[ebond]).  w0r: [64, 32] (the radial half of radial_nn.0.weight),
+ * b0eff: [2, 64] = bias + W0[:, :32] . embed_bondedness[flag].  h: [cap, 64]. */
+int jamun_edge_radial_hidden(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                             const float* w0r, const float* b0eff, float* h, jamun_stream_t stream);
+
+/* Conv.forward (e3tools/nn/_conv.py:96-119): gather, per-edge-weighted FullyConnectedTensorProduct,
+ * scatter-mean -- evaluated in the aggregate-then-transform form: per receiver
+ * A = sum_e [h_e,1] (x) f_e, out = alpha * A . M / max(1,deg).  x: [N, s_in + 3 v_in] SoA;
+ * (s_in,v_in) in {(120,32),(56,0)}.  m0: [65, s_in+v_in, 152]  m1: [65, s_in+2 v_in, 32] packed from
+ * radial_nn.3.{weight,bias}.  out: [N, 248] SoA (152 scalars | 32 x3). */
+int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                   const float* rhat, const float* m0, const float* m1, float alpha0, float alpha1, int N,
+                   float* out, jamun_stream_t stream);
+
+/* Gate + self-interaction + skip Linear + noise-conditional skip/scale
+ * (e3tools/nn/_gate.py:63-64, _interaction.py:26-30, model/noise_conditioning.py:50-73,
+ * arch/e3conv.py:131-133).  y = Lin_self(Gate(conv)) + Lin_skip(x_in);
+ * x_new = mix ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next (if s_next).
+ * Weights pre-scaled by 1/sqrt(fan_in): wself_s:[120,120] wself_v:[32,32] wskip_s:[s_in,120]
+ * wskip_v:[32,32] or NULL.  skip_w, s_next: [152] per-irrep or NULL. */
+int jamun_block_tail(const float* conv, const float* x_in, int s_in, int v_in, const float* x_res,
+                     const float* wself_s, const float* wself_v, const float* wskip_s, const float* wskip_v,
+                     const float* skip_w, const float* s_next, float c_act, float c_gate, int N,
+                     float* x_new, float* x_scaled, jamun_stream_t stream);
+
+/* Output head (e3tools/nn/_mlp.py:37-114, arch/e3conv.py:134-135): Linear -> Gate -> Linear(1x1e) * gain.
+ * w1_s: [120,152] w1_v:[32,32] pre-scaled; w2: [32] pre-scaled by gain/sqrt(32).  g: [N,3]. */
+int jamun_head(const float* x, const float* w1_s, const float* w1_v, const float* w2, float c_gate, int N,
+               float* g, jamun_stream_t stream);
+
+/* One fused walk-jump step (sampling/mcmc/functional/_splitting.py:26-41,136-178, model/denoiser.py:111-114,
+ * 200,213-215, sampling/walkjump/_single_measurement.py:57): given the network output g at the current y,
+ *   xhat = center(c_skip*ybar + c_out*g); score = (xhat - y)/sigma^2; psi = beta*clip(score)
+ *   [save y/xhat/score]; v = first ? v : v + (delta/2) psi            (closing B of the previous step)
+ *   if !last: v += u (delta/2) psi; y += (delta/2) v; v = a v + z sqrt(u) R; y += (delta/2) v   (B A O A)
+ *             ybar = center(y); p = c_in*ybar                          (prologue of the next evaluation)
+ * R = noise[N,3] if non-NULL else Philox4x32-10(seed, step) Box-Muller.  clip<=0 disables clipping.
+ * traj_* may be NULL.  score_in non-NULL: use that score instead of deriving xhat/score from g (generic
+ * score_fn protocol of mcmc/_splitting.py:56-58; g, xhat outputs are then ignored and may be NULL). */
+typedef struct {
+    float c_in, c_skip, c_out, sigma2;
+    float delta, u, a, z_sqrt_u, beta, clip;
+    int first, last, center;   /* center: 0 disables both mean-centrings (Denoiser(mean_center=False)) */
+    unsigned long long seed, step;
+} jamun_walk_params;
+
+int jamun_walk_step(float* y, float* v, float* ybar, float* p, const float* g, const float* score_in,
+                    const int* chain_ptr, int G, const jamun_walk_params* prm, const float* noise, float* xhat, float* score,
+                    float* traj_y, float* traj_xhat, float* traj_score, jamun_stream_t stream);
+
+/* out = a*x + b*noise with noise = given or Philox (initial y = x + sigma*eps, v0 = sqrt(u)*eps;
+ * utils/sampling_wrapper.py:21-24, functional/_splitting.py:11-23). */
+/* ABOBA pieces (functional/_splitting.py:44-109): drift y += (delta/2) v; and, given the score at the half
+ * step, psi = beta*clip(score); v += u (delta/2) psi; v = a v + z sqrt(u) R; v += (delta/2) psi; y += (delta/2) v. */
+int jamun_aboba_drift(float* y, const float* v, float half_delta, int n_atoms, jamun_stream_t stream);
+int jamun_aboba_kick(float* y, float* v, const float* score, const jamun_walk_params* prm, const float* noise,
+                     int n_atoms, jamun_stream_t stream);
+
+int jamun_gaussian_axpy(const float* x, float a, float b, const float* noise, unsigned long long seed,
+                        unsigned long long step, int n_atoms, float* out, jamun_stream_t stream);
+
+/* e3nn layout <-> SoA layout for `s x0e + v x1e` rows. */
+int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);
+int jamun_layout_from_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

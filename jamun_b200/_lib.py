@@ -1,0 +1,75 @@
+"""ctypes binding of the jamun_b200 C ABI (include/jamun_b200.h).
+
+The product has no CPU fallback: if the CUDA library is absent and cannot be built, importing any
+compute op raises.  The library is built in-tree by jamun_b200/csrc/build.py (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "csrc" / "libjamun_b200.so"
+_lib = None
+
+c_f = C.c_void_p  # device pointers travel as integers
+I, F, ULL = C.c_int, C.c_float, C.c_ulonglong
+
+
+class WalkParams(C.Structure):
+    _fields_ = [("c_in", F), ("c_skip", F), ("c_out", F), ("sigma2", F),
+                ("delta", F), ("u", F), ("a", F), ("z_sqrt_u", F), ("beta", F), ("clip", F),
+                ("first", I), ("last", I), ("center", I), ("seed", ULL), ("step", ULL)]
+
+
+_PROTOS = {
+    "jamun_abi_version": ([], I),
+    "jamun_last_error": ([], C.c_char_p),
+    "jamun_noise_mlp": ([c_f, c_f, c_f, c_f, F, I, I, c_f, c_f], I),
+    "jamun_atom_embed": ([c_f] * 8 + [I] * 4 + [c_f, I, c_f, c_f], I),
+    "jamun_center_scale": ([c_f, c_f, I, I, F, c_f, c_f, c_f], I),
+    "jamun_radius_csr": ([c_f, c_f, c_f, I, F, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_edge_geom": ([c_f, c_f, c_f, c_f, I, I, c_f, F, c_f, c_f, c_f], I),
+    "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
+    "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
+    "jamun_block_tail": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
+    "jamun_head": ([c_f, c_f, c_f, c_f, F, I, c_f, c_f], I),
+    "jamun_walk_step": ([c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, C.POINTER(WalkParams), c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_aboba_drift": ([c_f, c_f, F, I, c_f], I),
+    "jamun_aboba_kick": ([c_f, c_f, c_f, C.POINTER(WalkParams), c_f, I, c_f], I),
+    "jamun_gaussian_axpy": ([c_f, F, F, c_f, ULL, ULL, I, c_f, c_f], I),
+    "jamun_layout_to_soa": ([c_f, I, I, I, c_f, c_f], I),
+    "jamun_layout_from_soa": ([c_f, I, I, I, c_f, c_f], I),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the .so is missing and nvcc is available).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        from .csrc import build as _build  # noqa: WPS433
+
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover - environment dependent
+            raise RuntimeError(
+                f"jamun_b200: CUDA library {LIB_PATH} is missing and could not be built ({exc}). "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback."
+            ) from exc
+    handle = C.CDLL(str(LIB_PATH))
+    for name, (argtypes, restype) in _PROTOS.items():
+        fn = getattr(handle, name)  # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().jamun_last_error().decode()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,84 @@
+// Shared helpers for the jamun_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/jamun_b200.h"
+
+namespace jb {
+
+void set_error(const char* fmt, ...);
+
+inline cudaStream_t as_stream(jamun_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define JB_CHECK_ARG(cond, msg)                          \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            jb::set_error("%s: %s", __func__, msg);      \
+            return JAMUN_EINVAL;                         \
+        }                                                \
+    } while (0)
+
+#define JB_CHECK_LAUNCH()                                                        \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            jb::set_error("%s: CUDA error %s", __func__, cudaGetErrorString(e__)); \
+            return JAMUN_ECUDA;                                                  \
+        }                                                                        \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_acc(float x) { return x / (1.0f + expf(-x)); }
+
+// Philox4x32-10 (Salmon et al. 2011); key = seed, counter = (index, step).
+struct Philox {
+    static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+    __device__ static inline uint4 round(uint4 c, uint2 k) {
+        uint32_t hi0 = __umulhi(kM0, c.x), lo0 = kM0 * c.x;
+        uint32_t hi1 = __umulhi(kM1, c.z), lo1 = kM1 * c.z;
+        return make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    }
+    __device__ static inline uint4 gen(uint64_t seed, uint64_t step, uint64_t index) {
+        uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        uint4 c = make_uint4((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)step, (uint32_t)(step >> 32));
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            c = round(c, k);
+            k.x += kW0;
+            k.y += kW1;
+        }
+        return c;
+    }
+    // three standard normals for atom `index` at `step`
+    __device__ static inline float3 normal3(uint64_t seed, uint64_t step, uint64_t index) {
+        uint4 r = gen(seed, step, index);
+        const float k2p32 = 2.3283064365386963e-10f;  // 2^-32
+        float u0 = ((float)r.x + 0.5f) * k2p32, u1 = ((float)r.y + 0.5f) * k2p32;
+        float u2 = ((float)r.z + 0.5f) * k2p32, u3 = ((float)r.w + 0.5f) * k2p32;
+        u0 = fminf(u0, 0.99999994f);
+        u2 = fminf(u2, 0.99999994f);
+        float ra = sqrtf(-2.0f * logf(1.0f - u0)), rb = sqrtf(-2.0f * logf(1.0f - u2));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * u1, &s0, &c0);
+        sincospif(2.0f * u3, &s1, &c1);
+        (void)s1;
+        return make_float3(ra * c0, ra * s0, rb * c1);
+    }
+};
+
+}  // namespace jb

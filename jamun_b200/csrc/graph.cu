@@ -1,0 +1,307 @@
+// Graph-side kernels: per-chain mean-centre, capped radius graph -> receiver-sorted CSR, edge geometry,
+// radial-MLP hidden layer.  All HBM/latency-bound integer/elementwise work (kernels K0-K2).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace jb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace jb
+
+extern "C" int jamun_abi_version(void) { return 1; }
+extern "C" const char* jamun_last_error(void) { return jb::g_err; }
+
+namespace {
+using namespace jb;
+
+// ---- K0: mean-centre + scale, one warp per chain -------------------------------------------------
+__global__ void center_scale_kernel(const float* __restrict__ y, const int* __restrict__ chain_ptr, int G,
+                                    int center, float c_in, float* __restrict__ ybar, float* __restrict__ p) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= G) return;
+    int lo = chain_ptr[warp], hi = chain_ptr[warp + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = lo + lane; i < hi; i += 32) {
+        sx += y[3 * i];
+        sy += y[3 * i + 1];
+        sz += y[3 * i + 2];
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    float inv = 1.0f / fmaxf(1.0f, (float)(hi - lo));
+    float mx = center ? sx * inv : 0.f, my = center ? sy * inv : 0.f, mz = center ? sz * inv : 0.f;
+    for (int i = lo + lane; i < hi; i += 32) {
+        float bx = y[3 * i] - mx, by = y[3 * i + 1] - my, bz = y[3 * i + 2] - mz;
+        if (ybar) {
+            ybar[3 * i] = bx;
+            ybar[3 * i + 1] = by;
+            ybar[3 * i + 2] = bz;
+        }
+        if (p) {
+            p[3 * i] = bx * c_in;
+            p[3 * i + 1] = by * c_in;
+            p[3 * i + 2] = bz * c_in;
+        }
+    }
+}
+
+// ---- K1: radius graph.  One thread per receiver scans its chain in ascending index. ------------------
+// Distance in unfused fp32 (x,y,z order) so that edge sets are bit-reproducible against the oracle.
+__device__ __forceinline__ bool in_range(const float* __restrict__ pos, float xi, float yi, float zi, int j, float r2) {
+    float dx = __fsub_rn(xi, pos[3 * j]), dy = __fsub_rn(yi, pos[3 * j + 1]), dz = __fsub_rn(zi, pos[3 * j + 2]);
+    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return d2 < r2;
+}
+
+template <bool FILL>
+__global__ void radius_kernel(const float* __restrict__ pos, const int* __restrict__ chain_of,
+                              const int* __restrict__ chain_ptr, int N, float r2, int max_hits,
+                              const int* __restrict__ bond_rowptr, const int* __restrict__ bond_src,
+                              int* __restrict__ count, const int* __restrict__ rowptr, int* __restrict__ col,
+                              int* __restrict__ edst, unsigned char* __restrict__ ebond) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c = chain_of[i];
+    int lo = chain_ptr[c], hi = chain_ptr[c + 1];
+    float xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+    int hits = 0, n = 0;
+    int w = FILL ? rowptr[i] : 0;
+    for (int j = lo; j < hi; ++j) {
+        if (in_range(pos, xi, yi, zi, j, r2)) {
+            if (j != i) {
+                if (FILL) {
+                    col[w + n] = j;
+                    edst[w + n] = i;
+                    ebond[w + n] = 0;
+                }
+                ++n;
+            }
+            ++hits;
+            if (max_hits > 0 && hits >= max_hits) break;
+        }
+    }
+    int b0 = bond_rowptr ? bond_rowptr[i] : 0, b1 = bond_rowptr ? bond_rowptr[i + 1] : 0;
+    if (FILL) {
+        for (int b = b0; b < b1; ++b) {
+            col[w + n] = bond_src[b];
+            edst[w + n] = i;
+            ebond[w + n] = 1;
+            ++n;
+        }
+    } else {
+        count[i] = n + (b1 - b0);
+    }
+}
+
+// single-CTA exclusive scan; out[n] = total.  n <= a few 1e5, off the critical path.
+__global__ void exclusive_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
+    __shared__ int warp_tot[32];
+    __shared__ int warp_excl[32];
+    __shared__ int block_total;
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    constexpr int PER = 4;
+    for (int base = 0; base < n; base += blockDim.x * PER) {
+        int idx = base + tid * PER;
+        int v[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            v[k] = (idx + k < n) ? in[idx + k] : 0;
+            s += v[k];
+        }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int t = (lane < nwarps) ? warp_tot[lane] : 0;
+            int ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int q = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += q;
+            }
+            warp_excl[lane] = ti - t;
+            if (lane == 31) block_total = ti;
+        }
+        __syncthreads();
+        int excl = carry_s + warp_excl[wid] + incl - s;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            if (idx + k < n) out[idx + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 0) carry_s += block_total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry_s;
+}
+
+// ---- K2a: edge geometry.  One warp per 1 edge-slot group: lane = radial basis index. ----------------
+__global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restrict__ rowptr,
+                                 const int* __restrict__ col, const int* __restrict__ edst, int N,
+                                 const float* __restrict__ mu, float step, float* __restrict__ rhat,
+                                 float* __restrict__ rb) {
+    const int E = rowptr[N];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const float mu_k = mu[lane];
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < E; e += warps) {
+        int j = col[e], i = edst[e];
+        float dx = p[3 * j] - p[3 * i], dy = p[3 * j + 1] - p[3 * i + 1], dz = p[3 * j + 2] - p[3 * i + 2];
+        float d = sqrtf(dx * dx + dy * dy + dz * dz);
+        float inv = 1.0f / fmaxf(d, 1e-12f);
+        if (lane < 4) {
+            float v = lane == 0 ? dx * inv : lane == 1 ? dy * inv : lane == 2 ? dz * inv : d;
+            rhat[4 * (size_t)e + lane] = v;
+        }
+        float t = (d - mu_k) / step;
+        rb[(size_t)e * JAMUN_NBASIS + lane] = expf(-(t * t)) / 1.12f;
+    }
+}
+
+// ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0r[o][k] rb[e][k] + b0eff[flag][o]) --------
+__global__ void __launch_bounds__(256) edge_radial_hidden_kernel(const float* __restrict__ rb,
+                                                                 const unsigned char* __restrict__ ebond,
+                                                                 const int* __restrict__ rowptr, int N,
+                                                                 const float* __restrict__ w0r,
+                                                                 const float* __restrict__ b0eff,
+                                                                 float* __restrict__ h) {
+    __shared__ float w_s[JAMUN_EDGE_HID][JAMUN_NBASIS + 1];
+    __shared__ float b_s[2][JAMUN_EDGE_HID];
+    __shared__ float rb_s[4][JAMUN_NBASIS];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < JAMUN_EDGE_HID * JAMUN_NBASIS; t += 256) w_s[t / JAMUN_NBASIS][t % JAMUN_NBASIS] = w0r[t];
+    if (tid < 2 * JAMUN_EDGE_HID) b_s[tid / JAMUN_EDGE_HID][tid % JAMUN_EDGE_HID] = b0eff[tid];
+    const int E = rowptr[N];
+    const int o = tid & 63, sub = tid >> 6;
+    for (int e0 = blockIdx.x * 4; e0 < E; e0 += gridDim.x * 4) {
+        __syncthreads();
+        if (tid < 4 * JAMUN_NBASIS) {
+            int e = e0 + tid / JAMUN_NBASIS;
+            rb_s[tid / JAMUN_NBASIS][tid % JAMUN_NBASIS] = e < E ? rb[(size_t)e * JAMUN_NBASIS + tid % JAMUN_NBASIS] : 0.f;
+        }
+        __syncthreads();
+        int e = e0 + sub;
+        if (e < E) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < JAMUN_NBASIS; ++k) acc = fmaf(w_s[o][k], rb_s[sub][k], acc);
+            acc += b_s[ebond[e] ? 1 : 0][o];
+            h[(size_t)e * JAMUN_EDGE_HID + o] = siluf_acc(acc);
+        }
+    }
+}
+
+// ---- layout conversion ---------------------------------------------------------------------------------
+template <bool TO_SOA>
+__global__ void layout_kernel(const float* __restrict__ in, int s, int v, int N, float* __restrict__ out) {
+    const int D = s + 3 * v;
+    size_t total = (size_t)N * D;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        int n = (int)(t / D), k = (int)(t % D);
+        int k2 = k;
+        if (k >= s) {
+            int q = k - s;
+            if (TO_SOA) {  // t indexes the SoA output: q = c*v + u  <- e3nn index u*3 + c
+                int c = q / v, u = q % v;
+                k2 = s + u * 3 + c;
+            } else {  // t indexes the e3nn output: q = u*3 + c <- SoA c*v + u
+                int u = q / 3, c = q % 3;
+                k2 = s + c * v + u;
+            }
+        }
+        out[t] = in[(size_t)n * D + k2];
+    }
+}
+
+}  // namespace
+
+extern "C" int jamun_center_scale(const float* y, const int* chain_ptr, int G, int center, float c_in, float* ybar, float* p,
+                                  jamun_stream_t stream) {
+    JB_CHECK_ARG(y && chain_ptr && G >= 0, "null argument");
+    if (G == 0) return JAMUN_OK;
+    int blocks = (G * 32 + 255) / 256;
+    center_scale_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(y, chain_ptr, G, center, c_in, ybar, p);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_radius_csr(const float* pos, const int* chain_of, const int* chain_ptr, int N, float r2,
+                                int max_num_neighbors, const int* bond_rowptr, const int* bond_src, int* scratch,
+                                int* rowptr, int* col, int* edst, unsigned char* ebond, jamun_stream_t stream) {
+    JB_CHECK_ARG(pos && chain_of && chain_ptr && scratch && rowptr && col && edst && ebond, "null argument");
+    JB_CHECK_ARG(N >= 0, "negative N");
+    cudaStream_t s = jb::as_stream(stream);
+    int max_hits = max_num_neighbors < 0 ? 0 : max_num_neighbors + 1;
+    int blocks = (N + 127) / 128;
+    if (N > 0) {
+        radius_kernel<false><<<blocks, 128, 0, s>>>(pos, chain_of, chain_ptr, N, r2, max_hits, bond_rowptr, bond_src,
+                                                    scratch, nullptr, nullptr, nullptr, nullptr);
+        JB_CHECK_LAUNCH();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(scratch, rowptr, N);
+    JB_CHECK_LAUNCH();
+    if (N > 0) {
+        radius_kernel<true><<<blocks, 128, 0, s>>>(pos, chain_of, chain_ptr, N, r2, max_hits, bond_rowptr, bond_src,
+                                                   nullptr, rowptr, col, edst, ebond);
+        JB_CHECK_LAUNCH();
+    }
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_edge_geom(const float* p, const int* rowptr, const int* col, const int* edst, int N, int cap,
+                               const float* mu, float step, float* rhat, float* rb, jamun_stream_t stream) {
+    JB_CHECK_ARG(p && rowptr && col && edst && mu && rhat && rb, "null argument");
+    if (N == 0 || cap == 0) return JAMUN_OK;
+    long long warps = cap;
+    int blocks = (int)((warps * 32 + 255) / 256);
+    int max_blocks = jb::kNumSMs * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    edge_geom_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(p, rowptr, col, edst, N, mu, step, rhat, rb);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_edge_radial_hidden(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                                        const float* w0r, const float* b0eff, float* h, jamun_stream_t stream) {
+    JB_CHECK_ARG(rb && ebond && rowptr && w0r && b0eff && h, "null argument");
+    if (N == 0 || cap == 0) return JAMUN_OK;
+    int blocks = (cap + 3) / 4;
+    int max_blocks = jb::kNumSMs * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    edge_radial_hidden_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream) {
+    JB_CHECK_ARG(in && out && s >= 0 && v >= 0, "bad argument");
+    if (N == 0) return JAMUN_OK;
+    layout_kernel<true><<<jb::kNumSMs * 4, 256, 0, jb::as_stream(stream)>>>(in, s, v, N, out);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_layout_from_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream) {
+    JB_CHECK_ARG(in && out && s >= 0 && v >= 0, "bad argument");
+    if (N == 0) return JAMUN_OK;
+    layout_kernel<false><<<jb::kNumSMs * 4, 256, 0, jb::as_stream(stream)>>>(in, s, v, N, out);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}

@@ -1,0 +1,181 @@
+"""Device-side execution plan of the denoiser: topology constants, packed weights, workspaces and the
+kernel sequence of one E3Conv evaluation (arch/e3conv.py:110-138 of the reference).
+
+Nothing here computes on the host: tensors are device buffers handed to the C ABI (jamun_b200.ops).
+torch is used for allocation, one-off weight re-layout (indexing/concatenation when a plan is built)
+and stream plumbing only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .irreps import Irreps
+
+
+class Topology:
+    """Per-template constants resident in HBM: chain layout, bonded CSR by receiver, atom indices, and the
+    edge workspaces sized for the worst case so that no kernel ever needs a host-side edge count."""
+
+    def __init__(self, batch, device, max_num_neighbors: Optional[int] = 32):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("jamun_b200 runs on CUDA devices only (no CPU fallback)")
+        bvec = batch["batch"] if "batch" in batch else torch.zeros(batch.num_nodes, dtype=torch.long)
+        bvec = bvec.detach().to("cpu", torch.long)
+        N = int(bvec.numel())
+        G = int(bvec.max().item()) + 1 if N else 0
+        if N and not bool((bvec[1:] >= bvec[:-1]).all()):
+            raise ValueError("batch vector must be sorted (PyG Batch layout)")
+        counts = torch.bincount(bvec, minlength=G)
+        ptr = torch.zeros(G + 1, dtype=torch.long)
+        ptr[1:] = torch.cumsum(counts, 0)
+        self.N, self.G = N, G
+        self.device = dev
+        self.max_num_neighbors = max_num_neighbors
+        self.chain_ptr = ptr.to(dev, torch.int32)
+        self.chain_ptr_long = ptr.to(dev)
+        self.chain_of = bvec.to(dev, torch.int32)
+        self.batch_long = bvec.to(dev)
+        ei = batch["edge_index"].detach().to("cpu", torch.long) if "edge_index" in batch else torch.zeros(2, 0, dtype=torch.long)
+        order = torch.sort(ei[1], stable=True).indices  # receiver-major, original order within a receiver
+        self.bond_src = ei[0][order].to(dev, torch.int32).contiguous()
+        brow = torch.zeros(N + 1, dtype=torch.long)
+        brow[1:] = torch.cumsum(torch.bincount(ei[1], minlength=N), 0)
+        self.bond_rowptr = brow.to(dev, torch.int32)
+        self.num_bonded = int(ei.shape[1])
+        if self.bond_src.numel() == 0:
+            self.bond_src = torch.zeros(1, dtype=torch.int32, device=dev)
+        if max_num_neighbors is None:
+            cap = int((counts * (counts - 1)).sum().item()) + self.num_bonded
+        else:
+            per = torch.minimum(counts - 1, torch.full_like(counts, max_num_neighbors + 1)).clamp_min(0)
+            cap = int((counts * per).sum().item()) + self.num_bonded
+        self.cap = max(cap, 1)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.idx = []
+        for key in ("atom_type_index", "atom_code_index", "residue_code_index", "residue_sequence_index"):
+            self.idx.append(batch[key].detach().to(dev, torch.int32).contiguous() if key in batch else None)
+        # CSR + edge workspaces
+        self.rowptr = torch.zeros(N + 1, **i32)
+        self.scratch = torch.zeros(N + 1, **i32)
+        self.col = torch.zeros(self.cap, **i32)
+        self.edst = torch.zeros(self.cap, **i32)
+        self.ebond = torch.zeros(self.cap, dtype=torch.uint8, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.rhat = torch.zeros(self.cap, 4, **f32)
+        self.rb = torch.zeros(self.cap, ops.NBASIS, **f32)
+        self.h = torch.zeros(self.cap, ops.EDGE_HID, **f32)
+        # node workspaces
+        self.x0 = torch.zeros(N, ops.S0, **f32)
+        self.xa = [torch.zeros(N, ops.HID, **f32) for _ in range(2)]  # node_attr ping-pong
+        self.xs = [torch.zeros(N, ops.HID, **f32) for _ in range(2)]  # scaled node_attr ping-pong
+        self.conv = torch.zeros(N, ops.GATE_IN, **f32)
+        self.x0_key = None
+
+    def build_csr(self, pos: torch.Tensor, r_cut: float):
+        """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
+        r2 = float(torch.tensor(float(r_cut) * float(r_cut), dtype=torch.float64).to(torch.float32))
+        mnn = -1 if self.max_num_neighbors is None else int(self.max_num_neighbors)
+        ops.radius_csr(pos, self.chain_of, self.chain_ptr, r2, mnn, self.bond_rowptr, self.bond_src, self.scratch,
+                       self.rowptr, self.col, self.edst, self.ebond)
+
+    def set_csr_from_edge_index(self, edge_index: torch.Tensor, bond_mask: torch.Tensor):
+        """Compatibility path for callers that hand E3Conv.forward an explicit edge list."""
+        ei = edge_index.to(self.device, torch.long)
+        E = ei.shape[1]
+        if E > self.cap:
+            raise ValueError(f"{E} edges exceed the workspace capacity {self.cap}")
+        order = torch.sort(ei[1], stable=True).indices
+        self.col[:E] = ei[0][order].to(torch.int32)
+        self.edst[:E] = ei[1][order].to(torch.int32)
+        self.ebond[:E] = bond_mask.to(self.device)[order].to(torch.uint8)
+        rp = torch.zeros(self.N + 1, dtype=torch.long, device=self.device)
+        rp[1:] = torch.cumsum(torch.bincount(ei[1], minlength=self.N), 0)
+        self.rowptr.copy_(rp.to(torch.int32))
+
+    def edge_index(self):
+        """Materialise (edge_index [2,E] int64, bond_mask [E] int64) from the CSR -- host sync; tests/API only."""
+        E = int(self.rowptr[-1].item())
+        ei = torch.stack([self.col[:E].long(), self.edst[:E].long()])
+        return ei, self.ebond[:E].long()
+
+
+class E3ConvPlan:
+    """Kernel operands of one E3Conv module at one noise level (c_noise)."""
+
+    def __init__(self, g, c_noise: float, device):
+        from .e3tools.nn import ConvBlock, EquivariantMLP
+        from .model.atom_embedding import AtomEmbeddingWithResidueInformation
+
+        dev = torch.device(device)
+        if Irreps(g.irreps_sh) != Irreps("1x0e+1x1e") or Irreps(g.irreps_out) != Irreps("1x1e") \
+                or g.edge_attr_dim != 2 * ops.NBASIS:
+            raise NotImplementedError("B200 kernels are built for irreps_sh=1x0e+1x1e, irreps_out=1x1e, edge_attr_dim=64")
+        if not isinstance(g.atom_embedder, AtomEmbeddingWithResidueInformation):
+            raise NotImplementedError("use_residue_information=False is outside the kernels' scope")
+        blocks = [g.initial_projector, *g.layers]
+        if not all(isinstance(b, ConvBlock) for b in blocks) or not isinstance(g.output_head, EquivariantMLP) \
+                or len(g.output_head) != 2:
+            raise NotImplementedError("hidden_layer_factory must be ConvBlock and output_head_factory EquivariantMLP([hidden])")
+        self.c_noise = float(c_noise)
+        self.device = dev
+        with torch.no_grad():
+            emb = g.embed_bondedness.weight.detach().to(dev, torch.float32)
+            self.tables = [t.detach().to(dev, torch.float32).contiguous() for t in g.atom_embedder.tables()]
+            if sum(t.shape[1] for t in self.tables) != ops.S0:
+                raise NotImplementedError("atom embedding width must be 56")
+            self.use_residue_sequence_index = g.atom_embedder.use_residue_sequence_index
+            self.blocks: List[Dict] = []
+            for b in blocks:
+                pk = b.pack(emb)
+                self.blocks.append({k: (v.detach().to(dev, torch.float32).contiguous() if isinstance(v, torch.Tensor) else v)
+                                    for k, v in pk.items()})
+            f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+            self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
+            self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
+            self.skips = [ops.noise_mlp(*map(f32, m.weights.mlp_operands()), self.c_noise, True) for m in g.skip_connections]
+            blk, lin2 = g.output_head[0], g.output_head[1]
+            self.head_w1s = f32(blk.lin.packed(0))
+            self.head_w1v = f32(blk.lin.packed(1))
+            self.head_cgate = blk.gate.c_gate
+            self.head_w2 = f32(lin2.packed(1).reshape(-1) * g.output_gain.detach())
+        self.n_basis = ops.NBASIS
+
+    def radial_grid(self, r_cut: float):
+        """soft_one_hot_linspace(..., cutoff=True) grid: centres linspace(0, r, n+2)[1:-1] and their spacing."""
+        values = torch.linspace(0.0, float(r_cut), self.n_basis + 2, dtype=torch.float32)
+        step = float(values[1] - values[0])
+        return values[1:-1].to(self.device).contiguous(), step
+
+
+def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,
+                   mu: Optional[torch.Tensor] = None, step: Optional[float] = None) -> torch.Tensor:
+    """One evaluation of the network on scaled positions p over topo's current CSR -> g_out [N,3]."""
+    if mu is None:
+        mu, step = plan.radial_grid(r_cut)
+    ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
+    key = (id(plan),)
+    if topo.x0_key != key:  # constant per (topology, plan): embedding x initial noise scaling
+        idx = list(topo.idx)
+        if not plan.use_residue_sequence_index:
+            idx[3] = None
+        ops.atom_embed(idx, plan.tables, plan.s_init, topo.x0)
+        topo.x0_key = key
+    x_in, x_res = topo.x0, None
+    nb = len(plan.blocks)
+    for l, b in enumerate(plan.blocks):
+        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
+                     b["alpha0"], b["alpha1"], topo.conv)
+        x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
+        skip_w = plan.skips[l - 1] if l > 0 else None
+        s_next = plan.scales[l] if l < nb - 1 else None
+        ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"],
+                       b["wskip_v"], skip_w, s_next, b["c_act"], b["c_gate"], x_new, x_scaled if l < nb - 1 else None)
+        x_in, x_res = x_scaled, x_new
+    ops.head(x_res, plan.head_w1s, plan.head_w1v, plan.head_w2, plan.head_cgate, g_out)
+    return g_out

@@ -1,0 +1,179 @@
+"""Torch-tensor front end of the C ABI: argument checking, stream plumbing, nothing else.
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream (so the calls
+are CUDA-graph capturable) and returns torch tensors that alias caller-owned or freshly allocated
+device memory.  CPU tensors are rejected: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+S, V, HID, GATE_IN, S0, EDGE_HID, NBASIS = 120, 32, 216, 248, 56, 64, 32
+
+LAUNCHES = 0  # number of kernel launches issued through this module (bench.py's gpu_launches claim)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("jamun_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def noise_mlp(w1, b1, w2, b2, c_noise: float, apply_sigmoid: bool, out=None):
+    n = b1.numel()
+    out = torch.empty(n, device=b1.device, dtype=torch.float32) if out is None else out
+    rc = _lib.lib().jamun_noise_mlp(_ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), float(c_noise), n, int(apply_sigmoid),
+                                    _ptr(out), _stream())
+    _lib.check(rc, "jamun_noise_mlp")
+    _count()
+    return out
+
+
+def atom_embed(idx, tabs, scale, out=None):
+    N = idx[0].numel()
+    dims = [t.shape[1] for t in tabs]
+    out = torch.empty(N, sum(dims), device=tabs[0].device, dtype=torch.float32) if out is None else out
+    i32 = torch.int32
+    rc = _lib.lib().jamun_atom_embed(_ptr(idx[0], i32), _ptr(idx[1], i32), _ptr(idx[2], i32),
+                                     _ptr(idx[3], i32) if idx[3] is not None else None,
+                                     _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), *dims,
+                                     _ptr(scale), N, _ptr(out), _stream())
+    _lib.check(rc, "jamun_atom_embed")
+    _count()
+    return out
+
+
+def center_scale(y, chain_ptr, c_in: float, ybar=None, p=None, center: bool = True):
+    G = chain_ptr.numel() - 1
+    ybar = torch.empty_like(y) if ybar is None else ybar
+    p = torch.empty_like(y) if p is None else p
+    rc = _lib.lib().jamun_center_scale(_ptr(y), _ptr(chain_ptr, torch.int32), G, int(center), float(c_in), _ptr(ybar), _ptr(p),
+                                       _stream())
+    _lib.check(rc, "jamun_center_scale")
+    _count()
+    return ybar, p
+
+
+def radius_csr(pos, chain_of, chain_ptr, r2: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch, rowptr,
+               col, edst, ebond):
+    N = pos.shape[0]
+    i32 = torch.int32
+    rc = _lib.lib().jamun_radius_csr(_ptr(pos), _ptr(chain_of, i32), _ptr(chain_ptr, i32), N, float(r2),
+                                     int(max_num_neighbors), _ptr(bond_rowptr, i32), _ptr(bond_src, i32),
+                                     _ptr(scratch, i32), _ptr(rowptr, i32), _ptr(col, i32), _ptr(edst, i32),
+                                     _ptr(ebond, torch.uint8), _stream())
+    _lib.check(rc, "jamun_radius_csr")
+    _count(3)
+
+
+def edge_geom(p, rowptr, col, edst, mu, step: float, rhat, rb):
+    N, cap = p.shape[0], col.numel()
+    i32 = torch.int32
+    rc = _lib.lib().jamun_edge_geom(_ptr(p), _ptr(rowptr, i32), _ptr(col, i32), _ptr(edst, i32), N, cap, _ptr(mu),
+                                    float(step), _ptr(rhat), _ptr(rb), _stream())
+    _lib.check(rc, "jamun_edge_geom")
+    _count()
+
+
+def edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h):
+    N, cap = rowptr.numel() - 1, ebond.numel()
+    rc = _lib.lib().jamun_edge_radial_hidden(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap,
+                                             _ptr(w0r), _ptr(b0eff), _ptr(h), _stream())
+    _lib.check(rc, "jamun_edge_radial_hidden")
+    _count()
+
+
+def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: float, alpha1: float, out):
+    N = x.shape[0]
+    assert x.shape[1] == s_in + 3 * v_in and out.shape == (N, GATE_IN)
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_fwd(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat),
+                                   _ptr(m0), _ptr(m1), float(alpha0), float(alpha1), N, _ptr(out), _stream())
+    _lib.check(rc, "jamun_conv_fwd")
+    _count()
+    return out
+
+
+def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
+               c_act: float, c_gate: float, x_new, x_scaled):
+    N = conv.shape[0]
+    rc = _lib.lib().jamun_block_tail(_ptr(conv), _ptr(x_in), s_in, v_in, _ptr(x_res), _ptr(wself_s), _ptr(wself_v),
+                                     _ptr(wskip_s), _ptr(wskip_v), _ptr(skip_w), _ptr(s_next), float(c_act),
+                                     float(c_gate), N, _ptr(x_new), _ptr(x_scaled), _stream())
+    _lib.check(rc, "jamun_block_tail")
+    _count()
+
+
+def head(x, w1_s, w1_v, w2, c_gate: float, g):
+    rc = _lib.lib().jamun_head(_ptr(x), _ptr(w1_s), _ptr(w1_v), _ptr(w2), float(c_gate), x.shape[0], _ptr(g), _stream())
+    _lib.check(rc, "jamun_head")
+    _count()
+    return g
+
+
+def walk_step(y, v, ybar, p, g, chain_ptr, prm: "_lib.WalkParams", noise, xhat, score, traj_y=None, traj_xhat=None,
+              traj_score=None, score_in=None):
+    G = chain_ptr.numel() - 1
+    rc = _lib.lib().jamun_walk_step(_ptr(y), _ptr(v), _ptr(ybar), _ptr(p), _ptr(g), _ptr(score_in),
+                                    _ptr(chain_ptr, torch.int32), G,
+                                    C.byref(prm), _ptr(noise), _ptr(xhat), _ptr(score), _ptr(traj_y), _ptr(traj_xhat),
+                                    _ptr(traj_score), _stream())
+    _lib.check(rc, "jamun_walk_step")
+    _count()
+
+
+def aboba_drift(y, v, half_delta: float):
+    rc = _lib.lib().jamun_aboba_drift(_ptr(y), _ptr(v), float(half_delta), y.shape[0], _stream())
+    _lib.check(rc, "jamun_aboba_drift")
+    _count()
+
+
+def aboba_kick(y, v, score, prm: "_lib.WalkParams", noise):
+    rc = _lib.lib().jamun_aboba_kick(_ptr(y), _ptr(v), _ptr(score), C.byref(prm), _ptr(noise), y.shape[0], _stream())
+    _lib.check(rc, "jamun_aboba_kick")
+    _count()
+
+
+def gaussian_axpy(x, a: float, b: float, noise, seed: int, step: int, out):
+    n_atoms = out.shape[0]
+    rc = _lib.lib().jamun_gaussian_axpy(_ptr(x), float(a), float(b), _ptr(noise), int(seed), int(step), n_atoms,
+                                        _ptr(out), _stream())
+    _lib.check(rc, "jamun_gaussian_axpy")
+    _count()
+    return out
+
+
+def layout_to_soa(x, s: int, v: int):
+    out = torch.empty_like(x)
+    rc = _lib.lib().jamun_layout_to_soa(_ptr(x), s, v, x.shape[0], _ptr(out), _stream())
+    _lib.check(rc, "jamun_layout_to_soa")
+    _count()
+    return out
+
+
+def layout_from_soa(x, s: int, v: int):
+    out = torch.empty_like(x)
+    rc = _lib.lib().jamun_layout_from_soa(_ptr(x), s, v, x.shape[0], _ptr(out), _stream())
+    _lib.check(rc, "jamun_layout_from_soa")
+    _count()
+    return out

@@ -322,7 +322,9 @@ class FullyConnectedTP(nn.Module):
             b = x2[:, s2[i2]].reshape(Z, m2, 2 * l2 + 1)
             c = wigner_3j(l1, l2, lo, dtype=x1.dtype)
             coeff = math.sqrt((2 * lo + 1) / fan[io])
-            y = torch.einsum("zuvw,ijk,zui,zvj->zwk", w, c, a, b) * coeff
+            # two-step contraction (what e3nn's optimised einsum does): t = (a (x) b) . w3j, then the uvw mixing as a bmm
+            t = torch.einsum("ijk,zui,zvj->zuvk", c, a, b).reshape(Z, m1 * m2, 2 * lo + 1)
+            y = torch.bmm(w.reshape(Z, m1 * m2, mo).transpose(1, 2), t) * coeff
             outs[io] = y if outs[io] is None else outs[io] + y
         cols = []
         for io, (mo, lo, _) in enumerate(self.irreps_out):

@@ -1,0 +1,283 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (jamun_b200.ops -> libjamun_b200.so) against the oracle."""
+import math
+
+import pytest
+import torch
+
+import kernel_model as KM
+from conftest import make_oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+SIGMA = 0.04
+
+
+def _setup(models, sizes, seed=0, dtype=torch.float32):
+    import jamun_b200 as J
+    from jamun_b200 import synthetic
+    from oracle import jamun_oracle as O
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors(sizes)
+    gen = torch.Generator().manual_seed(seed)
+    y = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=gen)
+    return o32, o64, prod, t, y
+
+
+def test_library_loaded():
+    from jamun_b200 import _lib
+
+    assert _lib.lib().jamun_abi_version() == 1
+
+
+@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [1], [2, 1, 57], [40] * 5, [200]])
+def test_center_scale(sizes):
+    from jamun_b200 import engine, ops, synthetic, data
+    from oracle import jamun_oracle as O
+
+    t = synthetic.make_tensors(sizes)
+    y = (t["pos"] + 0.3).cuda()
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    ybar, p = ops.center_scale(y, topo.chain_ptr, 1.7)
+    ref = O.mean_center_pos(y.cpu(), t["batch"], len(sizes))
+    assert torch.allclose(ybar.cpu(), ref, atol=1e-6, rtol=0)
+    assert torch.allclose(p.cpu(), ref * 1.7, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("sizes,cap", [([22, 15, 9, 30], 32), ([60, 57, 3, 1, 2], 32), ([150, 40], 32), ([150, 40], 8),
+                                       ([150, 40], None), ([300], 32)])
+def test_radius_csr_bit_exact(sizes, cap):
+    """Edge sets identical to the oracle's radius_graph + bonded concatenation (compared after sorting), and the
+    within-row order is the documented one (radial ascending, then bonded)."""
+    from jamun_b200 import engine, synthetic, data
+    from oracle import jamun_oracle as O
+
+    t = synthetic.make_tensors(sizes)
+    pos = t["pos"]
+    r = 0.5872642993927002
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda", max_num_neighbors=cap)
+    topo.build_csr(pos.cuda(), r)
+    ei, bm = topo.edge_index()
+    ref_rad = O.radius_graph(pos, r, t["batch"], cap)
+    ref = torch.cat([ref_rad, t["edge_index"]], dim=1)
+    ref_bm = torch.cat([torch.zeros(ref_rad.shape[1], dtype=torch.long), torch.ones(t["edge_index"].shape[1], dtype=torch.long)])
+    assert ei.shape[1] == ref.shape[1]
+    N = pos.shape[0]
+    key = lambda e, m: torch.sort(e[1] * (2 * N) * 2 + e[0] * 2 + m).values  # noqa: E731
+    assert torch.equal(key(ei.cpu(), bm.cpu()), key(ref, ref_bm))
+    # receiver-sorted
+    assert bool((ei[1][1:] >= ei[1][:-1]).all())
+    # stable reorder of the oracle's list by receiver reproduces ours exactly (row order contract)
+    order = torch.sort(ref[1], stable=True).indices
+    assert torch.equal(ei.cpu(), ref[:, order])
+    rowptr = topo.rowptr.cpu().long()
+    assert torch.equal(rowptr[1:] - rowptr[:-1], torch.bincount(ref[1], minlength=N))
+
+
+def test_radius_empty_and_single():
+    from jamun_b200 import engine, synthetic, data
+
+    t = synthetic.make_tensors([1, 1])
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    topo.build_csr(t["pos"].cuda(), 0.5)
+    assert int(topo.rowptr[-1]) == 0
+
+
+def _ref_layers(o64, t, y):
+    """fp64 oracle intermediates for positions y."""
+    from oracle import jamun_oracle as O
+
+    b = make_oracle_batch(t, torch.float64)
+    sig = torch.tensor(SIGMA, dtype=torch.float64)
+    ybar = O.mean_center_pos(y.double(), b.batch, b.num_graphs)
+    c_in, c_skip, c_out, c_noise = o64.normalization_factors(sig, 0.332)
+    r_cut = o64.effective_radial_cutoff(sig) / c_in
+    yg = o64.add_edges(b.with_pos(ybar), r_cut)
+    ys = yg.with_pos(ybar * c_in)
+    g, hidden = o64.g(ys, c_noise.unsqueeze(0), r_cut, return_hidden=True)
+    return dict(ybar=ybar, yg=yg, ys=ys, g=g, hidden=hidden, r_cut=float(r_cut), c_in=float(c_in), c_noise=float(c_noise))
+
+
+@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65]])
+def test_network_layers_vs_oracle(models, sizes):
+    """Every stage of E3Conv against the fp64 oracle: edge features, radial hidden, each block's output, head."""
+    from jamun_b200 import engine, ops, data
+
+    o32, o64, prod, t, y = _setup(models, sizes)
+    ref = _ref_layers(o64, t, y)
+    g = prod.arch_module
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    ctx = prod.sigma_context(SIGMA)
+    assert abs(ctx.r_cut - 0.5872642993927002) < 1e-6
+    plan = g.plan(ctx.c_noise, "cuda")
+    ybar, p = ops.center_scale(y.cuda(), topo.chain_ptr, ctx.c_in)
+    topo.build_csr(ybar, ctx.r_cut)
+    ei, bm = topo.edge_index()
+    # same edge multiset as the oracle at these positions
+    src, dst = ref["yg"].edge_index
+    order = torch.sort(dst, stable=True).indices
+    assert torch.equal(ei.cpu(), torch.stack([src[order], dst[order]]))
+    E = ei.shape[1]
+    mu, step = plan.radial_grid(ctx.r_cut)
+    ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
+    rhat_ref, rb_ref = KM.edge_geom(ref["ys"].pos, src[order], dst[order], ref["r_cut"])
+    assert torch.allclose(topo.rhat[:E, :3].cpu().double(), rhat_ref, atol=2e-6)
+    assert torch.allclose(topo.rb[:E].cpu().double(), rb_ref, atol=2e-6)
+    g_out = torch.empty_like(p)
+    # run block by block, checking node features after each block
+    engine.e3conv_forward(plan, topo, p, ctx.r_cut, g_out)
+    N = p.shape[0]
+    # re-run with per-block inspection
+    x_in, x_res = topo.x0, None
+    nb = len(plan.blocks)
+    for l, b in enumerate(plan.blocks):
+        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"],
+                     b["alpha1"], topo.conv)
+        x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
+        ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"], b["wskip_v"],
+                       plan.skips[l - 1] if l > 0 else None, plan.scales[l] if l < nb - 1 else None, b["c_act"], b["c_gate"],
+                       x_new, x_scaled if l < nb - 1 else None)
+        got = ops.layout_from_soa(x_new, 120, 32).cpu().double()
+        want = ref["hidden"][l]
+        err = (got - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2e-5 * max(1.0, scale), f"block {l}: err {err} scale {scale}"
+        x_in, x_res = x_scaled, x_new
+    err = (g_out.cpu().double() - ref["g"]).abs().max().item()
+    assert err <= 1e-5, f"g err {err}"
+
+
+@pytest.mark.parametrize("sizes", [[22] * 8, [9, 29, 17, 12, 25], [57, 41, 36, 17]])
+def test_xhat_score_parity(models, sizes):
+    """north_star tolerance: denoised coordinates and scores within rtol 1e-4 / atol 1e-5 (fp32), teacher-forced."""
+    from jamun_b200 import data
+    from oracle import jamun_oracle as O
+
+    o32, o64, prod, t, y = _setup(models, sizes, seed=3)
+    batch = data.Batch.from_tensors(t).to("cuda")
+    yb = batch.clone("pos")
+    yb.pos = y.cuda()
+    xhat = prod.xhat(yb, SIGMA).pos.cpu()
+    score = prod.score(yb, SIGMA).cpu()
+    ob = make_oracle_batch(t)
+    with torch.no_grad():
+        xref = o32.xhat(ob.with_pos(y), SIGMA)
+        sref = o32.score(ob.with_pos(y), SIGMA)
+        xref64 = o64.xhat(make_oracle_batch(t, torch.float64).with_pos(y.double()), SIGMA)
+    assert torch.allclose(xhat, xref, rtol=1e-4, atol=1e-5), (xhat - xref).abs().max()
+    assert torch.allclose(xhat.double(), xref64, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(score, sref, rtol=1e-4, atol=1e-5 / SIGMA ** 2), (score - sref).abs().max()
+
+
+def test_output_gain_zero_identity(models):
+    """A freshly initialised model returns mean_center(c_skip * mean_center(y))."""
+    import jamun_b200 as J
+    from jamun_b200 import data, synthetic
+    from oracle import jamun_oracle as O
+
+    torch.manual_seed(1)
+    m = J.default_denoiser().cuda()
+    t = synthetic.make_tensors([22, 9])
+    b = data.Batch.from_tensors(t).to("cuda")
+    x = m.xhat(b, SIGMA).pos.cpu()
+    yb = O.mean_center_pos(t["pos"], t["batch"], 2)
+    c_skip = float(m.sigma_context(SIGMA).c_skip)
+    assert torch.allclose(x, O.mean_center_pos(c_skip * yb, t["batch"], 2), atol=1e-6)
+
+
+def test_equivariance_and_chain_independence(models):
+    from jamun_b200 import data, synthetic
+
+    o32, o64, prod, t, y = _setup(models, [22, 15, 9, 30], seed=5)
+    batch = data.Batch.from_tensors(t).to("cuda")
+
+    def run(pos):
+        yb = batch.clone("pos")
+        yb.pos = pos.cuda().contiguous()
+        return prod.xhat(yb, SIGMA).pos.cpu()
+
+    x = run(y)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(0)))
+    if torch.det(Q) < 0:
+        Q[:, 0] *= -1
+    xr = run(y @ Q.T + torch.tensor([0.3, -0.2, 0.1]))
+    assert torch.allclose(xr, x @ Q.T, atol=2e-5)
+    # perturbing chain 0 leaves the other chains' outputs bit-identical
+    y2 = y.clone()
+    y2[:22] += 0.01
+    x2 = run(y2)
+    assert torch.equal(x2[22:], x[22:])
+
+
+def test_walk_step_matches_oracle_baoab(models):
+    """Fused walk (K1..K6 per step) against the oracle's Python BAOAB with the same supplied noise, saved every step."""
+    from jamun_b200 import data, utils
+    from jamun_b200.sampling.mcmc import BAOAB
+    from jamun_b200.sampling.walkjump import SingleMeasurementSampler
+    from oracle import jamun_oracle as O
+
+    o32, o64, prod, t, y = _setup(models, [22, 15, 9], seed=7)
+    steps = 6
+    gen = torch.Generator().manual_seed(11)
+    noise = torch.randn(steps, y.shape[0], 3, generator=gen)
+    kw = dict(delta=0.04, friction=1.0, M=1.0, inverse_temperature=1.0, score_fn_clip=100.0)
+    it = iter(noise)
+    ob = make_oracle_batch(t)
+    with torch.no_grad():
+        ref = O.walk_jump(o32, ob, y, SIGMA, mcmc=O.baoab, v_init="gaussian", steps=steps, save_trajectory=True,
+                          noise_fn=lambda yy: next(it), **kw)
+    batch = data.Batch.from_tensors(t).to("cuda")
+    wrapped = utils.ModelSamplingWrapper(prod, batch, SIGMA)
+    sampler = SingleMeasurementSampler(BAOAB(steps=steps, save_trajectory=True, **kw), SIGMA)
+    out = sampler.sample(wrapped, y_init=y.cuda(), v_init="gaussian", noise=noise.cuda())
+    for key in ("y", "v", "xhat", "y_traj", "xhat_traj", "score_traj"):
+        got, want = out[key].cpu(), ref[key]
+        assert got.shape == want.shape, key
+        tol = dict(rtol=2e-4, atol=2e-5 if "score" not in key else 2e-5 / SIGMA ** 2)
+        assert torch.allclose(got, want, **tol), (key, (got - want).abs().max())
+    assert out["sample"] is out["xhat"]
+
+
+def test_generic_baoab_and_aboba_protocol():
+    """The reference's mcmc(y, score_fn) protocol with a closed-form score (harmonic well): kernels vs oracle loops."""
+    from jamun_b200.sampling.mcmc import ABOBA, BAOAB
+    from oracle import jamun_oracle as O
+
+    gen = torch.Generator().manual_seed(0)
+    y0 = torch.randn(50, 3, generator=gen)
+    steps = 9
+    noise = torch.randn(steps, 50, 3, generator=gen)
+    score = lambda y: -3.0 * y  # noqa: E731
+    kw = dict(delta=0.1, friction=0.7, M=2.0, inverse_temperature=1.3, score_fn_clip=2.5, steps=steps, save_trajectory=True,
+              save_every_n_steps=2, burn_in_steps=2)
+    for cls, fn in ((BAOAB, O.baoab), (ABOBA, O.aboba)):
+        it = iter(noise)
+        ref = fn(y0, score, v_init="gaussian", noise_fn=lambda yy: next(it), **kw)
+        got = cls(**kw)(y0.cuda(), score, v_init="gaussian", noise=noise.cuda())
+        for a, b in zip(got, ref):
+            assert a.shape == b.shape
+            assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-6), cls
+    with pytest.raises(RuntimeError):
+        BAOAB(v_init="nope")
+
+
+def test_philox_normals_statistics():
+    from jamun_b200 import ops
+
+    out = torch.empty(200_000, 3, device="cuda")
+    ops.gaussian_axpy(None, 0.0, 1.0, None, 1234, 1, out)
+    out2 = torch.empty_like(out)
+    ops.gaussian_axpy(None, 0.0, 1.0, None, 1234, 2, out2)
+    z = out.flatten()
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1) < 0.01
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1
+    assert abs(torch.corrcoef(torch.stack([out.flatten(), out2.flatten()]))[0, 1].item()) < 0.01
+    assert not torch.equal(out, out2)
+
+
+def test_no_cpu_fallback():
+    from jamun_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops.center_scale(torch.zeros(3, 3), torch.tensor([0, 3], dtype=torch.int32), 1.0)
