@@ -110,3 +110,21 @@ class Sampler:
         out = [torch.empty_like(sample) for _ in range(dist.get_world_size())]
         dist.all_gather(out, sample.contiguous())
         return torch.cat(out, dim=0)
+
+    @staticmethod
+    def gather_samples_ragged(sample: torch.Tensor) -> torch.Tensor:
+        """All-gather of per-rank samples with different atom counts (pads to the largest shard)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return sample
+        world = dist.get_world_size()
+        n = torch.tensor([sample.shape[0]], device=sample.device)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        mx = max(int(t) for t in ns)
+        buf = sample.new_zeros((mx,) + tuple(sample.shape[1:]))
+        buf[: sample.shape[0]] = sample
+        outs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf)
+        return torch.cat([o[: int(k)] for o, k in zip(outs, ns)], dim=0)

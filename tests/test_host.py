@@ -1,0 +1,218 @@
+"""CPU suite, part 2: host logic of the product -- weight re-layout, API surface, error conventions, the C-ABI
+library's exported symbols -- with no compute calls (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import kernel_model as KM
+from conftest import ROOT, make_oracle_batch
+from jamun_b200 import synthetic
+from oracle import jamun_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from jamun_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "jamun_b200.h")).read()
+    declared = set(re.findall(r"\b(jamun_[a-z0-9_]+)\s*\(", header))
+    declared -= {"jamun_stream_t"}
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    handle = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert _lib.lib().jamun_abi_version() == 1
+
+
+def test_walk_params_struct_matches_header():
+    from jamun_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "jamun_b200.h")).read()
+    body = header[header.index("typedef struct {"):header.index("} jamun_walk_params;")]
+    names = re.findall(r"\b([a-z_0-9]+)\s*[,;]", body)
+    assert names == [f[0] for f in _lib.WalkParams._fields_]
+
+
+def test_no_cpu_fallback_and_error_conventions():
+    import jamun_b200 as J
+    from jamun_b200 import data, ops
+    from jamun_b200.sampling.mcmc import ABOBA, BAOAB
+
+    with pytest.raises(RuntimeError):
+        ops.center_scale(torch.zeros(3, 3), torch.tensor([0, 3], dtype=torch.int32), 1.0)
+    with pytest.raises(ValueError):
+        J.default_denoiser(add_fixed_noise=True, add_fixed_ones=True)
+    for cls in (BAOAB, ABOBA):
+        with pytest.raises(RuntimeError):
+            cls(v_init="bogus")
+    m = J.default_denoiser()
+    b = data.Batch.from_tensors(synthetic.make_tensors([5, 4]))
+    with pytest.raises(RuntimeError):  # CPU tensors are rejected, never silently computed
+        m.xhat(b, 0.04)
+    with pytest.raises(NotImplementedError):
+        J.e3tools.nn.ConvBlock("10x0e+4x1e", "16x0e+4x1e", "1x0e+1x1e", 64).pack(torch.zeros(2, 32))
+
+
+def test_product_never_imports_oracle():
+    import subprocess
+    import sys
+
+    code = "import sys, jamun_b200, jamun_b200.sampling, jamun_b200.model; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jamun_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_state_dict_matches_reference_layout(models):
+    import jamun_b200 as J
+
+    o32, _, prod = models
+    a = {k: tuple(v.shape) for k, v in o32.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in prod.state_dict().items()}
+    assert a == b
+    compiled = J.default_denoiser(use_torch_compile=True)
+    assert all(k.startswith("g._orig_mod.") for k in compiled.state_dict())
+    compiled.load_state_dict(o32.state_dict())  # g. -> g._orig_mod.
+    sd = dict(compiled.state_dict())
+    sd["g._orig_mod.layers.0.gated_conv.f.f.tp.weight"] = torch.zeros(0)  # e3nn constant buffers are tolerated
+    sd["g._orig_mod.layers.0.gated_conv.f.f.tp.output_mask"] = torch.ones(248)
+    sd["g._orig_mod.layers.0.gated_conv.f.f.tp._compiled_main_left_right._w3j_1_1_1"] = torch.zeros(3, 3, 3)
+    plain = J.default_denoiser(use_torch_compile=False)
+    plain.load_state_dict(sd)
+    assert torch.equal(plain.state_dict()["g.output_head.1.weight"], o32.state_dict()["g.output_head.1.weight"])
+
+
+def test_checkpoint_roundtrip(tmp_path, models):
+    import jamun_b200 as J
+
+    o32 = models[0]
+    m = J.default_denoiser(use_torch_compile=True)
+    m.load_state_dict(o32.state_dict())
+    path = tmp_path / "last.ckpt"
+    torch.save({"state_dict": m.state_dict(), "hyper_parameters": m.hparams}, path)
+    m2 = J.model.Denoiser.load_from_checkpoint(str(path))
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_packed_operands_reproduce_oracle_fp64(models):
+    """Aggregate-then-transform algebra + Conv.pack / Linear.packed re-layout == the reference formulation (fp64)."""
+    import jamun_b200 as J
+
+    o32, o64, _ = models
+    prod = J.default_denoiser()
+    prod.load_state_dict(o32.state_dict())
+    g = prod.double().arch_module
+    t = synthetic.make_tensors([22, 15, 9, 30])
+    b = make_oracle_batch(t, torch.float64)
+    N = b.pos.shape[0]
+    sig = torch.tensor(0.04, dtype=torch.float64)
+    gen = torch.Generator().manual_seed(0)
+    ybar = O.mean_center_pos(b.pos + 0.04 * torch.randn(N, 3, generator=gen, dtype=torch.float64), b.batch, 4)
+    c_in, _, _, c_noise = o64.normalization_factors(sig, 0.332)
+    r_cut = o64.effective_radial_cutoff(sig) / c_in
+    yg = o64.add_edges(b.with_pos(ybar), r_cut)
+    ys = yg.with_pos(ybar * c_in)
+    with torch.no_grad():
+        gref, hidden = o64.g(ys, c_noise.unsqueeze(0), r_cut, return_hidden=True)
+        src, dst = yg.edge_index
+        order = torch.sort(dst, stable=True).indices
+        src, dst, eb = src[order], dst[order], yg.bond_mask[order]
+        rhat, rb = KM.edge_geom(ys.pos, src, dst, r_cut)
+        emb = g.embed_bondedness.weight
+        blocks = [g.initial_projector.pack(emb)] + [l.pack(emb) for l in g.layers]
+        cn = float(c_noise)
+        s_init = KM.noise_mlp(*g.initial_noise_scaling.mlp_operands(), cn, False)
+        scales = [KM.noise_mlp(*mm.mlp_operands(), cn, False) for mm in g.noise_scalings]
+        skips = [KM.noise_mlp(*mm.weights.mlp_operands(), cn, True) for mm in g.skip_connections]
+        x_in, x_res = o64.g.atom_embedder(b) * s_init, None
+        for l, bl in enumerate(blocks):
+            h = KM.radial_hidden(rb, eb, bl["w0r"], bl["b0eff"])
+            co = KM.conv(x_in, bl["s_in"], bl["v_in"], src, dst, h, rhat, bl["m0"], bl["m1"], bl["alpha0"], bl["alpha1"], N)
+            x_new, x_sc = KM.block_tail(co, x_in, bl["s_in"], bl["v_in"], x_res, bl, skips[l - 1] if l > 0 else None,
+                                        scales[l] if l < 5 else None)
+            assert torch.allclose(KM.from_soa(x_new, 120, 32), hidden[l], atol=1e-12), l
+            x_in, x_res = x_sc, x_new
+        hb, lin2 = g.output_head[0], g.output_head[1]
+        gg = KM.head(x_res, hb.lin.packed(0), hb.lin.packed(1), lin2.packed(1).reshape(-1) * g.output_gain, hb.gate.c_gate)
+    assert torch.allclose(gg, gref, atol=1e-13)
+    assert blocks[1]["m0"].shape == (65, 152, 152) and blocks[1]["m1"].shape == (65, 184, 32)
+    assert blocks[0]["m0"].shape == (65, 56, 152) and blocks[0]["m1"].shape == (65, 56, 32)
+
+
+def test_gate_constants_and_irreps():
+    from jamun_b200.e3tools.nn import _gate
+    from jamun_b200.irreps import Irreps
+
+    assert _gate.normalize2mom_const(lambda z: torch.nn.functional.leaky_relu(z, 0.01)) == pytest.approx(_gate.C_LEAKY_RELU, rel=1e-12)
+    assert _gate.normalize2mom_const(torch.sigmoid) == pytest.approx(_gate.C_SIGMOID, rel=1e-12)
+    ir = Irreps("120x0e + 32x1e")
+    assert ir.dim == 216 and ir.num_irreps == 152 and ir.scalars_vectors() == (120, 32)
+    assert Irreps("8x0e+8x0e+32x0e+8x0e").scalars_vectors() == (56, 0)
+    assert repr(_gate.Gate(ir).irreps_in) == "152x0e+32x1e"
+    with pytest.raises(NotImplementedError):
+        Irreps("4x2e").scalars_vectors()
+
+
+def test_batch_container_and_unbatch():
+    from jamun_b200 import data, utils
+
+    chains = [synthetic.make_chain(n, i) for i, n in enumerate([5, 3, 4])]
+    ds = [data.DataWithResidueInformation(**{k: torch.as_tensor(v) for k, v in c.items()}) for c in chains]
+    b = data.Batch.from_data_list(ds)
+    assert b.num_graphs == 3 and b.num_nodes == 12 and b.batch.tolist() == [0] * 5 + [1] * 3 + [2] * 4
+    assert b.edge_index.shape[1] == 4 + 2 + 3 and int(b.edge_index[:, 4:6].min()) >= 5
+    c = b.clone("pos")
+    c.pos += 1
+    assert not torch.equal(c.pos, b.pos) and c.atom_type_index is b.atom_type_index
+
+    class Dummy:
+        device = torch.device("cpu")
+
+    w = utils.ModelSamplingWrapper(Dummy(), b, 0.04)
+    out = w.unbatch_samples({"xhat": torch.arange(36.0).reshape(12, 3), "xhat_traj": torch.zeros(7, 12, 3), "t": torch.ones(7)})
+    assert [o["xhat"].shape[0] for o in out] == [5, 3, 4] and out[1]["xhat_traj"].shape == (3, 7, 3)
+    with pytest.raises(AssertionError):
+        w.positions_to_graph(torch.zeros(11, 3))
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jamun_b200.sampling import Sampler
+    from jamun_b200.sharding import shard_chains
+
+    sizes = synthetic.workload_sizes("2AA", 10)
+    mine = shard_chains(len(sizes), rank, world)
+    sample = torch.full((sum(sizes[i] for i in mine), 3), float(rank))
+    allx = Sampler.gather_samples_ragged(sample)
+    q.put((rank, list(mine), allx.shape[0], float(allx.sum())))
+    dist.destroy_process_group()
+
+
+def test_chain_sharding_and_gather_world2():
+    """N>1 path on CPU: contiguous chain shards + the single final gather, over gloo with world_size 2."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    sizes = synthetic.workload_sizes("2AA", 10)
+    assert res[0][1] == list(range(0, 5)) and res[1][1] == list(range(5, 10))
+    total = sum(sizes)
+    assert res[0][2] == res[1][2] == total
+    assert res[0][3] == pytest.approx(3.0 * sum(sizes[5:]))
