@@ -276,30 +276,55 @@ def run_native(args):
     e2e_value = total_atoms * args.inner * args.steps / (ems * 1e-3)
     bytes_io = int(y_host.numel() * 4)
 
-    # ---------------- roofline of the dominant kernel: jamun_conv_fwd (hidden block), timed alone with CUDA events
+    # ---------------- roofline of the dominant kernels, each timed alone with CUDA events on the launch stream
     pk, pk_src = peaks()
     plan = model.arch_module.plan(model.sigma_context(SIGMA).c_noise, dev)
-    b = plan.blocks[1]
+    blk = plan.blocks[1]
     x_in = topo.xs[0]
-    reps = 5
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], topo.conv)
-    torch.cuda.synchronize()
-    c0.record()
-    for _ in range(reps):
-        ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], topo.conv)
-    c1.record()
-    torch.cuda.synchronize()
-    conv_ms = c0.elapsed_time(c1) / reps
     E = int(topo.rowptr[-1].item())
     deg = E / max(1, atoms)
-    flop_per_atom = 2 * 65 * (152 * 152 + 3 * 184 * 32) + 2 * deg * 65 * (152 + 3 * 184)  # contraction + aggregate build
-    achieved = atoms * flop_per_atom / (conv_ms * 1e-3) / 1e12
-    tf32_peak = pk["bf16_tflops"] / 2.0  # dense tf32 = half the bf16 rate; fp32 parity needs 3 tf32 passes -> /3 for 3xTF32
-    roofline = {"kernel": "jamun_conv_fwd (hidden ConvBlock, 120x0e+32x1e)", "bound": "tensor", "achieved": achieved,
-                "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
-                "peak_source": f"{pk_src} bf16 burst / 2 (tf32 dense)", "ms_per_launch": conv_ms,
-                "flop_per_atom": flop_per_atom, "mean_in_degree": deg}
+
+    def time_kernel(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / reps
+
+    from jamun_b200 import engine as _engine
+
+    rp = topo.chunk_rows
+    st0, st1 = 65 * 5, 65 * 6
+    a1_off, comp = st0 * rp * 32, st1 * rp * 32
+    if topo.a_ws is None:
+        _engine.conv_tc(topo, blk, x_in, topo.conv)
+    nrows = min(rp, atoms)
+    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, 0, nrows, rp,
+                                                    topo.a_ws, topo.a_ws[a1_off:], comp, topo.inv_deg))
+    base = topo.a_ws.data_ptr()
+    gemm_ms = time_kernel(lambda: ops.gemm_tf32x3(
+        [base] + [base + 4 * (a1_off + c * comp) for c in range(3)], [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3,
+        [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216], [1.0] * 4, nrows, rp,
+        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
+    # algorithmic work per launch (SURVEY 8d minimal formulation): contraction 2*65*(152*152+3*184*32) FLOP per
+    # atom on the tensor pipe (x3 passes for fp32 parity are NOT counted); A operand 65*(152+3*184)*4 B per atom through HBM
+    gemm_flop = nrows * 2.0 * 65 * (152 * 152 + 3 * 184 * 32)
+    a_bytes = nrows * 65.0 * (160 + 3 * 192) * 4
+    tf32_peak = pk["bf16_tflops"] / 2.0
+    roofline = {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
+                "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
+                "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
+                "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
+                "second_kernel": {"kernel": "conv_build_kernel<120,32> (aggregate, CUDA cores, writes the A operand)", "bound": "hbm",
+                                  "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                  "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                  "fma_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 184) / (build_ms * 1e-3) / 1e12}}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -92,6 +92,21 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
                    const float* rhat, const float* m0, const float* m1, float alpha0, float alpha1, int N,
                    float* out, jamun_stream_t stream);
 
+/* Tensor-core evaluation of Conv.forward, split in two launches (DESIGN.md "conv on tcgen05"):
+ * (1) jamun_conv_build_a: per receiver, A[k',u'] = sum_e h'_e[k'] f_e[u'] written as the fp32 A operand of the GEMM in
+ *     stage-major layout ([stage][rows_pad][32]; stage = k'*nslots + slot; slots per the table in conv_build.cu) for
+ *     rows [row0, row0+nrows); a0 holds the 0e operand, a1 + c*a1_comp_stride the three 1e operands; inv_deg[i] = 1/max(1,deg).
+ * (2) jamun_gemm_tf32x3: out[r, out_col[s] + n] = row_scale[r] * alpha[s] * sum_K A_s[r,K] B_s[K,n] for up to 4 segments,
+ *     tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy), accumulators in TMEM.  b[s] is the weight operand
+ *     pre-packed per stage as (hi | lo) images in the UMMA K-major SWIZZLE_128B shared-memory layout
+ *     (jamun_b200/packing.py::pack_b_images).  rows_pad % 128 == 0; sum n_pad <= 256; n_pad % 16 == 0, <= 160. */
+int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                       const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                       long long a1_comp_stride, float* inv_deg, jamun_stream_t stream);
+int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                      const int* n_valid, const int* out_col, const float* alpha, int rows, int rows_pad,
+                      const float* row_scale, float* out, int out_ld, jamun_stream_t stream);
+
 /* Gate + self-interaction + skip Linear + noise-conditional skip/scale
  * (e3tools/nn/_gate.py:63-64, _interaction.py:26-30, model/noise_conditioning.py:50-73,
  * arch/e3conv.py:131-133).  y = Lin_self(Gate(conv)) + Lin_skip(x_in);

@@ -8,15 +8,23 @@ and stream plumbing only.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import ops, packing
 from .irreps import Irreps
 
 
+# "tc": aggregate builder + tcgen05 3xTF32 GEMM (product path); "simt": the exact-fp32 CUDA-core kernel (kept for
+# A/B validation of the tensor-core path, selectable with JAMUN_B200_CONV=simt)
+CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
+
+
 class Topology:
+    WORKSPACE_BYTES = 24 << 30
+
     """Per-template constants resident in HBM: chain layout, bonded CSR by receiver, atom indices, and the
     edge workspaces sized for the worst case so that no kernel ever needs a host-side edge count."""
 
@@ -74,7 +82,15 @@ class Topology:
         self.xa = [torch.zeros(N, ops.HID, **f32) for _ in range(2)]  # node_attr ping-pong
         self.xs = [torch.zeros(N, ops.HID, **f32) for _ in range(2)]  # scaled node_attr ping-pong
         self.conv = torch.zeros(N, ops.GATE_IN, **f32)
+        self.inv_deg = torch.zeros(max(N, 1), **f32)
         self.x0_key = None
+        # fp32 A operand of the tensor-core conv (stage-major), sized for the hidden blocks; large batches are
+        # processed in row chunks so the workspace stays below WORKSPACE_BYTES
+        per_row = 65 * (5 + 3 * 6) * 32 * 4
+        rows_pad = (N + 127) // 128 * 128
+        max_rows = max(128, (self.WORKSPACE_BYTES // per_row) // 128 * 128)
+        self.chunk_rows = min(rows_pad, max_rows)
+        self.a_ws = None  # allocated on first use
 
     def build_csr(self, pos: torch.Tensor, r_cut: float):
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
@@ -132,8 +148,12 @@ class E3ConvPlan:
             self.blocks: List[Dict] = []
             for b in blocks:
                 pk = b.pack(emb)
-                self.blocks.append({k: (v.detach().to(dev, torch.float32).contiguous() if isinstance(v, torch.Tensor) else v)
-                                    for k, v in pk.items()})
+                blk = {k: (v.detach().to(dev, torch.float32).contiguous() if isinstance(v, torch.Tensor) else v)
+                       for k, v in pk.items()}
+                w0, w1 = packing.conv_k_layout(blk["m0"], blk["m1"], blk["s_in"], blk["v_in"])
+                blk["b0_img"] = packing.pack_b_images(w0, 160)
+                blk["b1_img"] = packing.pack_b_images(w1, 32)
+                self.blocks.append(blk)
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
             self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
@@ -150,6 +170,30 @@ class E3ConvPlan:
         values = torch.linspace(0.0, float(r_cut), self.n_basis + 2, dtype=torch.float32)
         step = float(values[1] - values[0])
         return values[1:-1].to(self.device).contiguous(), step
+
+
+def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor) -> None:
+    """Conv.forward on the tensor cores: jamun_conv_build_a (aggregate, CUDA cores) -> jamun_gemm_tf32x3 (tcgen05)."""
+    s_in, v_in = b["s_in"], b["v_in"]
+    ns = (s_in + 31) // 32
+    nsl0, nsl1 = ns + (1 if v_in else 0), ns + (2 if v_in else 0)
+    st0, st1 = 65 * nsl0, 65 * nsl1
+    rp = topo.chunk_rows
+    if topo.a_ws is None:
+        topo.a_ws = torch.empty(65 * (5 + 3 * 6) * rp * 32, dtype=torch.float32, device=topo.device)
+    a0 = topo.a_ws
+    a1_off = st0 * rp * 32
+    comp = st1 * rp * 32
+    base = a0.data_ptr()
+    for row0 in range(0, topo.N, rp):
+        nrows = min(rp, topo.N - row0)
+        ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, row0, nrows, rp, a0, a0[a1_off:], comp,
+                         topo.inv_deg)
+        a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
+        b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
+        ops.gemm_tf32x3(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
+                        [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp,
+                        topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
 
 
 def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,
@@ -169,8 +213,11 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
     nb = len(plan.blocks)
     for l, b in enumerate(plan.blocks):
         ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
-        ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
-                     b["alpha0"], b["alpha1"], topo.conv)
+        if CONV_IMPL == "simt":
+            ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
+                         b["alpha0"], b["alpha1"], topo.conv)
+        else:
+            conv_tc(topo, b, x_in, topo.conv)
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None
         s_next = plan.scales[l] if l < nb - 1 else None

@@ -114,6 +114,26 @@ def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: floa
     return out
 
 
+def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, row0: int, nrows: int, rows_pad: int, a0, a1,
+                 a1_comp_stride: int, inv_deg):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_build_a(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), row0,
+                                       nrows, rows_pad, _ptr(a0), _ptr(a1), int(a1_comp_stride), _ptr(inv_deg), _stream())
+    _lib.check(rc, "jamun_conv_build_a")
+    _count()
+
+
+def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr,
+                out_ptr, out_ld: int):
+    """Raw-pointer front end (segments are slices of larger workspaces).  All lists have one entry per segment."""
+    n = len(a_ptrs)
+    VP, IA, FA = C.c_void_p * n, C.c_int * n, C.c_float * n
+    rc = _lib.lib().jamun_gemm_tf32x3(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col),
+                                      FA(*alpha), rows, rows_pad, row_scale_ptr, out_ptr, out_ld, _stream())
+    _lib.check(rc, "jamun_gemm_tf32x3")
+    _count()
+
+
 def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
                c_act: float, c_gate: float, x_new, x_scaled):
     N = conv.shape[0]

@@ -1,0 +1,103 @@
+"""GPU tests of the tensor-core path: the 3xTF32 tcgen05 GEMM against fp64 matmul, and the two-launch conv
+(aggregate builder + GEMM) against the exact-fp32 SIMT kernel and the oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gemm(A_list, B_list, n_pads, rows, row_scale=None, alphas=None):
+    from jamun_b200 import ops, packing
+
+    rows_pad = (rows + 127) // 128 * 128
+    dev = "cuda"
+    a_bufs, b_bufs, n_stages, n_valid, out_col = [], [], [], [], []
+    col = 0
+    for A, B, n_pad in zip(A_list, B_list, n_pads):
+        K = A.shape[1]
+        assert K % 32 == 0
+        S = K // 32
+        a_sm = torch.full((S, rows_pad, 32), float("nan"), device=dev)
+        a_sm[:, :rows] = A.to(dev).reshape(rows, S, 32).permute(1, 0, 2)
+        a_bufs.append(a_sm.contiguous())
+        b_bufs.append(packing.pack_b_images(B.to(dev), n_pad))
+        n_stages.append(S)
+        n_valid.append(B.shape[1])
+        out_col.append(col)
+        col += B.shape[1]
+    out = torch.full((rows, col), float("nan"), device=dev)
+    alphas = alphas or [1.0] * len(A_list)
+    ops.gemm_tf32x3([a.data_ptr() for a in a_bufs], [b.data_ptr() for b in b_bufs], n_stages, list(n_pads), n_valid, out_col,
+                    alphas, rows, rows_pad, row_scale.data_ptr() if row_scale is not None else None, out.data_ptr(), col)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("rows,K,N,n_pad", [(128, 32, 32, 32), (128, 64, 152, 160), (300, 32 * 9, 152, 160), (77, 32 * 13, 32, 32),
+                                            (1000, 32 * 40, 16, 16)])
+def test_gemm_tf32x3_matches_fp64(rows, K, N, n_pad):
+    gen = torch.Generator().manual_seed(rows + K + N)
+    A = torch.randn(rows, K, generator=gen)
+    B = torch.randn(K, N, generator=gen) * 0.3
+    out = _run_gemm([A], [B], [n_pad], rows).cpu().double()
+    ref = A.double() @ B.double()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err <= 1e-5 * scale, f"err {err} scale {scale}"  # tensor-core fp32 accumulation truncates (not RN)
+    # a single TF32 pass would be ~1e-3 relative: make sure the split is really active
+    assert err <= 1e-4 * (A.abs().double() @ B.abs().double()).max().item() / 30
+
+
+def test_gemm_multi_segment_scaling_and_wraparound():
+    gen = torch.Generator().manual_seed(7)
+    rows = 260
+    A0, A1, A2, A3 = (torch.randn(rows, 32 * s, generator=gen) for s in (7, 5, 5, 5))
+    B0 = torch.randn(32 * 7, 152, generator=gen)
+    B1 = torch.randn(32 * 5, 32, generator=gen)
+    rs = torch.rand(rows, generator=gen) + 0.5
+    out = _run_gemm([A0, A1, A2, A3], [B0, B1, B1, B1], [160, 32, 32, 32], rows, row_scale=rs.cuda(), alphas=[0.5, 2.0, 2.0, 2.0])
+    ref = torch.cat([0.5 * A0.double() @ B0.double()] + [2.0 * a.double() @ B1.double() for a in (A1, A2, A3)], dim=1) * rs.double()[:, None]
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 3e-6 * ref.abs().max().item(), err
+
+
+def test_gemm_hi_lo_exactness():
+    """Inputs exactly representable in tf32 x small integers: the result must be exact."""
+    A = torch.randint(-8, 9, (128, 64)).float()
+    B = torch.randint(-8, 9, (64, 32)).float()
+    out = _run_gemm([A], [B], [32], 128).cpu()
+    assert torch.equal(out, A @ B)
+
+
+@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31]])
+def test_conv_tc_matches_simt_and_fp64(models, sizes):
+    """Two-launch tensor-core conv == exact-fp32 SIMT conv (same operands) to ~1e-6, for the initial and a hidden block."""
+    import kernel_model as KM
+    from jamun_b200 import data, engine, ops, synthetic
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors(sizes)
+    gen = torch.Generator().manual_seed(1)
+    y = (t["pos"] + 0.04 * torch.randn(t["pos"].shape, generator=gen)).cuda()
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    ctx = prod.sigma_context(0.04)
+    plan = prod.arch_module.plan(ctx.c_noise, "cuda")
+    ybar, p = ops.center_scale(y, topo.chain_ptr, ctx.c_in)
+    topo.build_csr(ybar, ctx.r_cut)
+    mu, step = plan.radial_grid(ctx.r_cut)
+    ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
+    N = p.shape[0]
+    for l, x in ((0, None), (1, torch.randn(N, 216, generator=gen).cuda())):
+        b = plan.blocks[l]
+        if x is None:
+            x = torch.randn(N, 56, generator=gen).cuda()
+        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        ref = torch.empty(N, 248, device="cuda")
+        ops.conv_fwd(x, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], ref)
+        got = torch.full((N, 248), float("nan"), device="cuda")
+        engine.conv_tc(topo, b, x, got)
+        torch.cuda.synchronize()
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 5e-6 * max(1.0, scale), f"block {l}: err {err} scale {scale}"
