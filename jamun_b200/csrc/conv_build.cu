@@ -10,7 +10,8 @@
 //   segment 0 (0e, nslots0 = NS + [V>0]):  slot s<NS : x_s[32s+lane]          slot NS   : x_v . rhat
 //   segment 1+c (1e, nslots1 = NS + 2[V>0]): slot s<NS : x_s[32s+lane] rhat_c   slot NS   : x_v[c] / sqrt3
 //                                                                               slot NS+1 : (x_v x rhat)[c] / sqrt2
-//   stage index = k' * nslots + slot;  element (stage, row, lane) at ((stage * rows_pad) + row) * 32 + lane.
+//   stage index = k' * nslots + slot;  element (stage, row, lane) at ((stage * rows_pad) + row) * 32 + swz(lane, row),
+//   swz = (((lane / 4) ^ (row % 8)) * 4) + lane % 4  (so the GEMM's per-row shared-memory reads are conflict-free).
 #include "common.cuh"
 
 namespace {
@@ -33,6 +34,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // row within the chunk
     if (r >= nrows) return;
     const int i = row0 + r;
+    const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);  // 16-byte chunks XOR-swizzled with (row & 7)
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
     if (lane == 0) inv_deg[i] = 1.0f / (float)(e1 > e0 ? e1 - e0 : 1);
 
@@ -94,13 +96,13 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         for (int k = 0; k < RK; ++k) {
             if (k >= nk) break;
             const int kp = kb * RK + k;
-            float* p0 = a0 + ((size_t)(kp * NSL0) * rows_pad + r) * 32 + lane;
+            float* p0 = a0 + ((size_t)(kp * NSL0) * rows_pad + r) * 32 + swz;
 #pragma unroll
             for (int s = 0; s < NS; ++s) __stcs(p0 + (size_t)s * rows_pad * 32, s0[k][s]);
             if (V_IN > 0) __stcs(p0 + (size_t)NS * rows_pad * 32, aq[k]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float* p1 = a1 + c * a1_comp_stride + ((size_t)(kp * NSL1) * rows_pad + r) * 32 + lane;
+                float* p1 = a1 + c * a1_comp_stride + ((size_t)(kp * NSL1) * rows_pad + r) * 32 + swz;
 #pragma unroll
                 for (int s = 0; s < NS; ++s) __stcs(p1 + (size_t)s * rows_pad * 32, s1[k][c][s]);
                 if (V_IN > 0) {

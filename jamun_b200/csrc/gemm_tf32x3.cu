@@ -1,14 +1,16 @@
 // Node-tile GEMM on the 5th-gen tensor cores: out[rows, N] = scale_row * alpha * A[rows, K] . B[K, N] with fp32 accuracy
 // from three TF32 products (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
 //
-// One CTA owns 128 rows (nodes).  Roles (192 threads):
-//   warps 0-3  A producers: thread r streams row r of the fp32 A operand from HBM (stage-major layout, 128 B per stage),
-//              splits each value into tf32 hi / exact remainder lo in registers and writes both straight into TMEM with
-//              tcgen05.st -- the A operand never touches shared memory (TS-mode MMA).  Afterwards they run the epilogue.
-//   warp 4     B producer: one thread issues a 1-D bulk async copy per stage of the pre-swizzled (hi|lo) weight image
-//              (packed once on the host in the UMMA K-major SWIZZLE_128B layout) into a 4-deep shared-memory ring.
-//   warp 5     MMA issuer: one thread issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=n_pad) per stage and
-//              commits to the stage's "empty" mbarrier.
+// One CTA owns 128 rows (nodes).  Roles (352 threads; warp numbers below are for one converter group):
+//   warp 4     A loader: one thread issues a 16 KB 1-D bulk async copy per stage (the tile's 128 rows x 128 B are contiguous
+//              in the stage-major fp32 A layout) into a 6-deep shared-memory ring -- HBM latency is hidden by the copy engine.
+//   warps 0-3  converters: thread r reads row r of the landed tile (bank-conflict-free thanks to the XOR chunk swizzle the
+//              builder applied), splits each value into tf32 hi / exact remainder lo and writes both straight into TMEM
+//              with tcgen05.st (TS-mode MMA: the A operand is never re-read from shared memory).  Then the epilogue.
+//   warp 5     B loader: one bulk async copy per stage of the pre-swizzled (hi|lo) weight image (packed once on the host
+//              in the UMMA K-major SWIZZLE_128B layout) into a 3-deep shared-memory ring.
+//   warp 6     MMA issuer: one thread issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=n_pad) per stage and commits
+//              to the stage's "empty" mbarriers.
 // Up to four K-segments, each with its own A, B, N and TMEM accumulator columns, run back to back in one launch
 // (conv: one 0e segment with N=160 and three 1e segments with N=32).
 #include "common.cuh"
@@ -17,16 +19,20 @@
 namespace {
 using namespace jb;
 
-constexpr int kSlots = 4;                  // pipeline depth (A slots in TMEM, B slots in shared memory)
+constexpr int kTSlots = 4;                 // A slots in TMEM
+constexpr int kASlots = 6;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
+constexpr int kBSlots = 3;                 // weight images in shared memory
 constexpr int kBK = 32;                    // K per stage (one 128-byte swizzle row of tf32)
 constexpr int kMaxN = 160;
-constexpr int kBSlotBytes = 2 * kMaxN * 128;  // hi + lo images
+constexpr int kATileBytes = 128 * kBK * 4;    // 16 KB
+constexpr int kBSlotBytes = 2 * kMaxN * 128;  // hi + lo images, 40 KB
 constexpr int kTmemCols = 512;
 constexpr int kACol0 = 256;                // A slots live in TMEM columns [256, 512): 64 columns (hi 32 | lo 32) each
-constexpr int kThreads = 192;
+constexpr int kConvWarps = 8;              // two converter groups of 4 warps (TMEM lane quarters), alternating stages
+constexpr int kThreads = (kConvWarps + 3) * 32;  // + A loader, B loader, MMA issuer
 
 struct Seg {
-    const float* a;       // [n_stages][rows_pad][32]
+    const float* a;       // [n_stages][rows_pad][32], 16-byte chunks of a row XOR-swizzled with (row & 7)
     const float* b;       // [n_stages][2][n_pad*32] swizzled images
     float* out;           // output base (row-major, ld = out_ld)
     int n_stages, n_pad, n_valid, d_col, out_col;
@@ -39,15 +45,11 @@ struct Params {
 };
 
 struct __align__(1024) Smem {
-    uint8_t b[kSlots][kBSlotBytes];
-    uint64_t full_a[kSlots], full_b[kSlots], empty[kSlots], d_full;
+    uint8_t b[kBSlots][kBSlotBytes];
+    uint8_t a[kASlots][kATileBytes];
+    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full;
     uint32_t tmem_base;
 };
-
-__device__ __forceinline__ void load_stage(const float* __restrict__ p, float4 (&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(p) + q);
-}
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -56,10 +58,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     const int tile_row0 = blockIdx.x * 128;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) {
-            umma::mbar_init(&S.full_a[s], 128);
-            umma::mbar_init(&S.full_b[s], 1);
-            umma::mbar_init(&S.empty[s], 1);
+        for (int s = 0; s < kASlots; ++s) {
+            umma::mbar_init(&S.a_full[s], 1);
+            umma::mbar_init(&S.a_empty[s], 128);
+        }
+        for (int s = 0; s < kBSlots; ++s) {
+            umma::mbar_init(&S.b_full[s], 1);
+            umma::mbar_init(&S.b_empty[s], 1);
+        }
+        for (int s = 0; s < kTSlots; ++s) {
+            umma::mbar_init(&S.t_full[s], 128);
+            umma::mbar_init(&S.t_empty[s], 1);
         }
         umma::mbar_init(&S.d_full, 1);
         umma::fence_barrier_init();
@@ -73,30 +82,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     int total_stages = 0;
     for (int s = 0; s < P.nseg; ++s) total_stages += P.seg[s].n_stages;
 
-    if (warp < 4) {
-        // ------------------------------------------------ A producers
-        const int r = threadIdx.x;  // row within the tile == TMEM lane
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        int g = 0;
-        float4 cur[8], nxt[8];
-        // flattened (segment, stage) iteration with a one-stage register prefetch
-        int si = 0, st = 0;
-        auto stage_ptr = [&](int seg_i, int stage) {
-            return P.seg[seg_i].a + ((size_t)stage * P.rows_pad + tile_row0 + r) * kBK;
-        };
-        if (total_stages > 0) load_stage(stage_ptr(0, 0), cur);
-        while (g < total_stages) {
-            int nsi = si, nst = st + 1;
-            if (nst == P.seg[si].n_stages) { nsi = si + 1; nst = 0; }
-            if (g + 1 < total_stages) load_stage(stage_ptr(nsi, nst), nxt);
-            const int slot = g % kSlots;
-            const uint32_t par = (g / kSlots) & 1;
-            umma::mbar_wait(&S.empty[slot], par ^ 1);
-            umma::fence_after_sync();
+    if (warp < kConvWarps) {
+        // ------------------------------------------------ converters: smem fp32 tile -> (hi, lo) in TMEM
+        const int grp = warp >> 2;              // group g handles stages == g (mod 2)
+        const int r = threadIdx.x & 127;        // row within the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int sw = r & 7;
+        for (int g = grp; g < total_stages; g += kConvWarps / 4) {
+            const int sa = g % kASlots, st = g % kTSlots;
+            umma::mbar_wait(&S.a_full[sa], (g / kASlots) & 1);
+            const float4* row = reinterpret_cast<const float4*>(S.a[sa] + r * 128);
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float v[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+                const float4 c = row[q ^ sw];
+                const float v[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const uint32_t h = __float_as_uint(v[t]) & 0xFFFFE000u;
@@ -104,17 +104,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                     lo[4 * q + t] = __float_as_uint(v[t] - __uint_as_float(h));
                 }
             }
-            const uint32_t a_addr = tmem + lane_base + (uint32_t)(kACol0 + slot * 64);
+            umma::mbar_arrive(&S.a_empty[sa]);
+            umma::mbar_wait(&S.t_empty[st], ((g / kTSlots) & 1) ^ 1);
+            umma::fence_after_sync();
+            const uint32_t a_addr = tmem + lane_base + (uint32_t)(kACol0 + st * 64);
             umma::tmem_st32(a_addr, hi);
             umma::tmem_st32(a_addr + 32, lo);
             umma::wait_st();
             umma::fence_before_sync();
-            umma::mbar_arrive(&S.full_a[slot]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
-            si = nsi;
-            st = nst;
-            ++g;
+            umma::mbar_arrive(&S.t_full[st]);
         }
         // ------------------------------------------------ epilogue
         umma::mbar_wait(&S.d_full, 0);
@@ -122,6 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         const int row = tile_row0 + r;
         const float rs = (P.row_scale && row < P.rows) ? P.row_scale[row] : 1.0f;
         for (int s = 0; s < P.nseg; ++s) {
+            if ((s == 0) != (grp == 0) && P.nseg > 1) continue;  // group 0 drains segment 0, group 1 the rest
+            if (P.nseg == 1 && grp != 0) continue;
             const Seg& sg = P.seg[s];
             for (int c0 = 0; c0 < sg.n_pad; c0 += 32) {
                 uint32_t v[32];
@@ -136,51 +136,69 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             }
         }
         umma::fence_before_sync();
-    } else if (warp == 4) {
-        // ------------------------------------------------ B producer
-        if (lane == 0) {
-            int g = 0;
-            for (int s = 0; s < P.nseg; ++s) {
-                const Seg& sg = P.seg[s];
-                const uint32_t bytes = 2u * sg.n_pad * 128u;
-                for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                    const int slot = g % kSlots;
-                    const uint32_t par = (g / kSlots) & 1;
-                    umma::mbar_wait(&S.empty[slot], par ^ 1);
-                    umma::mbar_arrive_expect_tx(&S.full_b[slot], bytes);
-                    umma::bulk_g2s(S.b[slot], sg.b + (size_t)st * (bytes / 4), bytes, &S.full_b[slot]);
+    } else if (warp == kConvWarps) {
+        // ------------------------------------------------ A loader: one 16 KB bulk copy per stage
+        int g = 0;
+        for (int s = 0; s < P.nseg; ++s) {
+            const Seg& sg = P.seg[s];
+            for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int sa = g % kASlots;
+                umma::mbar_wait(&S.a_empty[sa], ((g / kASlots) & 1) ^ 1);
+                if (umma::elect_one()) {
+                    umma::mbar_arrive_expect_tx(&S.a_full[sa], kATileBytes);
+                    umma::bulk_g2s(S.a[sa], sg.a + ((size_t)st * P.rows_pad + tile_row0) * kBK, kATileBytes, &S.a_full[sa]);
                 }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kConvWarps + 1) {
+        // ------------------------------------------------ B loader
+        int g = 0;
+        for (int s = 0; s < P.nseg; ++s) {
+            const Seg& sg = P.seg[s];
+            const uint32_t bytes = 2u * sg.n_pad * 128u;
+            for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int sb = g % kBSlots;
+                umma::mbar_wait(&S.b_empty[sb], ((g / kBSlots) & 1) ^ 1);
+                if (umma::elect_one()) {
+                    umma::mbar_arrive_expect_tx(&S.b_full[sb], bytes);
+                    umma::bulk_g2s(S.b[sb], sg.b + (size_t)st * (bytes / 4), bytes, &S.b_full[sb]);
+                }
+                __syncwarp();
             }
         }
     } else {
-        // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            int g = 0;
-            for (int s = 0; s < P.nseg; ++s) {
-                const Seg& sg = P.seg[s];
-                const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
-                const uint32_t d_addr = tmem + (uint32_t)sg.d_col;
-                for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                    const int slot = g % kSlots;
-                    const uint32_t par = (g / kSlots) & 1;
-                    umma::mbar_wait(&S.full_a[slot], par);
-                    umma::mbar_wait(&S.full_b[slot], par);
-                    umma::fence_after_sync();
-                    const uint32_t a_hi = tmem + (uint32_t)(kACol0 + slot * 64), a_lo = a_hi + 32;
-                    const uint32_t b_hi = umma::smem_u32(S.b[slot]), b_lo = b_hi + sg.n_pad * 128;
+        // ------------------------------------------------ MMA issuer (whole warp converged; one elected lane issues)
+        int g = 0;
+        for (int s = 0; s < P.nseg; ++s) {
+            const Seg& sg = P.seg[s];
+            const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
+            const uint32_t d_addr = tmem + (uint32_t)sg.d_col;
+            const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
+            for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int ts = g % kTSlots, sb = g % kBSlots;
+                umma::mbar_wait(&S.t_full[ts], (g / kTSlots) & 1);
+                umma::mbar_wait(&S.b_full[sb], (g / kBSlots) & 1);
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    const uint32_t a_hi = tmem + (uint32_t)(kACol0 + ts * 64), a_lo = a_hi + 32;
+                    const uint32_t bh = umma::desc_lo_kmajor_sw128(umma::smem_u32(S.b[sb])), bl = bh + lo_off;
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
-                        const uint64_t dbh = umma::make_desc_kmajor_sw128(b_hi + k * 32);
-                        const uint64_t dbl = umma::make_desc_kmajor_sw128(b_lo + k * 32);
+                        const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
+                        const uint64_t dbl = umma::make_desc(bl + 2 * k, umma::kDescHiKmajorSw128);
                         umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st | k) != 0);
                         umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
                         umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
                     }
-                    umma::commit(&S.empty[slot]);
+                    umma::commit(&S.t_empty[ts]);
+                    umma::commit(&S.b_empty[sb]);
                 }
+                __syncwarp();
             }
-            umma::commit(&S.d_full);
         }
+        if (umma::elect_one()) umma::commit(&S.d_full);
+        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
@@ -212,6 +230,7 @@ extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* c
     }
     JB_CHECK_ARG(dcol <= kACol0, "accumulators exceed 256 TMEM columns");
     const size_t smem = sizeof(Smem) + 1024;
+    static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         jb::set_error("jamun_gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -8,6 +8,14 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (ptxas then knows the guarded region is single-threaded and issues the
+// uniform-datapath tcgen05 / bulk-copy instructions without its per-active-thread serialisation loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -90,6 +98,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ---- descriptors -------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO),
 // LBO = 1 (ignored for swizzled K-major), version 1 (Blackwell), layout type 2.
+// Low / high words separately: within a 1024-byte-aligned tile, stepping K by 8 tf32 (32 bytes) is `lo + 2`.
+__device__ __forceinline__ uint32_t desc_lo_kmajor_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+constexpr uint32_t kDescHiKmajorSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
