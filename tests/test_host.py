@@ -216,3 +216,25 @@ def test_chain_sharding_and_gather_world2():
     total = sum(sizes)
     assert res[0][2] == res[1][2] == total
     assert res[0][3] == pytest.approx(3.0 * sum(sizes[5:]))
+
+
+def test_jamun_alias_resolves_reference_targets():
+    """Hydra `_target_` strings / pickled hyper-parameters of the reference resolve to this implementation."""
+    import importlib
+    import pickle
+
+    import jamun  # noqa: F401
+    import jamun_b200
+
+    targets = {"jamun.model.Denoiser": jamun_b200.model.Denoiser, "jamun.model.arch.E3Conv": jamun_b200.model.arch.E3Conv,
+               "jamun.e3tools.nn.ConvBlock": jamun_b200.e3tools.nn.ConvBlock, "jamun.e3tools.nn.Conv": jamun_b200.e3tools.nn.Conv,
+               "jamun.e3tools.nn.EquivariantMLP": jamun_b200.e3tools.nn.EquivariantMLP,
+               "jamun.sampling.Sampler": jamun_b200.sampling.Sampler,
+               "jamun.sampling.walkjump.SingleMeasurementSampler": jamun_b200.sampling.walkjump.SingleMeasurementSampler,
+               "jamun.sampling.mcmc.BAOAB": jamun_b200.sampling.mcmc.BAOAB, "jamun.sampling.mcmc.ABOBA": jamun_b200.sampling.mcmc.ABOBA,
+               "jamun.utils.ModelSamplingWrapper": jamun_b200.utils.ModelSamplingWrapper,
+               "jamun.distributions.ConstantSigma": jamun_b200.distributions.ConstantSigma}
+    for path, obj in targets.items():
+        mod, name = path.rsplit(".", 1)
+        assert getattr(importlib.import_module(mod), name) is obj, path
+    assert pickle.loads(pickle.dumps(jamun_b200.default_arch())).func is jamun_b200.model.arch.E3Conv
