@@ -291,22 +291,26 @@ def run_native(args):
     from jamun_b200 import engine as _engine
 
     rp = topo.chunk_rows
-    st0, st1 = 65 * 5, 65 * 6
+    st0, st1 = 65 * 5, 65 * 2
     a1_off, comp = st0 * rp * 32, st1 * rp * 32
-    if topo.a_ws is None:
-        _engine.conv_tc(topo, blk, x_in, topo.conv)
+    _engine.conv_tc(topo, blk, x_in, topo.conv)
     nrows = min(rp, atoms)
-    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, 0, nrows, rp,
-                                                    topo.a_ws, topo.a_ws[a1_off:], comp, topo.inv_deg))
     base = topo.a_ws.data_ptr()
+    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, 0, nrows, rp,
+                                                    base, base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg))
+    p2 = topo.p2.data_ptr()
     gemm_ms = time_kernel(lambda: ops.gemm_tf32x3(
         [base] + [base + 4 * (a1_off + c * comp) for c in range(3)], [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3,
         [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216], [1.0] * 4, nrows, rp,
-        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
-    # algorithmic work per launch (SURVEY 8d minimal formulation): contraction 2*65*(152*152+3*184*32) FLOP per
-    # atom on the tensor pipe (x3 passes for fp32 parity are NOT counted); A operand 65*(152+3*184)*4 B per atom through HBM
-    gemm_flop = nrows * 2.0 * 65 * (152 * 152 + 3 * 184 * 32)
-    a_bytes = nrows * 65.0 * (160 + 3 * 192) * 4
+        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248, addend_ptrs=[None, p2, p2 + 128, p2 + 256], addend_ld=[0, 96, 96, 96]))
+    rows_all = (atoms + 127) // 128 * 128
+    ygemm_ms = time_kernel(lambda: ops.gemm_tf32x3([topo.xs_op.data_ptr()], [blk["wy_img"].data_ptr()], [4], [160], [160], [0], [1.0],
+                                                   atoms, rows_all, None, topo.y.data_ptr(), 65 * 32, col_blocks=13,
+                                                   b_block_floats=4 * 2 * 160 * 32))
+    # algorithmic work per launch: the aggregated contraction 2*65*(152*152 + 3*64*32) FLOP per atom on the
+    # tensor pipe (the x3 TF32 passes needed for fp32 parity are NOT counted); its A operand 65*(160+3*64)*4 B per atom via HBM
+    gemm_flop = nrows * 2.0 * 65 * (152 * 152 + 3 * 64 * 32)
+    a_bytes = nrows * 65.0 * (160 + 3 * 64) * 4
     tf32_peak = pk["bf16_tflops"] / 2.0
     roofline = {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
                 "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
@@ -314,10 +318,13 @@ def run_native(args):
                 "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
                 "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
                 "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
-                "second_kernel": {"kernel": "conv_build_kernel<120,32> (aggregate, CUDA cores, writes the A operand)", "bound": "hbm",
-                                  "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                                  "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                  "fma_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 184) / (build_ms * 1e-3) / 1e12}}
+                "second_kernel": {"kernel": "conv_build_kernel<120,32> (aggregate + path-2 gather, CUDA cores, writes the A operand)",
+                                  "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
+                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                  "fma_TFLOPs": nrows * deg * 2 * (65 * (152 + 3 * 64) + 65 * 32) / (build_ms * 1e-3) / 1e12},
+                "third_kernel": {"kernel": "gemm_tf32x3_kernel, 13 column blocks (per-node transform Y = x_s.W, N=2080)",
+                                 "ms_per_launch": ygemm_ms, "achieved": atoms * 2.0 * 120 * 2080 / (ygemm_ms * 1e-3) / 1e12,
+                                 "unit": "TFLOP/s"}}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -96,15 +96,25 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  * (1) jamun_conv_build_a: per receiver, A[k',u'] = sum_e h'_e[k'] f_e[u'] written as the fp32 A operand of the GEMM in
  *     stage-major layout ([stage][rows_pad][32]; stage = k'*nslots + slot; slots per the table in conv_build.cu) for
  *     rows [row0, row0+nrows); a0 holds the 0e operand, a1 + c*a1_comp_stride the three 1e operands; inv_deg[i] = 1/max(1,deg).
+ *     The path 0e(x)1e->1e is gathered from y[N, 65*32] = x_s . W (pre-transformed source rows) into p2[N, p2_ld]:
+ *     p2[i, c*32+w] = sum_e rhat_e[c] sum_k' h'_e[k'] y[src_e, k'*32+w], multiplied by p2_scale/deg when p2_scale != 0.
  * (2) jamun_gemm_tf32x3: out[r, out_col[s] + n] = row_scale[r] * alpha[s] * sum_K A_s[r,K] B_s[K,n] for up to 4 segments,
  *     tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy), accumulators in TMEM.  b[s] is the weight operand
  *     pre-packed per stage as (hi | lo) images in the UMMA K-major SWIZZLE_128B shared-memory layout
- *     (jamun_b200/packing.py::pack_b_images).  rows_pad % 128 == 0; sum n_pad <= 256; n_pad % 16 == 0, <= 160. */
+ *     (jamun_b200/packing.py::pack_b_images).  rows_pad % 128 == 0; sum n_pad <= 256; n_pad % 16 == 0, <= 160.
+ *     addend[s] (optional, [rows, addend_ld[s]]) is added to the accumulator before scaling.  col_blocks > 1 launches
+ *     one CTA column per block of output columns: block y uses b[s] + y*b_block_floats and writes at out_col[s] + y*n_valid[s]
+ *     (same A) -- used for the wide per-node transform Y = x_s . W (N = 65*32 = 13 blocks of 160).
+ * (3) jamun_pack_rows: copies columns [col0, col0+ncols) of a row-major matrix into the GEMM's stage-major, chunk-swizzled
+ *     A layout ([ceil(ncols/32)][rows_pad][32], zero padded). */
 int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                       const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
-                       long long a1_comp_stride, float* inv_deg, jamun_stream_t stream);
+                       const float* rhat, const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                       long long a1_comp_stride, float* p2, int p2_ld, float p2_scale, float* inv_deg,
+                       jamun_stream_t stream);
+int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
-                      const int* n_valid, const int* out_col, const float* alpha, int rows, int rows_pad,
+                      const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                      const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                       const float* row_scale, float* out, int out_ld, jamun_stream_t stream);
 
 /* Gate + self-interaction + skip Linear + noise-conditional skip/scale

@@ -1,92 +1,154 @@
-// Aggregate step of the equivariant convolution for the tensor-core path: per receiver node i
+// Aggregate step of the equivariant convolution for the tensor-core path.  Per receiver node i
 //   A_i[k', u'] = sum_{e -> i} h'_e[k'] * f_e[u']          (h' = [radial hidden (64), 1];  f = edge features)
-// written as the fp32 A operand of jamun_gemm_tf32x3 in its stage-major layout.
+// is written as the fp32 A operand of jamun_gemm_tf32x3 in its stage-major layout, for every tensor-product path whose
+// edge feature is cheap to aggregate: 0e(x)0e->0e, 1e(x)1e->0e, 1e(x)0e->1e, 1e(x)1e->1e.
 //
-// One warp per node; lanes run over a 32-wide feature slot (coalesced 128-byte gathers of the source row and
-// coalesced 128-byte stores of the operand row); a block of 4 radial channels is accumulated in registers per pass
-// over the node's in-edges, so each gathered source row feeds 4 x 23 FMAs.
+// The remaining path 0e(x)1e->1e (x_s * rhat_c, 120 scalars x 3 components: half of all aggregate FLOPs and operand
+// bytes if treated the same way) is evaluated transform-then-aggregate instead: a per-node GEMM first forms
+// Y_j[k', w] = sum_u M1[k', u, w] x_s,j[u] (jamun_gemm_tf32x3 with 13 column blocks), and this kernel gathers
+//   p2_i[c, w] = sum_{e -> i} rhat_e[c] * sum_k' h'_e[k'] * Y_j(e)[k', w]
+// with lanes over w -- 2 kFMA per edge instead of 23 k.  The GEMM epilogue adds p2 to the 1e accumulators.
 //
-// Operand layout (DESIGN.md "conv operand layout"), NS = ceil(S_IN/32) scalar slots:
-//   segment 0 (0e, nslots0 = NS + [V>0]):  slot s<NS : x_s[32s+lane]          slot NS   : x_v . rhat
-//   segment 1+c (1e, nslots1 = NS + 2[V>0]): slot s<NS : x_s[32s+lane] rhat_c   slot NS   : x_v[c] / sqrt3
-//                                                                               slot NS+1 : (x_v x rhat)[c] / sqrt2
-//   stage index = k' * nslots + slot;  element (stage, row, lane) at ((stage * rows_pad) + row) * 32 + swz(lane, row),
-//   swz = (((lane / 4) ^ (row % 8)) * 4) + lane % 4  (so the GEMM's per-row shared-memory reads are conflict-free).
+// One warp per node.  Scalars: lane L owns x_s[4L..4L+3] (one 16-byte gather per edge, one 16-byte operand store per
+// channel); vectors: lane owns multiplicity `lane`; RK = 4 radial channels are accumulated in registers per pass over the
+// in-edges with packed fp32 FMAs (FFMA2).  Per-edge invariants (row offsets, rhat) are cached in shared memory per warp.
+//
+// Operand layout, NS = ceil(S_IN/32) scalar slots:
+//   segment 0 (0e, nslots0 = NS + [V>0]):   slot s<NS : x_s[32s .. 32s+31]   slot NS : x_v . rhat
+//   segment 1+c (1e, nslots1 = 2[V>0]):     slot 0 : x_v[c] / sqrt3          slot 1  : (x_v x rhat)[c] / sqrt2
+//   stage index = k' * nslots + slot;  element (stage, row, p) at ((stage * rows_pad) + row) * 32 + swz(p, row),
+//   swz = (((p / 4) ^ (row % 8)) * 4) + p % 4  (so the GEMM's per-row shared-memory reads are conflict-free).
 #include "common.cuh"
 
 namespace {
 using namespace jb;
 
-constexpr int RK = 4;
 constexpr float kInvSqrt3 = 0.57735026918962576451f;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
+constexpr int YLD = (JAMUN_EDGE_HID + 1) * JAMUN_V;  // 2080
+constexpr int MAXD = 64;  // in-edges per node whose per-edge invariants are cached in shared memory
 
-template <int S_IN, int V_IN>
-__global__ void __launch_bounds__(256)
+// Blackwell packed fp32 FMA (SASS FFMA2): two FMAs per issue slot; ptxas folds the {a,a} pack into a scalar operand.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+
+template <int S_IN, int V_IN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
-                  const float* __restrict__ h, const float* __restrict__ rhat, int row0, int nrows, int rows_pad,
-                  float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride, float* __restrict__ inv_deg) {
+                  const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int row0,
+                  int nrows, int rows_pad, float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride,
+                  float* __restrict__ p2, int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
+    constexpr int RK = 4;
+    constexpr int NKB = JAMUN_EDGE_HID / RK;  // full blocks; block NKB is the bias channel (h' = 1)
     constexpr int D_IN = S_IN + 3 * V_IN;
     constexpr int NS = (S_IN + 31) / 32;
-    constexpr int NV0 = V_IN > 0 ? 1 : 0, NV1 = V_IN > 0 ? 2 : 0;
-    constexpr int NSL0 = NS + NV0, NSL1 = NS + NV1;
-    const int lane = threadIdx.x & 31;
+    constexpr int NSL0 = NS + (V_IN > 0 ? 1 : 0), NSL1 = V_IN > 0 ? 2 : 0;
+    __shared__ float4 meta_s[8][MAXD][2];  // per warp, per in-edge: {x row offset, y row offset, rx, ry}, {rz, -, -, -}
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // row within the chunk
     if (r >= nrows) return;
     const int i = row0 + r;
-    const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);  // 16-byte chunks XOR-swizzled with (row & 7)
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
-    if (lane == 0) inv_deg[i] = 1.0f / (float)(e1 > e0 ? e1 - e0 : 1);
+    const int deg = e1 - e0;
+    const float invd = 1.0f / (float)(deg > 0 ? deg : 1);
+    if (lane == 0) inv_deg[i] = invd;
+    const bool cached = deg <= MAXD;
+    if (cached) {
+        for (int t = lane; t < deg; t += 32) {
+            const int j = col[e0 + t];
+            const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(e0 + t));
+            meta_s[wib][t][0] = make_float4(__int_as_float(j * D_IN), __int_as_float(j * YLD), rh.x, rh.y);
+            meta_s[wib][t][1] = make_float4(rh.z, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+    }
+    const bool s_live = 4 * lane < NS * 32;
+    const bool s_load = 4 * lane < S_IN;
+    const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);  // position of a 4-byte element owned by `lane`
+    const int swz4 = ((lane & 7) ^ (r & 7)) << 2;                  // position of the 16-byte chunk of the scalar store
+    float pacc[3] = {0.f, 0.f, 0.f};
 
-    for (int kb = 0; kb <= JAMUN_EDGE_HID / RK; ++kb) {
-        const bool bias = kb == JAMUN_EDGE_HID / RK;
-        float s0[RK][NS], s1[RK][3][NS];
+    for (int kb = 0; kb <= NKB; ++kb) {
+        const bool bias = kb == NKB;
+        float s0[RK][4];
         float aq[RK], av[RK][3], ax[RK][3];
 #pragma unroll
         for (int k = 0; k < RK; ++k) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) s0[k][s] = s1[k][0][s] = s1[k][1][s] = s1[k][2][s] = 0.f;
+            for (int t = 0; t < 4; ++t) s0[k][t] = 0.f;
             aq[k] = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) av[k][c] = ax[k][c] = 0.f;
         }
-        for (int e = e0; e < e1; ++e) {
-            const int j = col[e];
-            const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+        for (int t = 0; t < deg; ++t) {
+            int xoff, yoff;
+            float rx, ry, rz;
+            if (cached) {
+                const float4 m0 = meta_s[wib][t][0], m1 = meta_s[wib][t][1];
+                xoff = __float_as_int(m0.x);
+                yoff = __float_as_int(m0.y);
+                rx = m0.z;
+                ry = m0.w;
+                rz = m1.x;
+            } else {
+                const int j = col[e0 + t];
+                const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(e0 + t));
+                xoff = j * D_IN;
+                yoff = j * YLD;
+                rx = rh.x;
+                ry = rh.y;
+                rz = rh.z;
+            }
             float4 hq4 = make_float4(1.f, 0.f, 0.f, 0.f);
-            if (!bias) hq4 = *reinterpret_cast<const float4*>(h + (size_t)e * JAMUN_EDGE_HID + kb * RK);
+            if (!bias) hq4 = *reinterpret_cast<const float4*>(h + (size_t)(e0 + t) * JAMUN_EDGE_HID + kb * RK);
             const float hq[RK] = {hq4.x, hq4.y, hq4.z, hq4.w};
-            const float* xj = x + (size_t)j * D_IN;
-            float xs[NS];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) xs[s] = (lane + 32 * s < S_IN) ? xj[lane + 32 * s] : 0.f;
+            const float* xj = x + xoff;
+            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s_load) xs = *reinterpret_cast<const float4*>(xj + 4 * lane);
+            // path 0e(x)1e->1e through the pre-transformed source rows
+            const float* yj = y + yoff + kb * RK * JAMUN_V + lane;
+            float ta = yj[0], tb = 0.f;
+            if (!bias) {
+                const float y1 = yj[JAMUN_V], y2 = yj[2 * JAMUN_V], y3 = yj[3 * JAMUN_V];
+                ta *= hq[0];
+                ffma2v(ta, tb, hq[1], hq[2], y1, y2);
+                ta = fmaf(hq[3], y3, ta);
+            }
+            const float tsum = ta + tb;
+            ffma2(pacc[0], pacc[1], tsum, rx, ry);
+            pacc[2] = fmaf(rz, tsum, pacc[2]);
             float vx = 0.f, vy = 0.f, vz = 0.f, q = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
             if (V_IN > 0) {
                 vx = xj[S_IN + lane];
                 vy = xj[S_IN + V_IN + lane];
                 vz = xj[S_IN + 2 * V_IN + lane];
-                q = vx * rh.x + vy * rh.y + vz * rh.z;
-                cx = vy * rh.z - vz * rh.y;
-                cy = vz * rh.x - vx * rh.z;
-                cz = vx * rh.y - vy * rh.x;
+                q = vx * rx + vy * ry + vz * rz;
+                cx = vy * rz - vz * ry;
+                cy = vz * rx - vx * rz;
+                cz = vx * ry - vy * rx;
             }
 #pragma unroll
             for (int k = 0; k < RK; ++k) {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const float t = hq[k] * xs[s];
-                    s0[k][s] += t;
-                    s1[k][0][s] = fmaf(t, rh.x, s1[k][0][s]);
-                    s1[k][1][s] = fmaf(t, rh.y, s1[k][1][s]);
-                    s1[k][2][s] = fmaf(t, rh.z, s1[k][2][s]);
-                }
+                ffma2(s0[k][0], s0[k][1], hq[k], xs.x, xs.y);
+                ffma2(s0[k][2], s0[k][3], hq[k], xs.z, xs.w);
                 if (V_IN > 0) {
-                    aq[k] = fmaf(hq[k], q, aq[k]);
-                    av[k][0] = fmaf(hq[k], vx, av[k][0]);
-                    av[k][1] = fmaf(hq[k], vy, av[k][1]);
-                    av[k][2] = fmaf(hq[k], vz, av[k][2]);
-                    ax[k][0] = fmaf(hq[k], cx, ax[k][0]);
-                    ax[k][1] = fmaf(hq[k], cy, ax[k][1]);
+                    ffma2(aq[k], av[k][0], hq[k], q, vx);
+                    ffma2(av[k][1], av[k][2], hq[k], vy, vz);
+                    ffma2(ax[k][0], ax[k][1], hq[k], cx, cy);
                     ax[k][2] = fmaf(hq[k], cz, ax[k][2]);
                 }
             }
@@ -96,45 +158,79 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         for (int k = 0; k < RK; ++k) {
             if (k >= nk) break;
             const int kp = kb * RK + k;
-            float* p0 = a0 + ((size_t)(kp * NSL0) * rows_pad + r) * 32 + swz;
+            if (s_live) {
+                float* ps = a0 + ((size_t)(kp * NSL0 + (lane >> 3)) * rows_pad + r) * 32 + swz4;
+                __stcs(reinterpret_cast<float4*>(ps), make_float4(s0[k][0], s0[k][1], s0[k][2], s0[k][3]));
+            }
+            if (V_IN > 0) {
+                __stcs(a0 + ((size_t)(kp * NSL0 + NS) * rows_pad + r) * 32 + swz, aq[k]);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) __stcs(p0 + (size_t)s * rows_pad * 32, s0[k][s]);
-            if (V_IN > 0) __stcs(p0 + (size_t)NS * rows_pad * 32, aq[k]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float* p1 = a1 + c * a1_comp_stride + ((size_t)(kp * NSL1) * rows_pad + r) * 32 + swz;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) __stcs(p1 + (size_t)s * rows_pad * 32, s1[k][c][s]);
-                if (V_IN > 0) {
-                    __stcs(p1 + (size_t)NS * rows_pad * 32, av[k][c] * kInvSqrt3);
-                    __stcs(p1 + (size_t)(NS + 1) * rows_pad * 32, ax[k][c] * kInvSqrt2);
+                for (int c = 0; c < 3; ++c) {
+                    float* p1 = a1 + c * a1_comp_stride + ((size_t)(kp * NSL1) * rows_pad + r) * 32 + swz;
+                    __stcs(p1, av[k][c] * kInvSqrt3);
+                    __stcs(p1 + (size_t)rows_pad * 32, ax[k][c] * kInvSqrt2);
                 }
             }
         }
+    }
+    // path-2 sums: raw (p2_scale == 0; the GEMM epilogue adds and scales them) or final (initial block: no 1e GEMM)
+    const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p2[(size_t)i * p2_ld + c * JAMUN_V + lane] = pacc[c] * sc;
+}
+
+// x[rows, ld] columns [col0, col0+ncols) -> stage-major chunk-swizzled A operand, zero padded to 32-column stages
+__global__ void pack_rows_kernel(const float* __restrict__ x, int ld, int col0, int ncols, int rows, int rows_pad,
+                                 float* __restrict__ a) {
+    const int nst = (ncols + 31) / 32;
+    const size_t total = (size_t)nst * rows_pad * 32;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(t & 31);
+        const size_t sr = t >> 5;
+        const int row = (int)(sr % rows_pad), st = (int)(sr / rows_pad);
+        const int c = st * 32 + lane;
+        const float v = (row < rows && c < ncols) ? x[(size_t)row * ld + col0 + c] : 0.f;
+        const int swz = (((lane >> 2) ^ (row & 7)) << 2) | (lane & 3);
+        a[sr * 32 + swz] = v;
     }
 }
 
 }  // namespace
 
-// a0: [65*nslots0][rows_pad][32], a1: 3 x [65*nslots1][rows_pad][32] (component stride a1_comp_stride floats).
+// a0: [65*nslots0][rows_pad][32]; a1: 3 x [65*2][rows_pad][32] (component stride a1_comp_stride floats; unused when v_in == 0);
+// y: [N, 65*32] pre-transformed source rows; p2: [N, p2_ld] path-2 sums (see the kernel for p2_scale).
 extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                                  const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
-                                  long long a1_comp_stride, float* inv_deg, jamun_stream_t stream) {
-    JB_CHECK_ARG(x && rowptr && col && h && rhat && a0 && a1 && inv_deg, "null argument");
+                                  const float* rhat, const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                                  long long a1_comp_stride, float* p2, int p2_ld, float p2_scale, float* inv_deg,
+                                  jamun_stream_t stream) {
+    JB_CHECK_ARG(x && rowptr && col && h && rhat && y && a0 && p2 && inv_deg, "null argument");
     JB_CHECK_ARG(nrows <= rows_pad, "nrows exceeds rows_pad");
+    JB_CHECK_ARG(((size_t)x & 15) == 0 && ((size_t)a0 & 15) == 0, "x and a0 must be 16-byte aligned");
     if (nrows == 0) return JAMUN_OK;
     const int blocks = (nrows * 32 + 255) / 256;
     cudaStream_t s = jb::as_stream(stream);
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
-        conv_build_kernel<JAMUN_S, JAMUN_V><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
-                                                                  (size_t)a1_comp_stride, inv_deg);
+        JB_CHECK_ARG(a1, "a1 required for vector inputs");
+        conv_build_kernel<JAMUN_S, JAMUN_V, 3><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1,
+                                                                     (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        conv_build_kernel<JAMUN_S0, 0><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
-                                                             (size_t)a1_comp_stride, inv_deg);
+        conv_build_kernel<JAMUN_S0, 0, 3><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1,
+                                                                (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
     } else {
         jb::set_error("jamun_conv_build_a: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;
     }
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a,
+                               jamun_stream_t stream) {
+    JB_CHECK_ARG(x && a && ncols > 0 && rows <= rows_pad && rows_pad % 128 == 0, "bad argument");
+    const size_t total = (size_t)((ncols + 31) / 32) * rows_pad * 32;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > jb::kNumSMs * 16) blocks = jb::kNumSMs * 16;
+    pack_rows_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(x, ld, col0, ncols, rows, rows_pad, a);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

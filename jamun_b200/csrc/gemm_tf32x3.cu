@@ -20,7 +20,7 @@ namespace {
 using namespace jb;
 
 constexpr int kTSlots = 4;                 // A slots in TMEM
-constexpr int kASlots = 6;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
+constexpr int kASlots = 4;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
 constexpr int kBSlots = 3;                 // weight images in shared memory
 constexpr int kBK = 32;                    // K per stage (one 128-byte swizzle row of tf32)
 constexpr int kMaxN = 160;
@@ -35,19 +35,24 @@ struct Seg {
     const float* a;       // [n_stages][rows_pad][32], 16-byte chunks of a row XOR-swizzled with (row & 7)
     const float* b;       // [n_stages][2][n_pad*32] swizzled images
     float* out;           // output base (row-major, ld = out_ld)
-    int n_stages, n_pad, n_valid, d_col, out_col;
+    const float* addend;  // optional [rows, addend_ld]: out = (acc + addend[row, n]) * alpha * row_scale
+    int n_stages, n_pad, n_valid, d_col, out_col, addend_ld;
     float alpha;
 };
 struct Params {
     Seg seg[4];
     int nseg, rows, rows_pad, out_ld;
+    // column blocks (same A, passes over B): pass y uses b += y * b_block_floats, out_col += y * n_valid (all segments)
+    long long b_block_floats;
+    int col_blocks;
     const float* row_scale;  // [rows] or null
 };
 
 struct __align__(1024) Smem {
     uint8_t b[kBSlots][kBSlotBytes];
     uint8_t a[kASlots][kATileBytes];
-    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full;
+    float epi[8][32 * 33];  // per-converter-warp transpose tiles of the epilogue
+    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full, d_empty;
     uint32_t tmem_base;
 };
 
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             umma::mbar_init(&S.t_empty[s], 1);
         }
         umma::mbar_init(&S.d_full, 1);
+        umma::mbar_init(&S.d_empty, kConvWarps * 32);
         umma::fence_barrier_init();
     }
     if (warp == 0) umma::tmem_alloc<kTmemCols>(&S.tmem_base);
@@ -88,7 +94,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         const int r = threadIdx.x & 127;        // row within the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int sw = r & 7;
-        for (int g = grp; g < total_stages; g += kConvWarps / 4) {
+        float* tile = S.epi[warp];
+        const int wrow0 = tile_row0 + (warp & 3) * 32;
+        const float rs_own = (P.row_scale && tile_row0 + r < P.rows) ? P.row_scale[tile_row0 + r] : 1.0f;
+        for (int cb = 0; cb < P.col_blocks; ++cb) {
+        for (int g = cb * total_stages + grp; g < (cb + 1) * total_stages; g += kConvWarps / 4) {
             const int sa = g % kASlots, st = g % kTSlots;
             umma::mbar_wait(&S.a_full[sa], (g / kASlots) & 1);
             const float4* row = reinterpret_cast<const float4*>(S.a[sa] + r * 128);
@@ -114,91 +124,117 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             umma::fence_before_sync();
             umma::mbar_arrive(&S.t_full[st]);
         }
-        // ------------------------------------------------ epilogue
-        umma::mbar_wait(&S.d_full, 0);
+        // ------------------------------------------------ epilogue: TMEM -> registers (thread = row) -> shared-memory transpose
+        // (the operand rings are idle by now) -> coalesced 128-byte row stores with lanes over columns
+        umma::mbar_wait(&S.d_full, cb & 1);
         umma::fence_after_sync();
-        const int row = tile_row0 + r;
-        const float rs = (P.row_scale && row < P.rows) ? P.row_scale[row] : 1.0f;
+        int chunk = 0;
         for (int s = 0; s < P.nseg; ++s) {
-            if ((s == 0) != (grp == 0) && P.nseg > 1) continue;  // group 0 drains segment 0, group 1 the rest
-            if (P.nseg == 1 && grp != 0) continue;
             const Seg& sg = P.seg[s];
-            for (int c0 = 0; c0 < sg.n_pad; c0 += 32) {
+            for (int c0 = 0; c0 < sg.n_pad; c0 += 32, ++chunk) {
+                if ((chunk & 1) != grp) continue;  // the two converter groups alternate 32-column chunks
                 uint32_t v[32];
                 umma::tmem_ld32(tmem + lane_base + (uint32_t)(sg.d_col + c0), v);
                 umma::wait_ld();
-                if (row < P.rows) {
-                    float* o = sg.out + (size_t)row * P.out_ld + sg.out_col + c0;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (c0 + c < sg.n_valid) o[c] = __uint_as_float(v[c]) * sg.alpha * rs;
+                for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(v[c]);
+                __syncwarp();
+                const int ncol = sg.n_valid - c0;  // valid columns in this chunk
+                if (lane < ncol) {
+                    const int col = sg.out_col + cb * sg.n_valid + c0 + lane;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = wrow0 + rr;
+                        const float rsv = __shfl_sync(0xffffffffu, rs_own, rr);
+                        if (row < P.rows) {
+                            float acc = tile[rr * 33 + lane];
+                            if (sg.addend) acc += sg.addend[(size_t)row * sg.addend_ld + c0 + lane];
+                            sg.out[(size_t)row * P.out_ld + col] = acc * sg.alpha * rsv;
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) (void)__shfl_sync(0xffffffffu, rs_own, rr);
                 }
+                __syncwarp();
             }
         }
         umma::fence_before_sync();
+        umma::mbar_arrive(&S.d_empty);  // accumulators drained: the next pass may overwrite them
+        }  // column-block pass
     } else if (warp == kConvWarps) {
         // ------------------------------------------------ A loader: one 16 KB bulk copy per stage
         int g = 0;
-        for (int s = 0; s < P.nseg; ++s) {
-            const Seg& sg = P.seg[s];
-            for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                const int sa = g % kASlots;
-                umma::mbar_wait(&S.a_empty[sa], ((g / kASlots) & 1) ^ 1);
-                if (umma::elect_one()) {
-                    umma::mbar_arrive_expect_tx(&S.a_full[sa], kATileBytes);
-                    umma::bulk_g2s(S.a[sa], sg.a + ((size_t)st * P.rows_pad + tile_row0) * kBK, kATileBytes, &S.a_full[sa]);
+        for (int cb = 0; cb < P.col_blocks; ++cb) {
+            for (int s = 0; s < P.nseg; ++s) {
+                const Seg& sg = P.seg[s];
+                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                    const int sa = g % kASlots;
+                    umma::mbar_wait(&S.a_empty[sa], ((g / kASlots) & 1) ^ 1);
+                    if (umma::elect_one()) {
+                        umma::mbar_arrive_expect_tx(&S.a_full[sa], kATileBytes);
+                        umma::bulk_g2s(S.a[sa], sg.a + ((size_t)st * P.rows_pad + tile_row0) * kBK, kATileBytes, &S.a_full[sa]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp == kConvWarps + 1) {
         // ------------------------------------------------ B loader
         int g = 0;
-        for (int s = 0; s < P.nseg; ++s) {
-            const Seg& sg = P.seg[s];
-            const uint32_t bytes = 2u * sg.n_pad * 128u;
-            for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                const int sb = g % kBSlots;
-                umma::mbar_wait(&S.b_empty[sb], ((g / kBSlots) & 1) ^ 1);
-                if (umma::elect_one()) {
-                    umma::mbar_arrive_expect_tx(&S.b_full[sb], bytes);
-                    umma::bulk_g2s(S.b[sb], sg.b + (size_t)st * (bytes / 4), bytes, &S.b_full[sb]);
+        for (int cb = 0; cb < P.col_blocks; ++cb) {
+            for (int s = 0; s < P.nseg; ++s) {
+                const Seg& sg = P.seg[s];
+                const uint32_t bytes = 2u * sg.n_pad * 128u;
+                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                    const int sb = g % kBSlots;
+                    umma::mbar_wait(&S.b_empty[sb], ((g / kBSlots) & 1) ^ 1);
+                    if (umma::elect_one()) {
+                        umma::mbar_arrive_expect_tx(&S.b_full[sb], bytes);
+                        umma::bulk_g2s(S.b[sb], sg.b + (size_t)cb * P.b_block_floats + (size_t)st * (bytes / 4), bytes, &S.b_full[sb]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
         // ------------------------------------------------ MMA issuer (whole warp converged; one elected lane issues)
         int g = 0;
-        for (int s = 0; s < P.nseg; ++s) {
-            const Seg& sg = P.seg[s];
-            const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
-            const uint32_t d_addr = tmem + (uint32_t)sg.d_col;
-            const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
-            for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                const int ts = g % kTSlots, sb = g % kBSlots;
-                umma::mbar_wait(&S.t_full[ts], (g / kTSlots) & 1);
-                umma::mbar_wait(&S.b_full[sb], (g / kBSlots) & 1);
+        for (int cb = 0; cb < P.col_blocks; ++cb) {
+            if (cb > 0) {  // the epilogue of the previous pass must have drained the accumulators
+                umma::mbar_wait(&S.d_empty, (cb - 1) & 1);
                 umma::fence_after_sync();
-                if (umma::elect_one()) {
-                    const uint32_t a_hi = tmem + (uint32_t)(kACol0 + ts * 64), a_lo = a_hi + 32;
-                    const uint32_t bh = umma::desc_lo_kmajor_sw128(umma::smem_u32(S.b[sb])), bl = bh + lo_off;
-#pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) {
-                        const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
-                        const uint64_t dbl = umma::make_desc(bl + 2 * k, umma::kDescHiKmajorSw128);
-                        umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st | k) != 0);
-                        umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
-                        umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
-                    }
-                    umma::commit(&S.t_empty[ts]);
-                    umma::commit(&S.b_empty[sb]);
-                }
-                __syncwarp();
             }
+            for (int s = 0; s < P.nseg; ++s) {
+                const Seg& sg = P.seg[s];
+                const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
+                const uint32_t d_addr = tmem + (uint32_t)sg.d_col;
+                const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
+                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                    const int ts = g % kTSlots, sb = g % kBSlots;
+                    umma::mbar_wait(&S.t_full[ts], (g / kTSlots) & 1);
+                    umma::mbar_wait(&S.b_full[sb], (g / kBSlots) & 1);
+                    umma::fence_after_sync();
+                    if (umma::elect_one()) {
+                        const uint32_t a_hi = tmem + (uint32_t)(kACol0 + ts * 64), a_lo = a_hi + 32;
+                        const uint32_t bh = umma::desc_lo_kmajor_sw128(umma::smem_u32(S.b[sb])), bl = bh + lo_off;
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k) {
+                            const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
+                            const uint64_t dbl = umma::make_desc(bl + 2 * k, umma::kDescHiKmajorSw128);
+                            umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st | k) != 0);
+                            umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
+                            umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
+                        }
+                        umma::commit(&S.t_empty[ts]);
+                        umma::commit(&S.b_empty[sb]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (umma::elect_one()) umma::commit(&S.d_full);
+            __syncwarp();
         }
-        if (umma::elect_one()) umma::commit(&S.d_full);
-        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
@@ -211,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
 
 // Generic entry: out[rows, n_valid] (+ column offsets) from up to 4 segments.  Exposed for tests and for the conv path.
 extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
-                                 const int* n_valid, const int* out_col, const float* alpha, int rows, int rows_pad,
+                                 const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                                 const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                                  const float* row_scale, float* out, int out_ld, jamun_stream_t stream) {
     JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
@@ -222,10 +259,14 @@ extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* c
     P.rows_pad = rows_pad;
     P.out_ld = out_ld;
     P.row_scale = row_scale;
+    P.b_block_floats = b_block_floats;
+    P.col_blocks = col_blocks;
+    JB_CHECK_ARG(col_blocks >= 1, "col_blocks must be >= 1");
     int dcol = 0;
     for (int s = 0; s < nseg; ++s) {
         JB_CHECK_ARG(n_pad[s] % 16 == 0 && n_pad[s] >= 16 && n_pad[s] <= kMaxN && n_valid[s] <= n_pad[s], "n_pad out of range");
-        P.seg[s] = Seg{a[s], b[s], out, n_stages[s], n_pad[s], n_valid[s], dcol, out_col[s], alpha[s]};
+        P.seg[s] = Seg{a[s], b[s], out, addend ? addend[s] : nullptr, n_stages[s], n_pad[s], n_valid[s], dcol, out_col[s],
+                       addend_ld ? addend_ld[s] : 0, alpha[s]};
         dcol += n_pad[s];
     }
     JB_CHECK_ARG(dcol <= kACol0, "accumulators exceed 256 TMEM columns");

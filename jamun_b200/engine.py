@@ -86,7 +86,7 @@ class Topology:
         self.x0_key = None
         # fp32 A operand of the tensor-core conv (stage-major), sized for the hidden blocks; large batches are
         # processed in row chunks so the workspace stays below WORKSPACE_BYTES
-        per_row = 65 * (5 + 3 * 6) * 32 * 4
+        per_row = 65 * (5 + 3 * 2) * 32 * 4
         rows_pad = (N + 127) // 128 * 128
         max_rows = max(128, (self.WORKSPACE_BYTES // per_row) // 128 * 128)
         self.chunk_rows = min(rows_pad, max_rows)
@@ -150,9 +150,10 @@ class E3ConvPlan:
                 pk = b.pack(emb)
                 blk = {k: (v.detach().to(dev, torch.float32).contiguous() if isinstance(v, torch.Tensor) else v)
                        for k, v in pk.items()}
-                w0, w1 = packing.conv_k_layout(blk["m0"], blk["m1"], blk["s_in"], blk["v_in"])
+                w0, w1, wy = packing.conv_k_layout(blk["m0"], blk["m1"], blk["s_in"], blk["v_in"])
                 blk["b0_img"] = packing.pack_b_images(w0, 160)
-                blk["b1_img"] = packing.pack_b_images(w1, 32)
+                blk["b1_img"] = packing.pack_b_images(w1, 32) if w1 is not None else None
+                blk["wy_img"] = packing.pack_b_column_blocks(wy, 160)
                 self.blocks.append(blk)
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
@@ -173,27 +174,44 @@ class E3ConvPlan:
 
 
 def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor) -> None:
-    """Conv.forward on the tensor cores: jamun_conv_build_a (aggregate, CUDA cores) -> jamun_gemm_tf32x3 (tcgen05)."""
+    """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
+    13 column blocks) -> jamun_conv_build_a (aggregate of the other paths + gather of Y, CUDA cores) -> jamun_gemm_tf32x3."""
     s_in, v_in = b["s_in"], b["v_in"]
     ns = (s_in + 31) // 32
-    nsl0, nsl1 = ns + (1 if v_in else 0), ns + (2 if v_in else 0)
+    nsl0, nsl1 = ns + (1 if v_in else 0), (2 if v_in else 0)
     st0, st1 = 65 * nsl0, 65 * nsl1
     rp = topo.chunk_rows
+    N = topo.N
+    rows_all = (N + 127) // 128 * 128
     if topo.a_ws is None:
-        topo.a_ws = torch.empty(65 * (5 + 3 * 6) * rp * 32, dtype=torch.float32, device=topo.device)
-    a0 = topo.a_ws
+        topo.a_ws = torch.empty(65 * (5 + 3 * 2) * rp * 32, dtype=torch.float32, device=topo.device)
+        topo.xs_op = torch.empty(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
+        topo.y = torch.empty(N, 65 * 32, dtype=torch.float32, device=topo.device)
+        topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
+    # per-node transform of the scalar inputs
+    ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
+    ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [160], [160], [0], [1.0], N, rows_all, None,
+                    topo.y.data_ptr(), 65 * 32, col_blocks=13, b_block_floats=ns * 2 * 160 * 32)
+    base = topo.a_ws.data_ptr()
     a1_off = st0 * rp * 32
     comp = st1 * rp * 32
-    base = a0.data_ptr()
-    for row0 in range(0, topo.N, rp):
-        nrows = min(rp, topo.N - row0)
-        ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, row0, nrows, rp, a0, a0[a1_off:], comp,
-                         topo.inv_deg)
-        a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
-        b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
-        ops.gemm_tf32x3(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
-                        [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp,
-                        topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
+    for row0 in range(0, N, rp):
+        nrows = min(rp, N - row0)
+        if v_in:
+            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, row0, nrows, rp, base,
+                             base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg)
+            a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
+            b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
+            p2 = topo.p2.data_ptr() + 4 * row0 * 96
+            ops.gemm_tf32x3(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
+                            [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
+                            out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN,
+                            addend_ptrs=[None, p2, p2 + 4 * 32, p2 + 4 * 64], addend_ld=[0, 96, 96, 96])
+        else:  # initial block: the 1e output is the path-2 gather alone, written in place by the builder
+            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, row0, nrows, rp, base, None, 0,
+                             out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
+            ops.gemm_tf32x3([base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
+                            topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
 
 
 def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,

@@ -114,22 +114,32 @@ def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: floa
     return out
 
 
-def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, row0: int, nrows: int, rows_pad: int, a0, a1,
-                 a1_comp_stride: int, inv_deg):
+def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, y, row0: int, nrows: int, rows_pad: int, a0_ptr: int,
+                 a1_ptr: int, a1_comp_stride: int, p2_ptr: int, p2_ld: int, p2_scale: float, inv_deg):
     i32 = torch.int32
-    rc = _lib.lib().jamun_conv_build_a(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), row0,
-                                       nrows, rows_pad, _ptr(a0), _ptr(a1), int(a1_comp_stride), _ptr(inv_deg), _stream())
+    rc = _lib.lib().jamun_conv_build_a(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), _ptr(y),
+                                       row0, nrows, rows_pad, a0_ptr, a1_ptr, int(a1_comp_stride), p2_ptr, p2_ld,
+                                       float(p2_scale), _ptr(inv_deg), _stream())
     _lib.check(rc, "jamun_conv_build_a")
     _count()
 
 
+def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
+    rc = _lib.lib().jamun_pack_rows(_ptr(x), x.shape[1], col0, ncols, x.shape[0], rows_pad, _ptr(a), _stream())
+    _lib.check(rc, "jamun_pack_rows")
+    _count()
+
+
 def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr,
-                out_ptr, out_ld: int):
+                out_ptr, out_ld: int, addend_ptrs=None, addend_ld=None, col_blocks: int = 1, b_block_floats: int = 0):
     """Raw-pointer front end (segments are slices of larger workspaces).  All lists have one entry per segment."""
     n = len(a_ptrs)
     VP, IA, FA = C.c_void_p * n, C.c_int * n, C.c_float * n
+    ad = VP(*addend_ptrs) if addend_ptrs is not None else None
+    adl = IA(*addend_ld) if addend_ld is not None else None
     rc = _lib.lib().jamun_gemm_tf32x3(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col),
-                                      FA(*alpha), rows, rows_pad, row_scale_ptr, out_ptr, out_ld, _stream())
+                                      FA(*alpha), ad, adl, col_blocks, b_block_floats, rows, rows_pad, row_scale_ptr, out_ptr,
+                                      out_ld, _stream())
     _lib.check(rc, "jamun_gemm_tf32x3")
     _count()
 

@@ -39,22 +39,29 @@ def pack_b_images(w: torch.Tensor, n_pad: int) -> torch.Tensor:
 
 
 def conv_k_layout(m0: torch.Tensor, m1: torch.Tensor, s_in: int, v_in: int):
-    """Re-order the conv contraction weights m0 [65,U0,152], m1 [65,U1,32] into the K order of jamun_conv_build_a
-    (per radial channel: scalar slots zero-padded to 32, then the vector slots) -> (w0 [K0,152], w1 [K1,32])."""
+    """Re-order the conv contraction weights m0 [65,U0,152], m1 [65,U1,32] into the operands of the tensor-core path:
+    w0 [K0,152]  : 0e contraction in the K order of jamun_conv_build_a (per radial channel: scalar slots zero-padded to
+                   32, then the x_v.rhat slot);
+    w1 [K1,32]   : 1e contraction of the aggregated vector paths (per radial channel: x_v[c] slot, cross slot); None if v_in == 0;
+    wy [32*NS, 65*32] : per-node transform of the path 0e(x)1e->1e, wy[u, k'*32+w] = m1[k', u, w]."""
     ns = (s_in + 31) // 32
     K = m0.shape[0]
-
-    def pad_scalar(m):
-        out = torch.zeros(K, ns * 32, m.shape[2], dtype=m.dtype, device=m.device)
-        out[:, :s_in] = m[:, :s_in]
-        return out
-
-    w0 = [pad_scalar(m0)]
-    w1 = [pad_scalar(m1)]
+    pad = torch.zeros(K, ns * 32, m0.shape[2], dtype=m0.dtype, device=m0.device)
+    pad[:, :s_in] = m0[:, :s_in]
+    w0 = [pad]
+    w1 = None
     if v_in:
         assert v_in == 32
         w0.append(m0[:, s_in:s_in + v_in])
-        w1 += [m1[:, s_in:s_in + v_in], m1[:, s_in + v_in:s_in + 2 * v_in]]
-    w0 = torch.cat(w0, dim=1)
-    w1 = torch.cat(w1, dim=1)
-    return w0.reshape(-1, m0.shape[2]).contiguous(), w1.reshape(-1, m1.shape[2]).contiguous()
+        w1 = torch.cat([m1[:, s_in:s_in + v_in], m1[:, s_in + v_in:s_in + 2 * v_in]], dim=1).reshape(-1, m1.shape[2]).contiguous()
+    w0 = torch.cat(w0, dim=1).reshape(-1, m0.shape[2]).contiguous()
+    wy = torch.zeros(ns * 32, K * m1.shape[2], dtype=m1.dtype, device=m1.device)
+    wy[:s_in] = m1[:, :s_in].permute(1, 0, 2).reshape(s_in, -1)
+    return w0, w1, wy
+
+
+def pack_b_column_blocks(w: torch.Tensor, block: int = 160) -> torch.Tensor:
+    """w [K, N] with N % block == 0 -> [N/block, K/32, 2, block*32]: one pack_b_images per column block."""
+    K, N = w.shape
+    assert N % block == 0
+    return torch.stack([pack_b_images(w[:, c:c + block].contiguous(), block) for c in range(0, N, block)]).contiguous()

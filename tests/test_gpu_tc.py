@@ -106,3 +106,30 @@ def test_conv_tc_matches_simt_and_fp64(models, sizes):
         err = (got - ref).abs().max().item()
         scale = ref.abs().max().item()
         assert err <= 5e-5 * max(1.0, scale), f"block {l}: err {err} scale {scale}"  # tcgen05 fp32 accumulation truncates
+
+
+def test_gemm_column_blocks_and_addend():
+    """grid.y column blocks (wide per-node transform) and the epilogue addend."""
+    from jamun_b200 import ops, packing
+
+    gen = torch.Generator().manual_seed(3)
+    rows, K, N = 300, 128, 480
+    rows_pad = 384
+    A = torch.randn(rows, K, generator=gen)
+    W = torch.randn(K, N, generator=gen)
+    add = torch.randn(rows, 32, generator=gen)
+    a_op = torch.empty(K // 32 * rows_pad * 32, device="cuda")
+    ops.pack_rows(A.cuda(), 0, K, rows_pad, a_op)
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    img = packing.pack_b_column_blocks(W.cuda(), 160)
+    ops.gemm_tf32x3([a_op.data_ptr()], [img.data_ptr()], [K // 32], [160], [160], [0], [1.0], rows, rows_pad, None, out.data_ptr(), N,
+                    col_blocks=3, b_block_floats=K // 32 * 2 * 160 * 32)
+    ref = A.double() @ W.double()
+    assert (out.cpu().double() - ref).abs().max() <= 1e-5 * ref.abs().max()
+    out2 = torch.full((rows, 32), float("nan"), device="cuda")
+    img2 = packing.pack_b_images(W[:, :32].contiguous().cuda(), 32)
+    addc = add.cuda()
+    ops.gemm_tf32x3([a_op.data_ptr()], [img2.data_ptr()], [K // 32], [32], [32], [0], [0.5], rows, rows_pad, None, out2.data_ptr(), 32,
+                    addend_ptrs=[addc.data_ptr()], addend_ld=[32])
+    ref2 = 0.5 * (A.double() @ W[:, :32].double() + add.double())
+    assert (out2.cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
