@@ -18,6 +18,7 @@
 //   segment 1+c (1e, nslots1 = 2[V>0]):     slot 0 : x_v[c] / sqrt3          slot 1  : (x_v x rhat)[c] / sqrt2
 //   stage index = k' * nslots + slot;  element (stage, row, p) at ((stage * rows_pad) + row) * 32 + swz(p, row),
 //   swz = (((p / 4) ^ (row % 8)) * 4) + p % 4  (so the GEMM's per-row shared-memory reads are conflict-free).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -46,18 +47,19 @@ __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1,
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
 }
 
-template <int S_IN, int V_IN, int MINB>
+template <int S_IN, int V_IN, int RK, int MINB, bool CACHED>
 __global__ void __launch_bounds__(256, MINB)
 conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int row0,
                   int nrows, int rows_pad, float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride,
                   float* __restrict__ p2, int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
-    constexpr int RK = 4;
+    static_assert(RK == 4 || RK == 8, "RK must be 4 or 8");
     constexpr int NKB = JAMUN_EDGE_HID / RK;  // full blocks; block NKB is the bias channel (h' = 1)
     constexpr int D_IN = S_IN + 3 * V_IN;
     constexpr int NS = (S_IN + 31) / 32;
     constexpr int NSL0 = NS + (V_IN > 0 ? 1 : 0), NSL1 = V_IN > 0 ? 2 : 0;
-    __shared__ float4 meta_s[8][MAXD][2];  // per warp, per in-edge: {x row offset, y row offset, rx, ry}, {rz, -, -, -}
+    // per warp, per in-edge: {x row offset, y row offset, rx, ry}, {rz, -, -, -} (CACHED: every node has <= MAXD in-edges)
+    __shared__ float4 meta_s[CACHED ? 8 : 1][CACHED ? MAXD : 1][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // row within the chunk
     if (r >= nrows) return;
@@ -66,8 +68,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     const int deg = e1 - e0;
     const float invd = 1.0f / (float)(deg > 0 ? deg : 1);
     if (lane == 0) inv_deg[i] = invd;
-    const bool cached = deg <= MAXD;
-    if (cached) {
+    if (CACHED) {
         for (int t = lane; t < deg; t += 32) {
             const int j = col[e0 + t];
             const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(e0 + t));
@@ -80,6 +81,10 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     const bool s_load = 4 * lane < S_IN;
     const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);  // position of a 4-byte element owned by `lane`
     const int swz4 = ((lane & 7) ^ (r & 7)) << 2;                  // position of the 16-byte chunk of the scalar store
+    const float* xl = x + (s_load ? 4 * lane : 0);                 // lane-adjusted bases: per edge only `+ offset` remains
+    const float* xv = x + S_IN + lane;
+    const float* yl = y + lane;
+    const float* hrow = h + (size_t)e0 * JAMUN_EDGE_HID;
     float pacc[3] = {0.f, 0.f, 0.f};
 
     for (int kb = 0; kb <= NKB; ++kb) {
@@ -94,10 +99,12 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
 #pragma unroll
             for (int c = 0; c < 3; ++c) av[k][c] = ax[k][c] = 0.f;
         }
-        for (int t = 0; t < deg; ++t) {
+        const float* hk = hrow + kb * RK;
+        const float* yk = yl + kb * RK * JAMUN_V;
+        for (int t = 0; t < deg; ++t, hk += JAMUN_EDGE_HID) {
             int xoff, yoff;
             float rx, ry, rz;
-            if (cached) {
+            if (CACHED) {
                 const float4 m0 = meta_s[wib][t][0], m1 = meta_s[wib][t][1];
                 xoff = __float_as_int(m0.x);
                 yoff = __float_as_int(m0.y);
@@ -113,29 +120,43 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
                 ry = rh.y;
                 rz = rh.z;
             }
-            float4 hq4 = make_float4(1.f, 0.f, 0.f, 0.f);
-            if (!bias) hq4 = *reinterpret_cast<const float4*>(h + (size_t)(e0 + t) * JAMUN_EDGE_HID + kb * RK);
-            const float hq[RK] = {hq4.x, hq4.y, hq4.z, hq4.w};
-            const float* xj = x + xoff;
-            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s_load) xs = *reinterpret_cast<const float4*>(xj + 4 * lane);
-            // path 0e(x)1e->1e through the pre-transformed source rows
-            const float* yj = y + yoff + kb * RK * JAMUN_V + lane;
-            float ta = yj[0], tb = 0.f;
+            float hq[RK];
             if (!bias) {
-                const float y1 = yj[JAMUN_V], y2 = yj[2 * JAMUN_V], y3 = yj[3 * JAMUN_V];
-                ta *= hq[0];
-                ffma2v(ta, tb, hq[1], hq[2], y1, y2);
-                ta = fmaf(hq[3], y3, ta);
+#pragma unroll
+                for (int q = 0; q < RK / 4; ++q) {
+                    const float4 w = *reinterpret_cast<const float4*>(hk + 4 * q);
+                    hq[4 * q] = w.x;
+                    hq[4 * q + 1] = w.y;
+                    hq[4 * q + 2] = w.z;
+                    hq[4 * q + 3] = w.w;
+                }
+            } else {
+                hq[0] = 1.f;
+#pragma unroll
+                for (int k = 1; k < RK; ++k) hq[k] = 0.f;
             }
-            const float tsum = ta + tb;
+            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s_load) xs = *reinterpret_cast<const float4*>(xl + xoff);
+            // path 0e(x)1e->1e through the pre-transformed source rows
+            const float* yj = yk + yoff;
+            float tsum;
+            if (!bias) {
+                float ta = hq[0] * yj[0], tb = 0.f;
+#pragma unroll
+                for (int k = 1; k + 1 < RK; k += 2) ffma2v(ta, tb, hq[k], hq[k + 1], yj[k * JAMUN_V], yj[(k + 1) * JAMUN_V]);
+                ta = fmaf(hq[RK - 1], yj[(RK - 1) * JAMUN_V], ta);
+                tsum = ta + tb;
+            } else {
+                tsum = yj[0];
+            }
             ffma2(pacc[0], pacc[1], tsum, rx, ry);
             pacc[2] = fmaf(rz, tsum, pacc[2]);
             float vx = 0.f, vy = 0.f, vz = 0.f, q = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
             if (V_IN > 0) {
-                vx = xj[S_IN + lane];
-                vy = xj[S_IN + V_IN + lane];
-                vz = xj[S_IN + 2 * V_IN + lane];
+                const float* vj = xv + xoff;
+                vx = vj[0];
+                vy = vj[V_IN];
+                vz = vj[2 * V_IN];
                 q = vx * rx + vy * ry + vz * rz;
                 cx = vy * rz - vz * ry;
                 cy = vz * rx - vx * rz;
@@ -200,26 +221,39 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, int ld, int col0, 
 // a0: [65*nslots0][rows_pad][32]; a1: 3 x [65*2][rows_pad][32] (component stride a1_comp_stride floats; unused when v_in == 0);
 // y: [N, 65*32] pre-transformed source rows; p2: [N, p2_ld] path-2 sums (see the kernel for p2_scale).
 extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                                  const float* rhat, const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1,
-                                  long long a1_comp_stride, float* p2, int p2_ld, float p2_scale, float* inv_deg,
-                                  jamun_stream_t stream) {
+                                  const float* rhat, const float* y, int max_degree, int row0, int nrows, int rows_pad,
+                                  float* a0, float* a1, long long a1_comp_stride, float* p2, int p2_ld, float p2_scale,
+                                  float* inv_deg, jamun_stream_t stream) {
     JB_CHECK_ARG(x && rowptr && col && h && rhat && y && a0 && p2 && inv_deg, "null argument");
     JB_CHECK_ARG(nrows <= rows_pad, "nrows exceeds rows_pad");
     JB_CHECK_ARG(((size_t)x & 15) == 0 && ((size_t)a0 & 15) == 0, "x and a0 must be 16-byte aligned");
     if (nrows == 0) return JAMUN_OK;
     const int blocks = (nrows * 32 + 255) / 256;
     cudaStream_t s = jb::as_stream(stream);
+#define JB_LAUNCH_BUILD(S_, V_, RK_, MB_, C_)                                                                              \
+    conv_build_kernel<S_, V_, RK_, MB_, C_><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, \
+                                                                   (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
+    static int variant = -1;  // tuning knob for experiments (JAMUN_BUILD_VARIANT)
+    if (variant < 0) {
+        const char* v = getenv("JAMUN_BUILD_VARIANT");
+        variant = v ? atoi(v) : 1;
+    }
+    const bool cached = max_degree <= MAXD;
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
         JB_CHECK_ARG(a1, "a1 required for vector inputs");
-        conv_build_kernel<JAMUN_S, JAMUN_V, 3><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1,
-                                                                     (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
+        if (!cached) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, false);
+        else if (variant == 1) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, true);
+        else if (variant == 2) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 2, true);
+        else if (variant == 3) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 1, true);
+        else JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 3, true);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        conv_build_kernel<JAMUN_S0, 0, 3><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1,
-                                                                (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
+        if (!cached) JB_LAUNCH_BUILD(JAMUN_S0, 0, 4, 2, false);
+        else JB_LAUNCH_BUILD(JAMUN_S0, 0, 8, 3, true);
     } else {
         jb::set_error("jamun_conv_build_a: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;
     }
+#undef JB_LAUNCH_BUILD
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
