@@ -142,7 +142,9 @@ int jamun_head(const float* x, const float* w1_s, const float* w1_v, const float
  *             ybar = center(y); p = c_in*ybar                          (prologue of the next evaluation)
  * R = noise[N,3] if non-NULL else Philox4x32-10(seed, step) Box-Muller.  clip<=0 disables clipping.
  * traj_* may be NULL.  score_in non-NULL: use that score instead of deriving xhat/score from g (generic
- * score_fn protocol of mcmc/_splitting.py:56-58; g, xhat outputs are then ignored and may be NULL). */
+ * score_fn protocol of mcmc/_splitting.py:56-58; g, xhat outputs are then ignored and may be NULL).
+ * dev_state non-NULL (CUDA-graph replay): the Philox step is dev_state[0] and the trajectory frame written is
+ * traj_* + dev_state[1] * 3 * n_atoms; jamun_walk_advance(dev_state, slot_inc) bumps both between replays. */
 typedef struct {
     float c_in, c_skip, c_out, sigma2;
     float delta, u, a, z_sqrt_u, beta, clip;
@@ -152,7 +154,9 @@ typedef struct {
 
 int jamun_walk_step(float* y, float* v, float* ybar, float* p, const float* g, const float* score_in,
                     const int* chain_ptr, int G, const jamun_walk_params* prm, const float* noise, float* xhat, float* score,
-                    float* traj_y, float* traj_xhat, float* traj_score, jamun_stream_t stream);
+                    float* traj_y, float* traj_xhat, float* traj_score, const unsigned long long* dev_state,
+                    jamun_stream_t stream);
+int jamun_walk_advance(unsigned long long* dev_state, int slot_inc, jamun_stream_t stream);
 
 /* out = a*x + b*noise with noise = given or Philox (initial y = x + sigma*eps, v0 = sqrt(u)*eps;
  * utils/sampling_wrapper.py:21-24, functional/_splitting.py:11-23). */

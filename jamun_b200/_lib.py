@@ -38,7 +38,8 @@ _PROTOS = {
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
     "jamun_block_tail": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_head": ([c_f, c_f, c_f, c_f, F, I, c_f, c_f], I),
-    "jamun_walk_step": ([c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, C.POINTER(WalkParams), c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_walk_step": ([c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, C.POINTER(WalkParams), c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_walk_advance": ([c_f, I, c_f], I),
     "jamun_aboba_drift": ([c_f, c_f, F, I, c_f], I),
     "jamun_aboba_kick": ([c_f, c_f, c_f, C.POINTER(WalkParams), c_f, I, c_f], I),
     "jamun_gaussian_axpy": ([c_f, F, F, c_f, ULL, ULL, I, c_f, c_f], I),

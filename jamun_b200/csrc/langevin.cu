@@ -12,9 +12,16 @@ __global__ void walk_step_kernel(float* __restrict__ y, float* __restrict__ v, f
                                  int G, jamun_walk_params prm, float sigma2, float half_delta, float u_half_delta,
                                  const float* __restrict__ noise, float* __restrict__ xhat, float* __restrict__ score,
                                  float* __restrict__ traj_y, float* __restrict__ traj_xhat,
-                                 float* __restrict__ traj_score) {
+                                 float* __restrict__ traj_score, const unsigned long long* __restrict__ dev_state) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (chain >= G) return;
+    if (dev_state) {  // graph replay: step counter and trajectory frame live in device memory
+        prm.step = dev_state[0];
+        const size_t off = (size_t)dev_state[1] * 3 * (size_t)chain_ptr[G];
+        if (traj_y) traj_y += off;
+        if (traj_xhat) traj_xhat += off;
+        if (traj_score) traj_score += off;
+    }
     const int lo = chain_ptr[chain], hi = chain_ptr[chain + 1];
     const float inv_n = 1.0f / fmaxf(1.0f, (float)(hi - lo));
 
@@ -194,7 +201,7 @@ __global__ void atom_embed_kernel(const int* __restrict__ i0, const int* __restr
 extern "C" int jamun_walk_step(float* y, float* v, float* ybar, float* p, const float* g, const float* score_in,
                                const int* chain_ptr, int G, const jamun_walk_params* prm, const float* noise,
                                float* xhat, float* score, float* traj_y, float* traj_xhat, float* traj_score,
-                               jamun_stream_t stream) {
+                               const unsigned long long* dev_state, jamun_stream_t stream) {
     JB_CHECK_ARG(y && v && ybar && p && (g || score_in) && chain_ptr && prm, "null argument");
     if (G == 0) return JAMUN_OK;
     const float sigma2 = prm->sigma2;
@@ -203,7 +210,19 @@ extern "C" int jamun_walk_step(float* y, float* v, float* ybar, float* p, const 
     int blocks = (G * 32 + 255) / 256;
     walk_step_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(y, v, ybar, p, g, score_in, chain_ptr, G, *prm, sigma2, half_delta,
                                                                 u_half_delta, noise, xhat, score, traj_y, traj_xhat,
-                                                                traj_score);
+                                                                traj_score, dev_state);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+__global__ void walk_advance_kernel(unsigned long long* st, int slot_inc) {
+    st[0] += 1;
+    st[1] += (unsigned long long)slot_inc;
+}
+
+extern "C" int jamun_walk_advance(unsigned long long* dev_state, int slot_inc, jamun_stream_t stream) {
+    JB_CHECK_ARG(dev_state, "null argument");
+    walk_advance_kernel<<<1, 1, 0, jb::as_stream(stream)>>>(dev_state, slot_inc);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -162,13 +162,19 @@ def head(x, w1_s, w1_v, w2, c_gate: float, g):
 
 
 def walk_step(y, v, ybar, p, g, chain_ptr, prm: "_lib.WalkParams", noise, xhat, score, traj_y=None, traj_xhat=None,
-              traj_score=None, score_in=None):
+              traj_score=None, score_in=None, dev_state=None):
     G = chain_ptr.numel() - 1
     rc = _lib.lib().jamun_walk_step(_ptr(y), _ptr(v), _ptr(ybar), _ptr(p), _ptr(g), _ptr(score_in),
                                     _ptr(chain_ptr, torch.int32), G,
                                     C.byref(prm), _ptr(noise), _ptr(xhat), _ptr(score), _ptr(traj_y), _ptr(traj_xhat),
-                                    _ptr(traj_score), _stream())
+                                    _ptr(traj_score), _ptr(dev_state, torch.int64), _stream())
     _lib.check(rc, "jamun_walk_step")
+    _count()
+
+
+def walk_advance(dev_state, slot_inc: int):
+    rc = _lib.lib().jamun_walk_advance(_ptr(dev_state, torch.int64), int(slot_inc), _stream())
+    _lib.check(rc, "jamun_walk_advance")
     _count()
 
 

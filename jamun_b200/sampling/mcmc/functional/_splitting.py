@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
 from typing import Callable, Optional, Tuple, Union
 
 import torch
@@ -137,12 +138,26 @@ def aboba(y: torch.Tensor, score_fn: Callable, steps: int, v_init: Union[str, to
     return y, v, y_traj, score_traj
 
 
+class _WalkWorkspace:
+    """Persistent device buffers of the fused walk (so CUDA graphs captured once can be replayed across calls)."""
+
+    def __init__(self, N: int, T: int, score_rows: int, save: bool, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.y, self.v, self.ybar, self.p, self.g, self.xhat, self.score = (torch.empty(N, 3, **f32) for _ in range(7))
+        self.y_traj = torch.empty(T, N, 3, **f32) if save else None
+        self.xhat_traj = torch.empty(T, N, 3, **f32) if save else None
+        self.score_traj = torch.empty(score_rows, N, 3, **f32)
+        self.state = torch.zeros(2, dtype=torch.int64, device=device)  # [philox step, trajectory slot]
+        self.graphs = {}
+
+
 def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, steps: int,
                 v_init: Union[str, torch.Tensor] = "zero", save_trajectory=False, save_every_n_steps=1, burn_in_steps=0,
                 verbose=False, cpu_offload=False, delta: float = 1.0, friction: float = 1.0, M: float = 1.0,
                 inverse_temperature: float = 1.0, score_fn_clip: Optional[float] = None,
-                noise: Optional[torch.Tensor] = None, **_):
-    """Walk-jump hot loop: per step [K1 radius CSR, K2 edge features, 6x(radial MLP, conv, tail), head, K6 step].
+                noise: Optional[torch.Tensor] = None, use_cuda_graph: Optional[bool] = None, **_):
+    """Walk-jump hot loop: per step [K1 radius CSR, K2 edge features, 6x(radial MLP, transform, aggregate, GEMM, tail),
+    head, K6 step].  Steady-state steps are replayed from a CUDA graph (step counter / trajectory slot in device memory).
 
     Returns dict(y, v, xhat, y_traj, xhat_traj, score_traj).  xhat / xhat_traj are the jumps at the final and at
     every saved y -- by-products of the score evaluation, not a second pass."""
@@ -151,38 +166,91 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
     ctx = model.sigma_context(sigma)
     plan = model.arch_module.plan(ctx.c_noise, y.device)
     mu, rb_step = plan.radial_grid(ctx.r_cut)
-    y = y.contiguous().clone()
     sid = next(_call_counter)
     u = pow(M, -1)
-    v = initialize_velocity(v_init, y, u, None if noise is None else noise[0].contiguous(), sid)
-    prm = _walk_params(delta, friction, M, inverse_temperature, score_fn_clip)
-    prm.c_in, prm.c_skip, prm.c_out, prm.sigma2 = ctx.c_in, ctx.c_skip, ctx.c_out, ctx.sigma2
-    prm.center = int(model.mean_center)
     N = y.shape[0]
     saved = [i for i in range(steps) if _saves(i, save_trajectory, save_every_n_steps, burn_in_steps)]
     slot = {i: k for k, i in enumerate(saved)}
     score_first_extra = bool(save_trajectory) and 0 not in slot  # reference keeps score(y_init) regardless of burn-in
     T = len(saved)
-    f32 = dict(dtype=torch.float32, device=y.device)
-    y_traj = torch.empty(T, N, 3, **f32) if save_trajectory else None
-    xhat_traj = torch.empty(T, N, 3, **f32) if save_trajectory else None
-    score_traj = torch.empty(T + int(score_first_extra), N, 3, **f32) if save_trajectory else torch.empty(1, N, 3, **f32)
     off = int(score_first_extra)
-    xhat, score, g = torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
-    ybar, p = ops.center_scale(y, topo.chain_ptr, ctx.c_in, center=model.mean_center)
-    for i in range(steps):
-        topo.build_csr(ybar, ctx.r_cut)
-        engine.e3conv_forward(plan, topo, p, ctx.r_cut, g, mu, rb_step)
+    score_rows = T + off if save_trajectory else 1
+    key = (T, score_rows, bool(save_trajectory))
+    cache = topo.__dict__.setdefault("_walk_ws", {})
+    ws = cache.get(key)
+    if ws is None:
+        if len(cache) > 4:
+            cache.clear()
+        ws = cache[key] = _WalkWorkspace(N, T, score_rows, bool(save_trajectory), y.device)
+    ws.y.copy_(y)
+    ws.v.copy_(initialize_velocity(v_init, ws.y, u, None if noise is None else noise[0].contiguous(), sid))
+    prm = _walk_params(delta, friction, M, inverse_temperature, score_fn_clip)
+    prm.c_in, prm.c_skip, prm.c_out, prm.sigma2 = ctx.c_in, ctx.c_skip, ctx.c_out, ctx.sigma2
+    prm.center = int(model.mean_center)
+    score_view = ws.score_traj[off:] if save_trajectory else None
+
+    def denoise():
+        topo.build_csr(ws.ybar, ctx.r_cut)
+        engine.e3conv_forward(plan, topo, ws.p, ctx.r_cut, ws.g, mu, rb_step)
+
+    def eager_step(i):
+        denoise()
         prm.first, prm.last = int(i == 0), int(i == steps - 1)
         prm.step = (sid << 32) + i + 1
         k = slot.get(i)
-        ty = y_traj[k] if k is not None else None
-        tx = xhat_traj[k] if k is not None else None
-        ts = score_traj[k + off] if k is not None else (score_traj[0] if i == 0 else None)
+        ty = ws.y_traj[k] if k is not None else None
+        tx = ws.xhat_traj[k] if k is not None else None
+        ts = ws.score_traj[k + off] if k is not None else (ws.score_traj[0] if i == 0 else None)
         nz = None if noise is None or i + 1 >= noise.shape[0] else noise[i + 1].contiguous()
-        ops.walk_step(y, v, ybar, p, g, topo.chain_ptr, prm, nz, xhat, score, ty, tx, ts)
+        ops.walk_step(ws.y, ws.v, ws.ybar, ws.p, ws.g, topo.chain_ptr, prm, nz, ws.xhat, ws.score, ty, tx, ts)
+
+    ops.center_scale(ws.y, topo.chain_ptr, ctx.c_in, ws.ybar, ws.p, center=model.mean_center)
+    if use_cuda_graph is None:
+        use_cuda_graph = noise is None and steps >= 4 and os.environ.get("JAMUN_B200_GRAPH", "1") != "0"
+    if not use_cuda_graph:
+        for i in range(steps):
+            eager_step(i)
+    else:
+        eager_step(0)  # also warms up every lazily allocated workspace before capture
+        gkey = (id(plan), float(delta), float(friction), float(M), float(inverse_temperature), score_fn_clip,
+                float(sigma), int(model.mean_center), int(prm.seed))
+
+        def graph_for(save: bool):
+            g = ws.graphs.get((gkey, save))
+            if g is None:
+                prm.first, prm.last = 0, 0
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    denoise()
+                    ops.walk_step(ws.y, ws.v, ws.ybar, ws.p, ws.g, topo.chain_ptr, prm, None, ws.xhat, ws.score,
+                                  ws.y_traj if save else None, ws.xhat_traj if save else None, score_view if save else None,
+                                  dev_state=ws.state)
+                    ops.walk_advance(ws.state, 1 if save else 0)
+                ws.graphs[(gkey, save)] = g
+            return g
+
+        first_slot = 1 if 0 in slot else 0
+        ws.state.copy_(torch.tensor([(sid << 32) + 2, first_slot], dtype=torch.int64))
+        if steps > 2:
+            # capture (does not execute) before the replay loop so the device state is untouched by capture
+            needed = {i in slot for i in range(1, steps - 1)}
+            graphs = {s: graph_for(s) for s in needed}
+            for i in range(1, steps - 1):
+                graphs[i in slot].replay()
+                ops._count(ws_launches(plan))
+        if steps > 1:
+            eager_step(steps - 1)
+    out_y, out_v, out_x = ws.y.clone(), ws.v.clone(), ws.xhat.clone()
+    y_traj = ws.y_traj.clone() if ws.y_traj is not None else None
+    xhat_traj = ws.xhat_traj.clone() if ws.xhat_traj is not None else None
+    score_traj = ws.score_traj.clone()
     if cpu_offload:
         y_traj = y_traj.cpu() if y_traj is not None else None
         xhat_traj = xhat_traj.cpu() if xhat_traj is not None else None
         score_traj = score_traj.cpu()
-    return {"y": y, "v": v, "xhat": xhat, "y_traj": y_traj, "xhat_traj": xhat_traj, "score_traj": score_traj}
+    return {"y": out_y, "v": out_v, "xhat": out_x, "y_traj": y_traj, "xhat_traj": xhat_traj, "score_traj": score_traj}
+
+
+def ws_launches(plan) -> int:
+    """Kernel launches inside one replayed walk-jump step (for bench.py's gpu_launches claim)."""
+    return 3 + 1 + len(plan.blocks) * 6 + 1 + 2

@@ -281,3 +281,27 @@ def test_no_cpu_fallback():
 
     with pytest.raises(RuntimeError):
         ops.center_scale(torch.zeros(3, 3), torch.tensor([0, 3], dtype=torch.int32), 1.0)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(models):
+    """Steady-state steps replayed from a CUDA graph (device-side step counter / trajectory slot) == eager launches."""
+    import itertools
+
+    from jamun_b200 import data, utils
+    from jamun_b200.sampling.mcmc.functional import _splitting, fused_baoab
+
+    o32, o64, prod, t, y = _setup(models, [22, 15, 9, 30, 12], seed=9)
+    batch = data.Batch.from_tensors(t).to("cuda")
+    topo = prod.topology_for(batch)
+    kw = dict(steps=9, v_init="gaussian", save_trajectory=True, save_every_n_steps=2, burn_in_steps=3, delta=0.04, friction=1.0,
+              M=1.0, inverse_temperature=1.0, score_fn_clip=100.0)
+    outs = []
+    for use_graph in (False, True, True):
+        torch.manual_seed(123)
+        _splitting._call_counter = itertools.count(1)
+        outs.append(fused_baoab(prod, topo, y.cuda(), SIGMA, use_cuda_graph=use_graph, **kw))
+    for key in ("y", "v", "xhat", "y_traj", "xhat_traj", "score_traj"):
+        assert outs[0][key].shape == outs[1][key].shape
+        assert torch.equal(outs[0][key], outs[1][key]), key
+        assert torch.equal(outs[0][key], outs[2][key]), key  # cached graph, second use
+    assert outs[0]["y_traj"].shape[0] == 3 and outs[0]["score_traj"].shape[0] == 4  # frames 4,6,8 (+ the initial score)
