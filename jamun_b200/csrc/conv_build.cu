@@ -47,7 +47,8 @@ __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1,
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
 }
 
-template <int S_IN, int V_IN, int RK, int MINB, bool CACHED>
+// ROLE 0: scalar operand slots + path-2 gather;  ROLE 1: vector operand slots;  ROLE 2: both (one warp does everything)
+template <int S_IN, int V_IN, int RK, int MINB, bool CACHED, int ROLE>
 __global__ void __launch_bounds__(256, MINB)
 conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int row0,
@@ -67,7 +68,8 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
     const int deg = e1 - e0;
     const float invd = 1.0f / (float)(deg > 0 ? deg : 1);
-    if (lane == 0) inv_deg[i] = invd;
+    constexpr bool DO_S = ROLE != 1, DO_V = ROLE != 0 && V_IN > 0;
+    if (lane == 0 && DO_S) inv_deg[i] = invd;
     if (CACHED) {
         for (int t = lane; t < deg; t += 32) {
             const int j = col[e0 + t];
@@ -136,23 +138,25 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
                 for (int k = 1; k < RK; ++k) hq[k] = 0.f;
             }
             float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s_load) xs = *reinterpret_cast<const float4*>(xl + xoff);
-            // path 0e(x)1e->1e through the pre-transformed source rows
-            const float* yj = yk + yoff;
-            float tsum;
-            if (!bias) {
-                float ta = hq[0] * yj[0], tb = 0.f;
+            if (DO_S) {
+                if (s_load) xs = *reinterpret_cast<const float4*>(xl + xoff);
+                // path 0e(x)1e->1e through the pre-transformed source rows
+                const float* yj = yk + yoff;
+                float tsum;
+                if (!bias) {
+                    float ta = hq[0] * yj[0], tb = 0.f;
 #pragma unroll
-                for (int k = 1; k + 1 < RK; k += 2) ffma2v(ta, tb, hq[k], hq[k + 1], yj[k * JAMUN_V], yj[(k + 1) * JAMUN_V]);
-                ta = fmaf(hq[RK - 1], yj[(RK - 1) * JAMUN_V], ta);
-                tsum = ta + tb;
-            } else {
-                tsum = yj[0];
+                    for (int k = 1; k + 1 < RK; k += 2) ffma2v(ta, tb, hq[k], hq[k + 1], yj[k * JAMUN_V], yj[(k + 1) * JAMUN_V]);
+                    ta = fmaf(hq[RK - 1], yj[(RK - 1) * JAMUN_V], ta);
+                    tsum = ta + tb;
+                } else {
+                    tsum = yj[0];
+                }
+                ffma2(pacc[0], pacc[1], tsum, rx, ry);
+                pacc[2] = fmaf(rz, tsum, pacc[2]);
             }
-            ffma2(pacc[0], pacc[1], tsum, rx, ry);
-            pacc[2] = fmaf(rz, tsum, pacc[2]);
             float vx = 0.f, vy = 0.f, vz = 0.f, q = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-            if (V_IN > 0) {
+            if (DO_V) {
                 const float* vj = xv + xoff;
                 vx = vj[0];
                 vy = vj[V_IN];
@@ -164,9 +168,11 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
             }
 #pragma unroll
             for (int k = 0; k < RK; ++k) {
-                ffma2(s0[k][0], s0[k][1], hq[k], xs.x, xs.y);
-                ffma2(s0[k][2], s0[k][3], hq[k], xs.z, xs.w);
-                if (V_IN > 0) {
+                if (DO_S) {
+                    ffma2(s0[k][0], s0[k][1], hq[k], xs.x, xs.y);
+                    ffma2(s0[k][2], s0[k][3], hq[k], xs.z, xs.w);
+                }
+                if (DO_V) {
                     ffma2(aq[k], av[k][0], hq[k], q, vx);
                     ffma2(av[k][1], av[k][2], hq[k], vy, vz);
                     ffma2(ax[k][0], ax[k][1], hq[k], cx, cy);
@@ -179,11 +185,11 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         for (int k = 0; k < RK; ++k) {
             if (k >= nk) break;
             const int kp = kb * RK + k;
-            if (s_live) {
+            if (s_live && DO_S) {
                 float* ps = a0 + ((size_t)(kp * NSL0 + (lane >> 3)) * rows_pad + r) * 32 + swz4;
                 __stcs(reinterpret_cast<float4*>(ps), make_float4(s0[k][0], s0[k][1], s0[k][2], s0[k][3]));
             }
-            if (V_IN > 0) {
+            if (DO_V) {
                 __stcs(a0 + ((size_t)(kp * NSL0 + NS) * rows_pad + r) * 32 + swz, aq[k]);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -195,9 +201,11 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         }
     }
     // path-2 sums: raw (p2_scale == 0; the GEMM epilogue adds and scales them) or final (initial block: no 1e GEMM)
-    const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
+    if (DO_S) {
+        const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p2[(size_t)i * p2_ld + c * JAMUN_V + lane] = pacc[c] * sc;
+        for (int c = 0; c < 3; ++c) p2[(size_t)i * p2_ld + c * JAMUN_V + lane] = pacc[c] * sc;
+    }
 }
 
 // x[rows, ld] columns [col0, col0+ncols) -> stage-major chunk-swizzled A operand, zero padded to 32-column stages
@@ -230,9 +238,9 @@ extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int*
     if (nrows == 0) return JAMUN_OK;
     const int blocks = (nrows * 32 + 255) / 256;
     cudaStream_t s = jb::as_stream(stream);
-#define JB_LAUNCH_BUILD(S_, V_, RK_, MB_, C_)                                                                              \
-    conv_build_kernel<S_, V_, RK_, MB_, C_><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, \
-                                                                   (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
+#define JB_LAUNCH_BUILD(S_, V_, RK_, MB_, C_, R_)                                                                             \
+    conv_build_kernel<S_, V_, RK_, MB_, C_, R_><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0,  \
+                                                                       a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
     static int variant = -1;  // tuning knob for experiments (JAMUN_BUILD_VARIANT)
     if (variant < 0) {
         const char* v = getenv("JAMUN_BUILD_VARIANT");
@@ -241,14 +249,18 @@ extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int*
     const bool cached = max_degree <= MAXD;
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
         JB_CHECK_ARG(a1, "a1 required for vector inputs");
-        if (!cached) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, false);
-        else if (variant == 1) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, true);
-        else if (variant == 2) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 2, true);
-        else if (variant == 3) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 1, true);
-        else JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 3, true);
+        if (!cached) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, false, 2);
+        else if (variant == 1) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, true, 2);
+        else if (variant == 2) {  // split roles, 4 channels per pass
+            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 4, true, 0);
+            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 4, true, 1);
+        } else {                  // split roles, 8 channels per pass
+            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 3, true, 0);
+            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 2, true, 1);
+        }
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        if (!cached) JB_LAUNCH_BUILD(JAMUN_S0, 0, 4, 2, false);
-        else JB_LAUNCH_BUILD(JAMUN_S0, 0, 8, 3, true);
+        if (!cached) JB_LAUNCH_BUILD(JAMUN_S0, 0, 4, 2, false, 2);
+        else JB_LAUNCH_BUILD(JAMUN_S0, 0, 8, 3, true, 2);
     } else {
         jb::set_error("jamun_conv_build_a: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;

@@ -176,35 +176,35 @@ __global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restr
 }
 
 // ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0r[o][k] rb[e][k] + b0eff[flag][o]) --------
+// 64 threads per edge stream (thread = output channel o, its weight row held in registers); each pair of warps walks a
+// strided list of edges: 8 uniform 16-byte loads of the edge's radial basis, 32 FMAs, one coalesced 256-byte store.
 __global__ void __launch_bounds__(256) edge_radial_hidden_kernel(const float* __restrict__ rb,
                                                                  const unsigned char* __restrict__ ebond,
                                                                  const int* __restrict__ rowptr, int N,
                                                                  const float* __restrict__ w0r,
                                                                  const float* __restrict__ b0eff,
                                                                  float* __restrict__ h) {
-    __shared__ float w_s[JAMUN_EDGE_HID][JAMUN_NBASIS + 1];
-    __shared__ float b_s[2][JAMUN_EDGE_HID];
-    __shared__ float rb_s[4][JAMUN_NBASIS];
-    const int tid = threadIdx.x;
-    for (int t = tid; t < JAMUN_EDGE_HID * JAMUN_NBASIS; t += 256) w_s[t / JAMUN_NBASIS][t % JAMUN_NBASIS] = w0r[t];
-    if (tid < 2 * JAMUN_EDGE_HID) b_s[tid / JAMUN_EDGE_HID][tid % JAMUN_EDGE_HID] = b0eff[tid];
-    const int E = rowptr[N];
-    const int o = tid & 63, sub = tid >> 6;
-    for (int e0 = blockIdx.x * 4; e0 < E; e0 += gridDim.x * 4) {
-        __syncthreads();
-        if (tid < 4 * JAMUN_NBASIS) {
-            int e = e0 + tid / JAMUN_NBASIS;
-            rb_s[tid / JAMUN_NBASIS][tid % JAMUN_NBASIS] = e < E ? rb[(size_t)e * JAMUN_NBASIS + tid % JAMUN_NBASIS] : 0.f;
-        }
-        __syncthreads();
-        int e = e0 + sub;
-        if (e < E) {
-            float acc = 0.f;
+    const int o = threadIdx.x & 63;
+    const int stream = (blockIdx.x * blockDim.x + threadIdx.x) >> 6;
+    const int nstreams = (gridDim.x * blockDim.x) >> 6;
+    float w[JAMUN_NBASIS];
 #pragma unroll
-            for (int k = 0; k < JAMUN_NBASIS; ++k) acc = fmaf(w_s[o][k], rb_s[sub][k], acc);
-            acc += b_s[ebond[e] ? 1 : 0][o];
-            h[(size_t)e * JAMUN_EDGE_HID + o] = siluf_acc(acc);
+    for (int k = 0; k < JAMUN_NBASIS; ++k) w[k] = w0r[o * JAMUN_NBASIS + k];
+    const float b0 = b0eff[o], b1 = b0eff[JAMUN_EDGE_HID + o];
+    const int E = rowptr[N];
+    for (int e = stream; e < E; e += nstreams) {
+        const float4* r4 = reinterpret_cast<const float4*>(rb + (size_t)e * JAMUN_NBASIS);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < JAMUN_NBASIS / 4; ++q) {
+            const float4 v = __ldg(r4 + q);
+            acc0 = fmaf(w[4 * q], v.x, acc0);
+            acc1 = fmaf(w[4 * q + 1], v.y, acc1);
+            acc0 = fmaf(w[4 * q + 2], v.z, acc0);
+            acc1 = fmaf(w[4 * q + 3], v.w, acc1);
         }
+        const float acc = acc0 + acc1 + (ebond[e] ? b1 : b0);
+        h[(size_t)e * JAMUN_EDGE_HID + o] = siluf_acc(acc);
     }
 }
 
@@ -283,7 +283,7 @@ extern "C" int jamun_edge_radial_hidden(const float* rb, const unsigned char* eb
     JB_CHECK_ARG(rb && ebond && rowptr && w0r && b0eff && h, "null argument");
     if (N == 0 || cap == 0) return JAMUN_OK;
     int blocks = (cap + 3) / 4;
-    int max_blocks = jb::kNumSMs * 8;
+    int max_blocks = jb::kNumSMs * 8;  // 8 resident CTAs x 4 edge streams per SM
     if (blocks > max_blocks) blocks = max_blocks;
     edge_radial_hidden_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h);
     JB_CHECK_LAUNCH();

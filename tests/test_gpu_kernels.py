@@ -148,7 +148,7 @@ def test_network_layers_vs_oracle(models, sizes):
     assert err <= 1e-5, f"g err {err}"
 
 
-@pytest.mark.parametrize("sizes", [[22] * 8, [9, 29, 17, 12, 25], [57, 41, 36, 17]])
+@pytest.mark.parametrize("sizes", [[22] * 8, [9, 29, 17, 12, 25], [57, 41, 36, 17], [300, 5]])
 def test_xhat_score_parity(models, sizes):
     """north_star tolerance: denoised coordinates and scores within rtol 1e-4 / atol 1e-5 (fp32), teacher-forced."""
     from jamun_b200 import data
