@@ -296,7 +296,7 @@ def run_native(args):
     _engine.conv_tc(topo, blk, x_in, topo.conv)
     nrows = min(rp, atoms)
     base = topo.a_ws.data_ptr()
-    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, topo.max_degree, 0, nrows, rp,
+    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, 0, nrows, rp,
                                                     base, base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg))
     p2 = topo.p2.data_ptr()
     gemm_ms = time_kernel(lambda: ops.gemm_tf32x3(

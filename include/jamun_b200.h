@@ -99,6 +99,8 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  *     The path 0e(x)1e->1e is gathered from y[N, 65*32] = x_s . W (pre-transformed source rows) into p2[N, p2_ld]:
  *     p2[i, c*32+w] = sum_e rhat_e[c] sum_k' h'_e[k'] y[src_e, k'*32+w], multiplied by p2_scale/deg when p2_scale != 0.
  *     max_degree: an upper bound of the in-degree of every node (<= 64 selects the shared-memory-cached fast kernel).
+ *     chain_of/chain_ptr/src_max (optional): src_max = the largest number of nodes in the chains spanned by any aligned
+ *     block of 8 consecutive nodes; when it fits, the block-staged kernel (sources of x / Y in shared memory) is used.
  * (2) jamun_gemm_tf32x3: out[r, out_col[s] + n] = row_scale[r] * alpha[s] * sum_K A_s[r,K] B_s[K,n] for up to 4 segments,
  *     tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy), accumulators in TMEM.  b[s] is the weight operand
  *     pre-packed per stage as (hi | lo) images in the UMMA K-major SWIZZLE_128B shared-memory layout
@@ -109,9 +111,9 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  * (3) jamun_pack_rows: copies columns [col0, col0+ncols) of a row-major matrix into the GEMM's stage-major, chunk-swizzled
  *     A layout ([ceil(ncols/32)][rows_pad][32], zero padded). */
 int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                       const float* rhat, const float* y, int max_degree, int row0, int nrows, int rows_pad, float* a0,
-                       float* a1, long long a1_comp_stride, float* p2, int p2_ld, float p2_scale, float* inv_deg,
-                       jamun_stream_t stream);
+                       const float* rhat, const float* y, const int* chain_of, const int* chain_ptr, int src_max,
+                       int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride,
+                       float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream);
 int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,

@@ -32,7 +32,7 @@ _PROTOS = {
     "jamun_edge_geom": ([c_f, c_f, c_f, c_f, I, I, c_f, F, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
-    "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
+    "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
