@@ -53,6 +53,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def measured_traffic(args, atoms):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload only)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if args.workload == "2AA" and (args.chains or 1024) == 1024:
+            return d["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -314,7 +327,7 @@ def run_native(args):
     tf32_peak = pk["bf16_tflops"] / 2.0
     roofline = {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
                 "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": measured_traffic(args, atoms),
                 "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
                 "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
                 "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
