@@ -171,6 +171,11 @@ int jamun_aboba_kick(float* y, float* v, const float* score, const jamun_walk_pa
 int jamun_gaussian_axpy(const float* x, float a, float b, const float* noise, unsigned long long seed,
                         unsigned long long step, int n_atoms, float* out, jamun_stream_t stream);
 
+/* Dense layer used by the module-level compatibility forwards (ScalarMLP of e3tools/nn/_mlp.py:10-34 on arbitrary
+ * edge_attr): out[r, o] = act(sum_k w[o, k] in[r, k] + b[o]); act 0 = identity, 1 = SiLU. */
+int jamun_linear_act(const float* in, const float* w, const float* b, int rows, int K, int O, int act, float* out,
+                     jamun_stream_t stream);
+
 /* e3nn layout <-> SoA layout for `s x0e + v x1e` rows. */
 int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);
 int jamun_layout_from_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);

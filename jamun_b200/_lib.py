@@ -43,6 +43,7 @@ _PROTOS = {
     "jamun_aboba_drift": ([c_f, c_f, F, I, c_f], I),
     "jamun_aboba_kick": ([c_f, c_f, c_f, C.POINTER(WalkParams), c_f, I, c_f], I),
     "jamun_gaussian_axpy": ([c_f, F, F, c_f, ULL, ULL, I, c_f, c_f], I),
+    "jamun_linear_act": ([c_f, c_f, c_f, I, I, I, I, c_f, c_f], I),
     "jamun_layout_to_soa": ([c_f, I, I, I, c_f, c_f], I),
     "jamun_layout_from_soa": ([c_f, I, I, I, c_f, c_f], I),
 }

@@ -280,3 +280,25 @@ extern "C" int jamun_atom_embed(const int* idx0, const int* idx1, const int* idx
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
+
+// ---- generic dense layer for module-level (compatibility) forwards: out[e][o] = act(sum_k w[o][k] in[e][k] + b[o]) ---------
+namespace {
+__global__ void linear_act_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                                  int rows, int K, int O, int act, float* __restrict__ out) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)rows * O; t += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t / O), o = (int)(t % O);
+        float acc = b ? b[o] : 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(w[(size_t)o * K + k], in[(size_t)e * K + k], acc);
+        out[t] = act == 1 ? jb::siluf_acc(acc) : acc;
+    }
+}
+}  // namespace
+
+extern "C" int jamun_linear_act(const float* in, const float* w, const float* b, int rows, int K, int O, int act, float* out,
+                                jamun_stream_t stream) {
+    JB_CHECK_ARG(in && w && out && K > 0 && O > 0, "bad argument");
+    if (rows == 0) return JAMUN_OK;
+    linear_act_kernel<<<jb::kNumSMs * 8, 256, 0, jb::as_stream(stream)>>>(in, w, b, rows, K, O, act, out);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}

@@ -72,6 +72,41 @@ class Conv(torch.nn.Module):
     def irreps_in1_mul(self, i1: int) -> int:
         return self.irreps_in[i1][0]
 
+    # ---- module-level forwards with the reference's signatures (compatibility path; the sampler uses engine.conv_tc).
+    # Host-side glue (edge sort, layout permutations) is torch; the arithmetic runs in jamun_linear_act + jamun_conv_fwd.
+    def _run(self, x_nodes, src, dst, n_recv, edge_attr, edge_sh):
+        from ... import ops
+
+        dev = x_nodes.device
+        pk = self.pack(torch.zeros(2, self.edge_attr_dim // 2, device=dev))
+        lins = [m for m in self.radial_nn if isinstance(m, torch.nn.Linear)]
+        order = torch.sort(dst, stable=True).indices
+        rowptr = torch.zeros(n_recv + 1, dtype=torch.long, device=dev)
+        rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_recv), 0)
+        col = src[order].to(torch.int32).contiguous()
+        h = ops.linear_act(edge_attr[order].contiguous().float(), lins[0].weight.detach().contiguous(),
+                           lins[0].bias.detach().contiguous(), act=1)
+        sh = edge_sh[order].float()
+        rhat = torch.zeros(sh.shape[0], 4, device=dev)
+        rhat[:, :3] = sh[:, 1:4] / math.sqrt(3.0)
+        s_in, v_in = pk["s_in"], pk["v_in"]
+        xs = ops.layout_to_soa(x_nodes.contiguous().float(), s_in, v_in) if v_in else x_nodes.contiguous().float()
+        out = torch.empty(n_recv, 248, device=dev)
+        ops.conv_fwd(xs, s_in, v_in, rowptr.to(torch.int32), col, h, rhat.contiguous(), pk["m0"].detach().contiguous(),
+                     pk["m1"].detach().contiguous(), pk["alpha0"], pk["alpha1"], out)
+        return ops.layout_from_soa(out, 152, 32)
+
+    def apply_per_edge(self, node_attr_src, edge_attr, edge_sh):
+        """Per-edge messages tp(x_src, sh, radial_nn(edge_attr)) [E, 248] (each edge is its own receiver)."""
+        E = node_attr_src.shape[0]
+        idx = torch.arange(E, device=node_attr_src.device)
+        return self._run(node_attr_src, idx, idx, E, edge_attr, edge_sh)
+
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh):
+        """[N, irreps_in.dim], [2,E], [E, edge_attr_dim], [E, 4] -> scatter-mean of the messages, [N, 248] (e3nn layout)."""
+        src, dst = edge_index
+        return self._run(node_attr, src, dst, node_attr.shape[0], edge_attr, edge_sh)
+
 
 class ConvBlock(torch.nn.Module):
     def __init__(self, irreps_in, irreps_out, irreps_sh, edge_attr_dim: int, act=None, act_gates=None,
@@ -87,6 +122,9 @@ class ConvBlock(torch.nn.Module):
     @property
     def conv(self) -> Conv:
         return self.gated_conv.f.f
+
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh):
+        return self.gated_conv(node_attr, edge_index, edge_attr, edge_sh)
 
     def pack(self, embed_bondedness: torch.Tensor):
         """Operands of jamun_conv_fwd + jamun_block_tail for this block."""

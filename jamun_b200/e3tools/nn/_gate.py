@@ -32,6 +32,19 @@ class Gate(torch.nn.Module):
         self.irreps_in = (scalars + gates + gated).simplify()
         self.c_act, self.c_gate = C_LEAKY_RELU, C_SIGMOID
 
+    def forward(self, x):
+        """Module-level compatibility forward: [scalars | gates | gated] -> [act(scalars) | gated * act(gates)] (elementwise glue)."""
+        ns, ng = self.irreps_scalars.dim, self.irreps_gates.dim
+        s = torch.nn.functional.leaky_relu(x[:, :ns], 0.01) * self.c_act
+        g = torch.sigmoid(x[:, ns:ns + ng]) * self.c_gate
+        v = x[:, ns + ng:]
+        outs, og, ov = [s], 0, 0
+        for m, ir in self.irreps_gated:
+            outs.append((v[:, ov:ov + m * ir.dim].reshape(-1, m, ir.dim) * g[:, og:og + m, None]).reshape(x.shape[0], -1))
+            og += m
+            ov += m * ir.dim
+        return torch.cat(outs, dim=1)
+
 
 class Gated(torch.nn.Module):
     def __init__(self, layer, irreps_in, irreps_out, act=None, act_gates=None):
@@ -40,3 +53,6 @@ class Gated(torch.nn.Module):
         self.gate = Gate(self.irreps_out, act=act, act_gates=act_gates)
         self.f = layer(irreps_in=self.irreps_in, irreps_out=self.gate.irreps_in)
         self.irreps_sh = self.f.irreps_sh
+
+    def forward(self, *args, **kwargs):
+        return self.gate(self.f(*args, **kwargs))

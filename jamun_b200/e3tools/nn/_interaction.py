@@ -13,3 +13,9 @@ class LinearSelfInteraction(torch.nn.Module):
         self.irreps_in, self.irreps_out = f.irreps_in, f.irreps_out
         self.skip_connection = Linear(self.irreps_in, self.irreps_out)
         self.self_interaction = Linear(self.irreps_out, self.irreps_out)
+
+    def forward(self, x, *args):
+        s = self.skip_connection(x)
+        x = self.f(x, *args)
+        x = self.self_interaction(x)
+        return x + s

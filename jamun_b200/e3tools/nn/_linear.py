@@ -60,5 +60,25 @@ class Linear(torch.nn.Module):
         return W.contiguous()
 
     def forward(self, x):
-        raise NotImplementedError(
-            "jamun_b200.e3tools.nn.Linear is evaluated inside the fused block kernels (jamun_block_tail / jamun_head)")
+        """Module-level compatibility forward (e3nn layout in/out); the sampler evaluates these inside the fused block kernels."""
+        from ... import ops
+
+        n = x.shape[0]
+        sl_in, outs = self.irreps_in.slices(), []
+        ls = sorted({ir.l for _, ir in self.irreps_out})
+        res = {}
+        for l in ls:
+            d = 2 * l + 1
+            blocks = [x[:, sl].reshape(n, m, d) for sl, (m, ir) in zip(sl_in, self.irreps_in) if ir.l == l]
+            cols = sum(m for m, ir in self.irreps_out if ir.l == l)
+            if not blocks:
+                res[l] = x.new_zeros(n, cols, d)
+                continue
+            xin = torch.cat(blocks, dim=1).permute(0, 2, 1).reshape(n * d, -1).contiguous().float()
+            w = self.packed(l).detach().T.contiguous()
+            res[l] = ops.linear_act(xin, w, None, act=0).reshape(n, d, cols).permute(0, 2, 1)
+        off = {l: 0 for l in ls}
+        for m, ir in self.irreps_out:
+            outs.append(res[ir.l][:, off[ir.l]:off[ir.l] + m].reshape(n, -1))
+            off[ir.l] += m
+        return torch.cat(outs, dim=1)

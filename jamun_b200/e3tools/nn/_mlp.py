@@ -33,6 +33,9 @@ class EquivariantMLPBlock(torch.nn.Module):
         self.lin = Linear(self.irreps_in, self.gate.irreps_in)
         self.norm = None
 
+    def forward(self, x):
+        return self.gate(self.lin(x))
+
 
 class EquivariantMLP(torch.nn.Sequential):
     def __init__(self, irreps_in, irreps_out, irreps_hidden_list, act=None, act_gates=None, norm_layer=None):

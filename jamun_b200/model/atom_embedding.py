@@ -28,6 +28,15 @@ class AtomEmbeddingWithResidueInformation(nn.Module):
         self.irreps_out = Irreps(f"{atom_type_embedding_dim}x0e + {atom_type_embedding_dim}x0e + "
                                  f"{residue_code_embedding_dim}x0e + {residue_index_embedding_dim}x0e")
 
+    def forward(self, data):
+        """Module-level compatibility forward on jamun_atom_embed."""
+        from .. import ops
+
+        dev = self.atom_type_embedding.weight.device
+        idx = [data[k].to(dev, torch.int32).contiguous() for k in ("atom_type_index", "atom_code_index", "residue_code_index")]
+        idx.append(data["residue_sequence_index"].to(dev, torch.int32).contiguous() if self.use_residue_sequence_index else None)
+        return ops.atom_embed(idx, [t.detach().contiguous() for t in self.tables()], None)
+
     def tables(self):
         return [self.atom_type_embedding.weight, self.atom_code_embedding.weight, self.residue_code_embedding.weight,
                 self.residue_index_embedding.weight]

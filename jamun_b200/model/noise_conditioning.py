@@ -21,6 +21,21 @@ class NoiseConditionalScaling(nn.Module):
             self.scale_predictor[-1].weight.fill_(0.0)
             self.scale_predictor[-1].bias.fill_(1.0)
 
+    def _expand(self, scales):
+        reps = torch.tensor([ir.dim for m, ir in self.irreps_in for _ in range(m)], device=scales.device)
+        return torch.repeat_interleave(scales, reps, dim=-1)
+
+    def scales(self, c_noise, sigmoid: bool = False):
+        from .. import ops
+
+        dev = self.scale_predictor[0].weight.device
+        ops_ = [t.detach() for t in self.mlp_operands()]
+        return ops.noise_mlp(*ops_, float(torch.as_tensor(c_noise).reshape(-1)[0]), sigmoid).to(dev)
+
+    def forward(self, x, c_noise):
+        """Module-level compatibility forward: per-irrep scales from jamun_noise_mlp, broadcast multiply."""
+        return x * self._expand(self.scales(c_noise))
+
     def mlp_operands(self):
         l0, l2 = self.scale_predictor[0], self.scale_predictor[2]
         return l0.weight.reshape(-1).contiguous(), l0.bias.contiguous(), l2.weight.contiguous(), l2.bias.contiguous()
@@ -31,3 +46,7 @@ class NoiseConditionalSkipConnection(nn.Module):
         super().__init__()
         self.weights = NoiseConditionalScaling(irreps_in, noise_input_dims=noise_input_dims)
         self.irreps_in = self.irreps_out = Irreps(irreps_in)
+
+    def forward(self, x1, x2, c_noise):
+        w = self.weights._expand(self.weights.scales(c_noise, sigmoid=True))
+        return x1 * w + x2 * (1 - w)

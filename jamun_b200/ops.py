@@ -213,3 +213,11 @@ def layout_from_soa(x, s: int, v: int):
     _lib.check(rc, "jamun_layout_from_soa")
     _count()
     return out
+
+
+def linear_act(x, w, b, act: int = 0):
+    out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+    rc = _lib.lib().jamun_linear_act(_ptr(x), _ptr(w), _ptr(b), x.shape[0], x.shape[1], w.shape[0], int(act), _ptr(out), _stream())
+    _lib.check(rc, "jamun_linear_act")
+    _count()
+    return out

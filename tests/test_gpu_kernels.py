@@ -305,3 +305,111 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(models):
         assert torch.equal(outs[0][key], outs[1][key]), key
         assert torch.equal(outs[0][key], outs[2][key]), key  # cached graph, second use
     assert outs[0]["y_traj"].shape[0] == 3 and outs[0]["score_traj"].shape[0] == 4  # frames 4,6,8 (+ the initial score)
+
+
+def test_module_level_forwards_match_oracle_modules(models):
+    """The reference's plug-in seams at module granularity: Conv.forward / apply_per_edge, ConvBlock, o3.Linear stand-in,
+    Gate, EquivariantMLP, NoiseConditionalScaling/SkipConnection, atom embedder -- same signatures, e3nn layouts."""
+    from jamun_b200 import synthetic
+
+    o32, o64, prod = models
+    g, og = prod.arch_module, o32.g
+    t = synthetic.make_tensors([14, 9, 20])
+    N = t["pos"].shape[0]
+    gen = torch.Generator().manual_seed(4)
+    ob = make_oracle_batch(t)
+    ei = O_radius(t)
+    E = ei.shape[1]
+    bm = torch.zeros(E, dtype=torch.long)
+    ea, sh = og.edge_features(t["pos"] * 1.7, ei, bm, 0.587)
+    x = torch.randn(N, 216, generator=gen)
+    with torch.no_grad():
+        layer, olayer = g.layers[1], og.layers[1]
+        want = olayer.gated_conv.f.f(x, ei, ea, sh)
+        got = layer.conv(x.cuda(), ei.cuda(), ea.cuda(), sh.cuda()).cpu()
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+        want_e = olayer.gated_conv.f.f.tp(x[ei[0]], sh, olayer.gated_conv.f.f.radial_nn(ea))
+        got_e = layer.conv.apply_per_edge(x[ei[0]].cuda(), ea.cuda(), sh.cuda()).cpu()
+        assert torch.allclose(got_e, want_e, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(layer(x.cuda(), ei.cuda(), ea.cuda(), sh.cuda()).cpu(), olayer(x, ei, ea, sh), rtol=1e-4, atol=2e-5)
+        assert torch.allclose(g.output_head(x.cuda()).cpu(), og.output_head(x), rtol=1e-4, atol=1e-5)
+        lin, olin = layer.gated_conv.self_interaction, olayer.gated_conv.self_interaction
+        assert torch.allclose(lin(x.cuda()).cpu(), olin(x), rtol=1e-5, atol=1e-5)
+        c = torch.tensor([-0.8047])
+        assert torch.allclose(g.noise_scalings[0](x.cuda(), c).cpu(), og.noise_scalings[0](x, c), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(g.skip_connections[0](x.cuda(), 2 * x.cuda(), c).cpu(), og.skip_connections[0](x, 2 * x, c), rtol=1e-5, atol=1e-6)
+        from jamun_b200 import data
+        b = data.Batch.from_tensors(t).to("cuda")
+        assert torch.allclose(g.atom_embedder(b).cpu(), og.atom_embedder(ob), atol=0)
+        x56 = torch.randn(N, 56, generator=gen)
+        assert torch.allclose(g.initial_projector(x56.cuda(), ei.cuda(), ea.cuda(), sh.cuda()).cpu(),
+                              og.initial_projector(x56, ei, ea, sh), rtol=1e-4, atol=2e-5)
+
+
+def O_radius(t):
+    from oracle import jamun_oracle as O
+
+    return torch.cat([O.radius_graph(t["pos"], 0.587, t["batch"], 32), t["edge_index"]], dim=1)
+
+
+def test_reference_call_path_xhat_normalized_and_explicit_edges(models):
+    """Denoiser.xhat_normalized -> add_edges -> g(y_scaled, c_noise, r_cut) (the reference's own call sequence), and
+    E3Conv.forward fed an explicit edge_index/bond_mask, both agree with the fused denoise_positions path."""
+    from jamun_b200 import data, utils
+
+    o32, o64, prod, t, y = _setup(models, [22, 15, 9], seed=2)
+    batch = data.Batch.from_tensors(t).to("cuda")
+    yb = utils.mean_center(batch.clone("pos"))
+    yb2 = batch.clone("pos")
+    yb2.pos = y.cuda()
+    yb2 = utils.mean_center(yb2)
+    fused = prod.xhat(yb2, SIGMA).pos
+    xn = prod.xhat_normalized(yb2, SIGMA)
+    assert torch.allclose(utils.mean_center(xn).pos, fused, atol=1e-6)
+    # explicit edge list (materialised from the CSR), fresh graph object without a cached topology/CSR
+    ctx = prod.sigma_context(SIGMA)
+    yb3 = prod.add_edges(yb2.clone("pos"), ctx.r_cut, materialize=True)
+    fresh = data.Batch.from_tensors(t).to("cuda")
+    fresh.pos = yb2.pos * ctx.c_in
+    fresh.edge_index, fresh.bond_mask = yb3.edge_index, yb3.bond_mask
+    gout = prod.arch_module(fresh, torch.tensor([ctx.c_noise]), ctx.r_cut).pos
+    want = (xn.pos - ctx.c_skip * yb2.pos) / ctx.c_out
+    assert torch.allclose(gout, want, atol=2e-5), (gout - want).abs().max()
+
+
+def test_sampler_end_to_end_with_callbacks(models):
+    """jamun.sampling.Sampler.sample: outer loop over batches, chain continuation, callback protocol, unbatching."""
+    from jamun_b200 import data
+    from jamun_b200.sampling import Sampler
+    from jamun_b200.sampling.mcmc import BAOAB
+    from jamun_b200.sampling.walkjump import SingleMeasurementSampler
+
+    o32, o64, prod, t, y = _setup(models, [22, 15, 9], seed=2)
+
+    class Rec:
+        def __init__(self):
+            self.events, self.samples = [], []
+
+        def on_sample_start(self, sampler):
+            self.events.append("start")
+
+        def on_before_sample_batch(self, sampler):
+            self.events.append("before")
+
+        def on_after_sample_batch(self, sample, sampler):
+            self.events.append("after")
+            self.samples.append(sample)
+
+        def on_sample_end(self, sampler):
+            self.events.append("end")
+
+    rec = Rec()
+    torch.manual_seed(5)
+    sampler = Sampler(callbacks=[rec])
+    bs = SingleMeasurementSampler(BAOAB(delta=0.04, friction=1.0, M=1.0, steps=5, save_trajectory=True, save_every_n_steps=2,
+                                        score_fn_clip=100.0), SIGMA)
+    sampler.sample(prod, bs, num_batches=2, init_graphs=data.Batch.from_tensors(t), continue_chain=True)
+    assert rec.events == ["start", "before", "after", "before", "after", "end"]
+    graphs = rec.samples[0]
+    assert len(graphs) == 3 and graphs[0]["xhat_traj"].shape == (22, 3, 3) and graphs[2]["sample"].shape == (9, 3)
+    assert all(torch.isfinite(gph["xhat"]).all() for gph in graphs)
