@@ -96,7 +96,7 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  * (1) jamun_conv_build_a: per receiver, A[k',u'] = sum_e h'_e[k'] f_e[u'] written as the fp32 A operand of the GEMM in
  *     stage-major layout ([stage][rows_pad][32]; stage = k'*nslots + slot; slots per the table in conv_build.cu) for
  *     rows [row0, row0+nrows); a0 holds the 0e operand, a1 + c*a1_comp_stride the three 1e operands; inv_deg[i] = 1/max(1,deg).
- *     The path 0e(x)1e->1e is gathered from y[N, 65*32] = x_s . W (pre-transformed source rows) into p2[N, p2_ld]:
+ *     The path 0e(x)1e->1e is gathered from y[N, 2176] = x_s . W (pre-transformed source rows, 65*32 used columns) into p2[N, p2_ld]:
  *     p2[i, c*32+w] = sum_e rhat_e[c] sum_k' h'_e[k'] y[src_e, k'*32+w], multiplied by p2_scale/deg when p2_scale != 0.
  *     max_degree: an upper bound of the in-degree of every node (<= 64 selects the shared-memory-cached fast kernel).
  *     chain_of/chain_ptr/src_max (optional): src_max = the largest number of nodes in the chains spanned by any aligned
@@ -107,7 +107,7 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  *     (jamun_b200/packing.py::pack_b_images).  rows_pad % 128 == 0; sum n_pad <= 256; n_pad % 16 == 0, <= 160.
  *     addend[s] (optional, [rows, addend_ld[s]]) is added to the accumulator before scaling.  col_blocks > 1 launches
  *     one CTA column per block of output columns: block y uses b[s] + y*b_block_floats and writes at out_col[s] + y*n_valid[s]
- *     (same A) -- used for the wide per-node transform Y = x_s . W (N = 65*32 = 13 blocks of 160).
+ *     (same A) -- used for the wide per-node transform Y = x_s . W (N = 65*32 = 2080, run as 17 blocks of 128; y row stride 2176).
  * (3) jamun_pack_rows: copies columns [col0, col0+ncols) of a row-major matrix into the GEMM's stage-major, chunk-swizzled
  *     A layout ([ceil(ncols/32)][rows_pad][32], zero padded). */
 int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,

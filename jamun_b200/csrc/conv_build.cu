@@ -26,7 +26,7 @@ using namespace jb;
 
 constexpr float kInvSqrt3 = 0.57735026918962576451f;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
-constexpr int YLD = (JAMUN_EDGE_HID + 1) * JAMUN_V;  // 2080
+constexpr int YLD = 17 * 128;  // row stride of Y: (64+1)*32 = 2080 columns padded to 17 column blocks of 128
 constexpr int MAXD = 64;  // in-edges per node whose per-edge invariants are cached in shared memory
 
 // Blackwell packed fp32 FMA (SASS FFMA2): two FMAs per issue slot; ptxas folds the {a,a} pack into a scalar operand.
@@ -48,7 +48,7 @@ __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1,
 }
 
 // ROLE 0: scalar operand slots + path-2 gather;  ROLE 1: vector operand slots;  ROLE 2: both (one warp does everything)
-template <int S_IN, int V_IN, int RK, int MINB, bool CACHED, int ROLE, int BT = 256>
+template <int S_IN, int V_IN, int RK, int MINB, bool CACHED, int ROLE, int BT = 256, int EUNROLL = 0>
 __global__ void __launch_bounds__(BT, MINB)
 conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int row0,
@@ -103,6 +103,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         }
         const float* hk = hrow + kb * RK;
         const float* yk = yl + kb * RK * JAMUN_V;
+#pragma unroll(EUNROLL == 0 ? 2 : EUNROLL)
         for (int t = 0; t < deg; ++t, hk += JAMUN_EDGE_HID) {
             int xoff, yoff;
             float rx, ry, rz;
@@ -442,6 +443,15 @@ extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int*
                 x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
         else if (variant == 4)
             conv_build_kernel<JAMUN_S, JAMUN_V, 4, 4, true, 2, 128><<<(nrows * 32 + 127) / 128, 128, 0, s>>>(
+                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
+        else if (variant == 6)
+            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 3, true, 2, 256, 1><<<blocks, 256, 0, s>>>(
+                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
+        else if (variant == 7)
+            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 6, true, 2, 128, 1><<<(nrows * 32 + 127) / 128, 128, 0, s>>>(
+                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
+        else if (variant == 10)
+            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 2, true, 2, 256, 4><<<blocks, 256, 0, s>>>(
                 x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
         else if (variant == 5)
             conv_build_kernel<JAMUN_S, JAMUN_V, 4, 7, true, 2, 96><<<(nrows * 32 + 95) / 96, 96, 0, s>>>(

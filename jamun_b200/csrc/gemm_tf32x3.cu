@@ -52,7 +52,7 @@ struct __align__(1024) Smem {
     uint8_t b[kBSlots][kBSlotBytes];
     uint8_t a[kASlots][kATileBytes];
     float epi[8][32 * 33];  // per-converter-warp transpose tiles of the epilogue
-    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full, d_empty;
+    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full[2], d_empty[2];
     uint32_t tmem_base;
 };
 
@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             umma::mbar_init(&S.t_full[s], 128);
             umma::mbar_init(&S.t_empty[s], 1);
         }
-        umma::mbar_init(&S.d_full, 1);
-        umma::mbar_init(&S.d_empty, kConvWarps * 32);
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(&S.d_full[s], 1);
+            umma::mbar_init(&S.d_empty[s], kConvWarps * 32);
+        }
         umma::fence_barrier_init();
     }
     if (warp == 0) umma::tmem_alloc<kTmemCols>(&S.tmem_base);
@@ -87,6 +89,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
 
     int total_stages = 0;
     for (int s = 0; s < P.nseg; ++s) total_stages += P.seg[s].n_stages;
+    // A-stationary mode (wide per-node transforms: few K stages, many column-block passes): the converted operand stays in its
+    // TMEM slots after pass 0; later passes only stream weight images and issue MMAs.
+    const bool stationary = P.col_blocks > 1 && total_stages <= kTSlots;
+    // ... and with one segment of N <= 128 the accumulator is double-buffered (TMEM columns [0,128) / [128,256)) so the MMAs of
+    // pass p+1 overlap the epilogue of pass p.
+    const bool dbuf = stationary && P.nseg == 1 && P.seg[0].n_pad <= 128;
 
     if (warp < kConvWarps) {
         // ------------------------------------------------ converters: smem fp32 tile -> (hi, lo) in TMEM
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         const int wrow0 = tile_row0 + (warp & 3) * 32;
         const float rs_own = (P.row_scale && tile_row0 + r < P.rows) ? P.row_scale[tile_row0 + r] : 1.0f;
         for (int cb = 0; cb < P.col_blocks; ++cb) {
-        for (int g = cb * total_stages + grp; g < (cb + 1) * total_stages; g += kConvWarps / 4) {
+        for (int g = cb * total_stages + grp; g < (cb + 1) * total_stages && !(stationary && cb > 0); g += kConvWarps / 4) {
             const int sa = g % kASlots, st = g % kTSlots;
             umma::mbar_wait(&S.a_full[sa], (g / kASlots) & 1);
             const float4* row = reinterpret_cast<const float4*>(S.a[sa] + r * 128);
@@ -126,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         }
         // ------------------------------------------------ epilogue: TMEM -> registers (thread = row) -> shared-memory transpose
         // (the operand rings are idle by now) -> coalesced 128-byte row stores with lanes over columns
-        umma::mbar_wait(&S.d_full, cb & 1);
+        const int db = dbuf ? (cb & 1) : 0;
+        umma::mbar_wait(&S.d_full[db], dbuf ? (cb >> 1) & 1 : cb & 1);
         umma::fence_after_sync();
         int chunk = 0;
         for (int s = 0; s < P.nseg; ++s) {
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             for (int c0 = 0; c0 < sg.n_pad; c0 += 32, ++chunk) {
                 if ((chunk & 1) != grp) continue;  // the two converter groups alternate 32-column chunks
                 uint32_t v[32];
-                umma::tmem_ld32(tmem + lane_base + (uint32_t)(sg.d_col + c0), v);
+                umma::tmem_ld32(tmem + lane_base + (uint32_t)(sg.d_col + db * 128 + c0), v);
                 umma::wait_ld();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(v[c]);
@@ -160,12 +169,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             }
         }
         umma::fence_before_sync();
-        umma::mbar_arrive(&S.d_empty);  // accumulators drained: the next pass may overwrite them
+        umma::mbar_arrive(&S.d_empty[db]);  // accumulators drained: a later pass may overwrite them
         }  // column-block pass
     } else if (warp == kConvWarps) {
         // ------------------------------------------------ A loader: one 16 KB bulk copy per stage
         int g = 0;
-        for (int cb = 0; cb < P.col_blocks; ++cb) {
+        for (int cb = 0; cb < (stationary ? 1 : P.col_blocks); ++cb) {
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
                 for (int st = 0; st < sg.n_stages; ++st, ++g) {
@@ -201,18 +210,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         // ------------------------------------------------ MMA issuer (whole warp converged; one elected lane issues)
         int g = 0;
         for (int cb = 0; cb < P.col_blocks; ++cb) {
-            if (cb > 0) {  // the epilogue of the previous pass must have drained the accumulators
-                umma::mbar_wait(&S.d_empty, (cb - 1) & 1);
+            const int db = dbuf ? (cb & 1) : 0;
+            if (dbuf ? cb >= 2 : cb > 0) {  // the epilogue that last used this accumulator buffer must have drained it
+                umma::mbar_wait(&S.d_empty[db], dbuf ? ((cb - 2) >> 1) & 1 : (cb - 1) & 1);
                 umma::fence_after_sync();
             }
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
                 const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
-                const uint32_t d_addr = tmem + (uint32_t)sg.d_col;
+                const uint32_t d_addr = tmem + (uint32_t)(sg.d_col + db * 128);
                 const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
                 for (int st = 0; st < sg.n_stages; ++st, ++g) {
-                    const int ts = g % kTSlots, sb = g % kBSlots;
-                    umma::mbar_wait(&S.t_full[ts], (g / kTSlots) & 1);
+                    const int gl = g - cb * total_stages;  // stage index within the pass
+                    const int ts = stationary ? gl : g % kTSlots, sb = g % kBSlots;
+                    if (!stationary || cb == 0) umma::mbar_wait(&S.t_full[ts], stationary ? 0 : (g / kTSlots) & 1);
                     umma::mbar_wait(&S.b_full[sb], (g / kBSlots) & 1);
                     umma::fence_after_sync();
                     if (umma::elect_one()) {
@@ -226,13 +237,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
                         }
-                        umma::commit(&S.t_empty[ts]);
+                        if (!stationary) umma::commit(&S.t_empty[ts]);
                         umma::commit(&S.b_empty[sb]);
                     }
                     __syncwarp();
                 }
             }
-            if (umma::elect_one()) umma::commit(&S.d_full);
+            if (umma::elect_one()) umma::commit(&S.d_full[db]);
             __syncwarp();
         }
     }

@@ -7,6 +7,7 @@ and stream plumbing only.
 """
 from __future__ import annotations
 
+import itertools
 import math
 import os
 from typing import Dict, List, Optional
@@ -20,6 +21,7 @@ from .irreps import Irreps
 # "tc": aggregate builder + tcgen05 3xTF32 GEMM (product path); "simt": the exact-fp32 CUDA-core kernel (kept for
 # A/B validation of the tensor-core path, selectable with JAMUN_B200_CONV=simt)
 CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
+Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
 
 class Topology:
@@ -101,6 +103,8 @@ class Topology:
         max_rows = max(128, (self.WORKSPACE_BYTES // per_row) // 128 * 128)
         self.chunk_rows = min(rows_pad, max_rows)
         self.a_ws = None  # allocated on first use
+        self.y0 = None
+        self.y0_key = None
 
     def build_csr(self, pos: torch.Tensor, r_cut: float):
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
@@ -133,6 +137,8 @@ class Topology:
 class E3ConvPlan:
     """Kernel operands of one E3Conv module at one noise level (c_noise)."""
 
+    _serials = itertools.count(1)
+
     def __init__(self, g, c_noise: float, device):
         from .e3tools.nn import ConvBlock, EquivariantMLP
         from .model.atom_embedding import AtomEmbeddingWithResidueInformation
@@ -149,6 +155,7 @@ class E3ConvPlan:
             raise NotImplementedError("hidden_layer_factory must be ConvBlock and output_head_factory EquivariantMLP([hidden])")
         self.c_noise = float(c_noise)
         self.device = dev
+        self.serial = next(E3ConvPlan._serials)  # cache key for plan-dependent constants held by topologies
         with torch.no_grad():
             emb = g.embed_bondedness.weight.detach().to(dev, torch.float32)
             self.tables = [t.detach().to(dev, torch.float32).contiguous() for t in g.atom_embedder.tables()]
@@ -163,7 +170,9 @@ class E3ConvPlan:
                 w0, w1, wy = packing.conv_k_layout(blk["m0"], blk["m1"], blk["s_in"], blk["v_in"])
                 blk["b0_img"] = packing.pack_b_images(w0, 160)
                 blk["b1_img"] = packing.pack_b_images(w1, 32) if w1 is not None else None
-                blk["wy_img"] = packing.pack_b_column_blocks(wy, 160)
+                wy_pad = torch.zeros(wy.shape[0], Y_LD, dtype=wy.dtype, device=wy.device)
+                wy_pad[:, :wy.shape[1]] = wy
+                blk["wy_img"] = packing.pack_b_column_blocks(wy_pad, 128)
                 self.blocks.append(blk)
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
@@ -183,7 +192,7 @@ class E3ConvPlan:
         return values[1:-1].to(self.device).contiguous(), step
 
 
-def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor) -> None:
+def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None) -> None:
     """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
     13 column blocks) -> jamun_conv_build_a (aggregate of the other paths + gather of Y, CUDA cores) -> jamun_gemm_tf32x3."""
     s_in, v_in = b["s_in"], b["v_in"]
@@ -196,19 +205,30 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor) -> None
     if topo.a_ws is None:
         topo.a_ws = torch.empty(65 * (5 + 3 * 2) * rp * 32, dtype=torch.float32, device=topo.device)
         topo.xs_op = torch.empty(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
-        topo.y = torch.empty(N, 65 * 32, dtype=torch.float32, device=topo.device)
+        topo.y = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
         topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
-    # per-node transform of the scalar inputs
-    ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
-    ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [160], [160], [0], [1.0], N, rows_all, None,
-                    topo.y.data_ptr(), 65 * 32, col_blocks=13, b_block_floats=ns * 2 * 160 * 32)
+    # per-node transform of the scalar inputs.  For the initial block the input (atom embedding x noise scale) does not depend
+    # on positions, so its transform is computed once per (topology, plan) and kept.
+    y_buf = topo.y
+    if y_const_key is not None:
+        if topo.y0 is None or topo.y0_key != y_const_key:
+            topo.y0 = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
+            ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
+            ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0], N, rows_all, None,
+                            topo.y0.data_ptr(), Y_LD, col_blocks=17, b_block_floats=ns * 2 * 128 * 32)
+            topo.y0_key = y_const_key
+        y_buf = topo.y0
+    else:
+        ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
+        ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0], N, rows_all, None,
+                        topo.y.data_ptr(), Y_LD, col_blocks=17, b_block_floats=ns * 2 * 128 * 32)
     base = topo.a_ws.data_ptr()
     a1_off = st0 * rp * 32
     comp = st1 * rp * 32
     for row0 in range(0, N, rp):
         nrows = min(rp, N - row0)
         if v_in:
-            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base,
+            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base,
                              base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg)
             a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
             b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
@@ -218,7 +238,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor) -> None
                             out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN,
                             addend_ptrs=[None, p2, p2 + 4 * 32, p2 + 4 * 64], addend_ld=[0, 96, 96, 96])
         else:  # initial block: the 1e output is the path-2 gather alone, written in place by the builder
-            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base, None, 0,
+            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base, None, 0,
                              out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
             ops.gemm_tf32x3([base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
                             topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
@@ -230,7 +250,7 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
     if mu is None:
         mu, step = plan.radial_grid(r_cut)
     ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
-    key = (id(plan),)
+    key = (plan.serial,)
     if topo.x0_key != key:  # constant per (topology, plan): embedding x initial noise scaling
         idx = list(topo.idx)
         if not plan.use_residue_sequence_index:
@@ -245,7 +265,7 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
             ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
                          b["alpha0"], b["alpha1"], topo.conv)
         else:
-            conv_tc(topo, b, x_in, topo.conv)
+            conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None)
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None
         s_next = plan.scales[l] if l < nb - 1 else None

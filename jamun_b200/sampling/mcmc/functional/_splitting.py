@@ -212,7 +212,7 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
             eager_step(i)
     else:
         eager_step(0)  # also warms up every lazily allocated workspace before capture
-        gkey = (id(plan), float(delta), float(friction), float(M), float(inverse_temperature), score_fn_clip,
+        gkey = (plan.serial, float(delta), float(friction), float(M), float(inverse_temperature), score_fn_clip,
                 float(sigma), int(model.mean_center), int(prm.seed))
 
         def graph_for(save: bool):
@@ -253,4 +253,4 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
 
 def ws_launches(plan) -> int:
     """Kernel launches inside one replayed walk-jump step (for bench.py's gpu_launches claim)."""
-    return 3 + 1 + len(plan.blocks) * 6 + 1 + 2
+    return 3 + 1 + len(plan.blocks) * 6 - 2 + 1 + 2  # the initial block's transform is cached
