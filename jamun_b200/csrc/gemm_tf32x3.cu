@@ -20,7 +20,7 @@ namespace {
 using namespace jb;
 
 constexpr int kTSlots = 4;                 // A slots in TMEM
-constexpr int kASlots = 4;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
+constexpr int kASlots = 6;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
 constexpr int kBSlots = 3;                 // weight images in shared memory
 constexpr int kBK = 32;                    // K per stage (one 128-byte swizzle row of tf32)
 constexpr int kMaxN = 160;
@@ -51,7 +51,6 @@ struct Params {
 struct __align__(1024) Smem {
     uint8_t b[kBSlots][kBSlotBytes];
     uint8_t a[kASlots][kATileBytes];
-    float epi[8][32 * 33];  // per-converter-warp transpose tiles of the epilogue
     uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full[2], d_empty[2];
     uint32_t tmem_base;
 };
@@ -59,7 +58,7 @@ struct __align__(1024) Smem {
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P) {
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int tile_row0 = blockIdx.x * 128;
 
     if (threadIdx.x == 0) {
@@ -102,8 +101,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         const int r = threadIdx.x & 127;        // row within the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int sw = r & 7;
-        float* tile = S.epi[warp];
-        const int wrow0 = tile_row0 + (warp & 3) * 32;
         const float rs_own = (P.row_scale && tile_row0 + r < P.rows) ? P.row_scale[tile_row0 + r] : 1.0f;
         for (int cb = 0; cb < P.col_blocks; ++cb) {
         for (int g = cb * total_stages + grp; g < (cb + 1) * total_stages && !(stationary && cb > 0); g += kConvWarps / 4) {
@@ -132,8 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             umma::fence_before_sync();
             umma::mbar_arrive(&S.t_full[st]);
         }
-        // ------------------------------------------------ epilogue: TMEM -> registers (thread = row) -> shared-memory transpose
-        // (the operand rings are idle by now) -> coalesced 128-byte row stores with lanes over columns
+        // ------------------------------------------------ epilogue: TMEM -> registers (thread = row) -> scaled 16-byte stores
         const int db = dbuf ? (cb & 1) : 0;
         umma::mbar_wait(&S.d_full[db], dbuf ? (cb >> 1) & 1 : cb & 1);
         umma::fence_after_sync();
@@ -145,27 +141,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                 uint32_t v[32];
                 umma::tmem_ld32(tmem + lane_base + (uint32_t)(sg.d_col + db * 128 + c0), v);
                 umma::wait_ld();
+                // thread = row: 8 x 16-byte stores per 32-column chunk (few instructions; the 8 pieces of a 128-byte line
+                // merge in L2)
+                const int row = tile_row0 + r;
+                if (row < P.rows) {
+                    const float sc = sg.alpha * rs_own;
+                    float* o = sg.out + (size_t)row * P.out_ld + sg.out_col + cb * sg.n_valid + c0;
+                    const float* ad = sg.addend ? sg.addend + (size_t)row * sg.addend_ld + c0 : nullptr;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(v[c]);
-                __syncwarp();
-                const int ncol = sg.n_valid - c0;  // valid columns in this chunk
-                if (lane < ncol) {
-                    const int col = sg.out_col + cb * sg.n_valid + c0 + lane;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = wrow0 + rr;
-                        const float rsv = __shfl_sync(0xffffffffu, rs_own, rr);
-                        if (row < P.rows) {
-                            float acc = tile[rr * 33 + lane];
-                            if (sg.addend) acc += sg.addend[(size_t)row * sg.addend_ld + c0 + lane];
-                            sg.out[(size_t)row * P.out_ld + col] = acc * sg.alpha * rsv;
+                    for (int q = 0; q < 8; ++q) {
+                        float f[4] = {__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                      __uint_as_float(v[4 * q + 3])};
+                        if (c0 + 4 * q + 3 < sg.n_valid) {
+                            if (ad) {
+                                const float4 a4 = *reinterpret_cast<const float4*>(ad + 4 * q);
+                                f[0] += a4.x;
+                                f[1] += a4.y;
+                                f[2] += a4.z;
+                                f[3] += a4.w;
+                            }
+                            *reinterpret_cast<float4*>(o + 4 * q) = make_float4(f[0] * sc, f[1] * sc, f[2] * sc, f[3] * sc);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (c0 + 4 * q + t < sg.n_valid) o[4 * q + t] = (f[t] + (ad ? ad[4 * q + t] : 0.f)) * sc;
                         }
                     }
-                } else {
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) (void)__shfl_sync(0xffffffffu, rs_own, rr);
                 }
-                __syncwarp();
             }
         }
         umma::fence_before_sync();
