@@ -78,7 +78,7 @@ int jamun_edge_geom(const float* p, const int* rowptr, const int* col, const int
                     const float* mu, float step, float* rhat, float* rb, jamun_stream_t stream);
 
 /* Radial MLP hidden layer (e3tools/nn/_conv.py:84-94, _mlp.py:21-34), bondedness embedding folded:
- * h = SiLU(w0r . rb + b0eff[ebond]).  w0r: [64, 32] (the radial half of radial_nn.0.weight),
+ * h = SiLU(rb . w0r + b0eff[ebond]).  w0r: [32, 64] (the radial half of radial_nn.0.weight, transposed: basis-major),
  * b0eff: [2, 64] = bias + W0[:, :32] . embed_bondedness[flag].  h: [cap, 64]. */
 int jamun_edge_radial_hidden(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
                              const float* w0r, const float* b0eff, float* h, jamun_stream_t stream);

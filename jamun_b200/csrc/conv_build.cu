@@ -29,24 +29,6 @@ constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr int YLD = 17 * 128;  // row stride of Y: (64+1)*32 = 2080 columns padded to 17 column blocks of 128
 constexpr int MAXD = 64;  // in-edges per node whose per-edge invariants are cached in shared memory
 
-// Blackwell packed fp32 FMA (SASS FFMA2): two FMAs per issue slot; ptxas folds the {a,a} pack into a scalar operand.
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
-}
-__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
-}
-
 // ROLE 0: scalar operand slots + path-2 gather;  ROLE 1: vector operand slots;  ROLE 2: both (one warp does everything)
 template <int S_IN, int V_IN, int RK, int MINB, bool CACHED, int ROLE, int BT = 256, int EUNROLL = 0>
 __global__ void __launch_bounds__(BT, MINB)

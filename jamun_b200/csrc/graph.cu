@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace jb {
 static thread_local char g_err[512] = "";
@@ -175,36 +176,88 @@ __global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restr
     }
 }
 
-// ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0r[o][k] rb[e][k] + b0eff[flag][o]) --------
-// 64 threads per edge stream (thread = output channel o, its weight row held in registers); each pair of warps walks a
-// strided list of edges: 8 uniform 16-byte loads of the edge's radial basis, 32 FMAs, one coalesced 256-byte store.
-__global__ void __launch_bounds__(256) edge_radial_hidden_kernel(const float* __restrict__ rb,
-                                                                 const unsigned char* __restrict__ ebond,
-                                                                 const int* __restrict__ rowptr, int N,
-                                                                 const float* __restrict__ w0r,
-                                                                 const float* __restrict__ b0eff,
-                                                                 float* __restrict__ h) {
-    const int o = threadIdx.x & 63;
-    const int stream = (blockIdx.x * blockDim.x + threadIdx.x) >> 6;
-    const int nstreams = (gridDim.x * blockDim.x) >> 6;
-    float w[JAMUN_NBASIS];
-#pragma unroll
-    for (int k = 0; k < JAMUN_NBASIS; ++k) w[k] = w0r[o * JAMUN_NBASIS + k];
-    const float b0 = b0eff[o], b1 = b0eff[JAMUN_EDGE_HID + o];
+// ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0rt[k][o] rb[e][k] + b0eff[flag][o]) --------
+// A [E x 32] . [32 x 64] product on the FP32 pipe.  One CTA of 128 threads owns a tile of 128 edges: the tile's radial
+// basis (16 KB, contiguous) and the transposed weight (8 KB) arrive by two bulk async copies; each thread keeps an
+// 8-edge x 8-channel register tile (packed FFMA2), so every operand fetched from shared memory feeds 8 FMAs.  Lane layout
+// (lane = channel group + 8 * edge group) makes each quarter-warp read one 128-byte row (weights) or one address
+// (basis, broadcast), and lets 8 lanes store one contiguous 128-byte half row of h.
+constexpr int kRhTile = 128;
+__global__ void __launch_bounds__(128, 4) edge_radial_hidden_kernel(const float* __restrict__ rb,
+                                                                    const unsigned char* __restrict__ ebond,
+                                                                    const int* __restrict__ rowptr, int N,
+                                                                    const float* __restrict__ w0rt,
+                                                                    const float* __restrict__ b0eff,
+                                                                    float* __restrict__ h) {
+    __shared__ __align__(128) float s_rb[kRhTile * JAMUN_NBASIS];
+    __shared__ __align__(128) float s_w[JAMUN_NBASIS * JAMUN_EDGE_HID];
+    __shared__ float s_b[2 * JAMUN_EDGE_HID];
+    __shared__ __align__(8) uint64_t bar;
     const int E = rowptr[N];
-    for (int e = stream; e < E; e += nstreams) {
-        const float4* r4 = reinterpret_cast<const float4*>(rb + (size_t)e * JAMUN_NBASIS);
-        float acc0 = 0.f, acc1 = 0.f;
+    const int e0 = blockIdx.x * kRhTile;
+    if (e0 >= E) return;
+    const int nvalid = min(kRhTile, E - e0);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::fence_barrier_init();
+    }
+    s_b[tid] = b0eff[tid];
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t rb_bytes = (uint32_t)nvalid * JAMUN_NBASIS * 4u, w_bytes = JAMUN_NBASIS * JAMUN_EDGE_HID * 4u;
+        umma::mbar_arrive_expect_tx(&bar, rb_bytes + w_bytes);
+        umma::bulk_g2s(s_rb, rb + (size_t)e0 * JAMUN_NBASIS, rb_bytes, &bar);
+        umma::bulk_g2s(s_w, w0rt, w_bytes, &bar);
+    }
+    umma::mbar_wait(&bar, 0);
+
+    const int og = tid & 7, eg = tid >> 3;  // channels {4 og .. +3} and {32 + 4 og .. +3};  edges 8 eg .. 8 eg + 7
+    float acc[8][8];
 #pragma unroll
-        for (int q = 0; q < JAMUN_NBASIS / 4; ++q) {
-            const float4 v = __ldg(r4 + q);
-            acc0 = fmaf(w[4 * q], v.x, acc0);
-            acc1 = fmaf(w[4 * q + 1], v.y, acc1);
-            acc0 = fmaf(w[4 * q + 2], v.z, acc0);
-            acc1 = fmaf(w[4 * q + 3], v.w, acc1);
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float4* rb4 = reinterpret_cast<const float4*>(s_rb) + eg * 8 * (JAMUN_NBASIS / 4);
+    const float4* w4 = reinterpret_cast<const float4*>(s_w) + og;
+#pragma unroll 2
+    for (int k4 = 0; k4 < JAMUN_NBASIS / 4; ++k4) {
+        float4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = rb4[i * (JAMUN_NBASIS / 4) + k4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 wa = w4[(k4 * 4 + c) * (JAMUN_EDGE_HID / 4)];
+            const float4 wb = w4[(k4 * 4 + c) * (JAMUN_EDGE_HID / 4) + 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float rv = c == 0 ? r[i].x : c == 1 ? r[i].y : c == 2 ? r[i].z : r[i].w;
+                jb::ffma2(acc[i][0], acc[i][1], rv, wa.x, wa.y);
+                jb::ffma2(acc[i][2], acc[i][3], rv, wa.z, wa.w);
+                jb::ffma2(acc[i][4], acc[i][5], rv, wb.x, wb.y);
+                jb::ffma2(acc[i][6], acc[i][7], rv, wb.z, wb.w);
+            }
         }
-        const float acc = acc0 + acc1 + (ebond[e] ? b1 : b0);
-        h[(size_t)e * JAMUN_EDGE_HID + o] = siluf_acc(acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int el = eg * 8 + i;
+        if (el < nvalid) {
+            const int e = e0 + el;
+            const float* bias = s_b + (ebond[e] ? JAMUN_EDGE_HID : 0) + 4 * og;
+            float4 lo, hi;
+            lo.x = jb::siluf_acc(acc[i][0] + bias[0]);
+            lo.y = jb::siluf_acc(acc[i][1] + bias[1]);
+            lo.z = jb::siluf_acc(acc[i][2] + bias[2]);
+            lo.w = jb::siluf_acc(acc[i][3] + bias[3]);
+            hi.x = jb::siluf_acc(acc[i][4] + bias[32]);
+            hi.y = jb::siluf_acc(acc[i][5] + bias[33]);
+            hi.z = jb::siluf_acc(acc[i][6] + bias[34]);
+            hi.w = jb::siluf_acc(acc[i][7] + bias[35]);
+            float4* dst = reinterpret_cast<float4*>(h + (size_t)e * JAMUN_EDGE_HID) + og;
+            dst[0] = lo;
+            dst[8] = hi;
+        }
     }
 }
 
@@ -282,10 +335,9 @@ extern "C" int jamun_edge_radial_hidden(const float* rb, const unsigned char* eb
                                         const float* w0r, const float* b0eff, float* h, jamun_stream_t stream) {
     JB_CHECK_ARG(rb && ebond && rowptr && w0r && b0eff && h, "null argument");
     if (N == 0 || cap == 0) return JAMUN_OK;
-    int blocks = (cap + 3) / 4;
-    int max_blocks = jb::kNumSMs * 8;  // 8 resident CTAs x 4 edge streams per SM
-    if (blocks > max_blocks) blocks = max_blocks;
-    edge_radial_hidden_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h);
+    // one CTA per 128-edge tile of the capacity; the live edge count is device-side (rowptr[N]), surplus CTAs exit
+    int blocks = (cap + kRhTile - 1) / kRhTile;
+    edge_radial_hidden_kernel<<<blocks, 128, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

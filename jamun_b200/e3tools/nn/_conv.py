@@ -33,7 +33,7 @@ class Conv(torch.nn.Module):
         self.radial_nn = radial_nn(edge_attr_dim, self.tp.weight_numel)
 
     def pack(self, embed_bondedness: torch.Tensor):
-        """-> dict(w0r [64,32], b0eff [2,64], m0 [65,U0,152], m1 [65,U1,32], alpha0, alpha1, s_in, v_in)."""
+        """-> dict(w0r [32,64] (k-major), b0eff [2,64], m0 [65,U0,152], m1 [65,U1,32], alpha0, alpha1, s_in, v_in)."""
         if not isinstance(self.tp, FullyConnectedTensorProduct) or not isinstance(self.radial_nn, ScalarMLP):
             raise NotImplementedError("the B200 conv kernel is built for FullyConnectedTensorProduct + ScalarMLP")
         if self.irreps_sh != Irreps("1x0e+1x1e") or self.irreps_out.simplify() != Irreps("152x0e+32x1e"):
@@ -45,7 +45,7 @@ class Conv(torch.nn.Module):
         s_in, v_in = self.irreps_in.scalars_vectors()
         nb = embed_bondedness.shape[1]
         W0, b0 = lins[0].weight, lins[0].bias
-        w0r = W0[:, nb:].contiguous()
+        w0r = W0[:, nb:].T.contiguous()
         b0eff = (b0[None, :] + embed_bondedness @ W0[:, :nb].T).contiguous()
         Mfull = torch.cat([lins[1].weight.T, lins[1].bias[None, :]], dim=0)  # [65, P]
         K = Mfull.shape[0]

@@ -34,7 +34,7 @@ def edge_geom(p, src, dst, r_cut, n_basis=32):
 
 
 def radial_hidden(rb, ebond, w0r, b0eff):
-    z = rb @ w0r.T + b0eff[ebond.long()]
+    z = rb @ w0r + b0eff[ebond.long()]
     return z * torch.sigmoid(z)
 
 
