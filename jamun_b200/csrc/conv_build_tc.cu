@@ -1,0 +1,359 @@
+// Aggregate step of the equivariant convolution on the tensor cores (tcgen05, kind::tf32, 3xTF32 split).
+//
+// Per receiver node i the aggregate   A_i[k', u'] = sum_{e -> i} h'_e[k'] * f_e[u']      (conv_build.cu, same output)
+// is a small GEMM  F_i^T . H_i  with K = in-degree (<= 33 for the capped radius graph), M = 344 edge-feature columns and
+// N = 65 radial channels.  conv_build_kernel evaluates it with FFMA2 at ~25 % of the FP32 pipe because every pass over
+// the in-edges can keep only 4 channels x 11 columns in registers; here the FP32 pipe only *stages* the operands and the
+// product runs as tcgen05.mma with the accumulator in tensor memory:
+//
+//   producers (8 warps)   one item = (node, chunk of <= 32 in-edges).  Warp g gathers in-edges 4g..4g+3 (lanes over the
+//                         feature columns), forms the 1e features (x_v . rhat, x_v/sqrt3, x_v x rhat/sqrt2), splits every
+//                         value into tf32 hi + lo and writes 16-byte K-quads into K-major SWIZZLE_128B tiles
+//                         (rows = feature columns for F, channels for H; one 128-byte row = 32 in-edges): conflict-free.
+//   MMA warp (1 thread)   per item and column group t (scalars | x_v.rhat, x_v | x_v x rhat: M tiles of 128, 128, 96 rows):
+//                         D_t[u', k'] (+)= Fhi.Hhi + Fhi.Hlo + Flo.Hhi  for each 8-edge K step (N = 80 >= 65);
+//                         commit -> accumulator full, commit -> operand slot free.  Row 64 of H is the constant 1
+//                         (the bias channel h' = 1).
+//   epilogue (2 x 4 warps) TMEM lane = feature column, so for a fixed channel the 32 lanes of a warp hold the 32
+//                         consecutive elements of one 128-byte operand row of jamun_gemm_tf32x3's A layout: every store
+//                         instruction writes one full line.
+//
+// Two operand slots and two sets of three 80-column accumulators keep the roles overlapped; the kernel is persistent
+// with one CTA per SM (222 KB of shared memory) and is bound by the HBM write of A (91.5 KB per node).
+// The path 0e(x)1e->1e gather (p2) is conv_p2_kernel below.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+using namespace jb;
+
+constexpr float kInvSqrt3 = 0.57735026918962576451f;
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+constexpr int YLD = 17 * 128;
+constexpr int kSlots = 2;        // operand slots
+constexpr int kAccCols = 80;     // accumulator width: 65 channels padded to a legal N
+constexpr int kProducerWarps = 8;
+constexpr int kEpiWarps = 8;     // two sets of four (TMEM lane quarter = warp % 4)
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kThreads = 32 * (kEpiWarps + 1 + kProducerWarps);
+constexpr int kHBytes = kAccCols * 128;  // H tile: channel rows 0..64 (rows 65..79 are never written nor used)
+
+template <int S_IN, int V_IN>
+struct Shape {
+    static constexpr int D_IN = S_IN + 3 * V_IN;
+    static constexpr int NS = (S_IN + 31) / 32;
+    static constexpr int NSL0 = NS + (V_IN > 0 ? 1 : 0), NSL1 = V_IN > 0 ? 2 : 0;
+    static constexpr int NCOL = NS + (V_IN > 0 ? 7 : 0);  // 32-column groups of F
+    static constexpr int F_BYTES = NCOL * 32 * 128;
+    static constexpr int NT = V_IN > 0 ? 3 : 1;           // M tiles (accumulators) per node
+    static constexpr int SLOT_BYTES = 2 * kHBytes + 2 * F_BYTES;
+    // barriers | slots | tail the last M tile's 128-row read may run into
+    static constexpr int SMEM_BYTES = 1024 /*alignment*/ + 1024 /*barriers*/ + kSlots * SLOT_BYTES + 8192;
+    __host__ __device__ static constexpr int tgroups(int t) { return t == 0 ? NS : t == 1 ? 4 : 3; }  // live 32-column groups
+    __host__ __device__ static constexpr int trow0(int t) { return t == 0 ? 0 : t == 1 ? NS * 32 : NS * 32 + 128; }
+};
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void store_split(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, float a, float b,
+                                            float c, float d) {
+    const float ah = tf32_hi(a), bh = tf32_hi(b), ch = tf32_hi(c), dh = tf32_hi(d);
+    *reinterpret_cast<float4*>(hi_tile + off) = make_float4(ah, bh, ch, dh);
+    *reinterpret_cast<float4*>(lo_tile + off) = make_float4(a - ah, b - bh, c - ch, d - dh);
+}
+
+template <int S_IN, int V_IN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
+                     const float* __restrict__ h, const float* __restrict__ rhat, int row0, int nrows, int rows_pad,
+                     float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride) {
+    using SH = Shape<S_IN, V_IN>;
+    constexpr int NS = SH::NS, NCOL = SH::NCOL, NT = SH::NT;
+    constexpr int kBufs = 2 * NT;
+    extern __shared__ unsigned char dsm_raw[];
+    unsigned char* dsm = reinterpret_cast<unsigned char*>(((uintptr_t)dsm_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+    uint64_t* full = bars;                  // [kSlots]  producers -> MMA
+    uint64_t* empty = bars + kSlots;        // [kSlots]  MMA -> producers
+    uint64_t* tfull = bars + 2 * kSlots;    // [kBufs]   MMA -> epilogue
+    uint64_t* tempty = tfull + kBufs;       // [kBufs]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kBufs);
+    unsigned char* slots = dsm + 1024;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; ++s) {
+            umma::mbar_init(&full[s], kProducerWarps);
+            umma::mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < kBufs; ++b) {
+            umma::mbar_init(&tfull[b], 1);
+            umma::mbar_init(&tempty[b], 4);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == kMmaWarp) umma::tmem_alloc<512>(tmem_slot);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per = (nrows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * per;
+    const int r_end = min(nrows, r_begin + per);
+
+    if (warp > kMmaWarp) {
+        // ------------------------------------------------------------------ producers
+        const int g = warp - kMmaWarp - 1;
+        const uint32_t off = (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)((g ^ (lane & 7)) << 4);
+        int it = 0;
+        for (int r = r_begin; r < r_end; ++r) {
+            const int i = row0 + r;
+            const int e0 = rowptr[i];
+            const int deg = rowptr[i + 1] - e0;
+            const int nchunks = deg > 32 ? (deg + 31) >> 5 : 1;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int n = min(32, deg - 32 * c);
+                const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
+                const int s = it % kSlots;
+                umma::mbar_wait(&empty[s], (((uint32_t)it / kSlots) & 1u) ^ 1u);
+                unsigned char* slot = slots + s * SH::SLOT_BYTES;
+                unsigned char* Hhi = slot;
+                unsigned char* Hlo = slot + kHBytes;
+                unsigned char* Fhi = slot + 2 * kHBytes;
+                unsigned char* Flo = Fhi + SH::F_BYTES;
+                if (4 * g < n) {
+                    const int nv = min(4, n - 4 * g);
+                    const int eb = e0 + 32 * c + 4 * g;
+                    float f[NCOL][4];
+                    float hh[2][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < nv) {
+                            const int e = eb + q;
+                            const int j = col[e];
+                            const float* xr = x + (size_t)j * SH::D_IN;
+#pragma unroll
+                            for (int sl = 0; sl < NS; ++sl) f[sl][q] = (lane + 32 * sl < S_IN) ? xr[lane + 32 * sl] : 0.f;
+                            if constexpr (V_IN > 0) {
+                                const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+                                const float vx = xr[S_IN + lane], vy = xr[S_IN + V_IN + lane], vz = xr[S_IN + 2 * V_IN + lane];
+                                f[NS][q] = vx * rh.x + vy * rh.y + vz * rh.z;
+                                f[NS + 1][q] = vx * kInvSqrt3;
+                                f[NS + 2][q] = vy * kInvSqrt3;
+                                f[NS + 3][q] = vz * kInvSqrt3;
+                                f[NS + 4][q] = (vy * rh.z - vz * rh.y) * kInvSqrt2;
+                                f[NS + 5][q] = (vz * rh.x - vx * rh.z) * kInvSqrt2;
+                                f[NS + 6][q] = (vx * rh.y - vy * rh.x) * kInvSqrt2;
+                            }
+                            const float* he = h + (size_t)e * JAMUN_EDGE_HID;
+                            hh[0][q] = he[lane];
+                            hh[1][q] = he[32 + lane];
+                        } else {
+#pragma unroll
+                            for (int sl = 0; sl < NCOL; ++sl) f[sl][q] = 0.f;
+                            hh[0][q] = hh[1][q] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < NCOL; ++sl) store_split(Fhi, Flo, off + sl * 4096, f[sl][0], f[sl][1], f[sl][2], f[sl][3]);
+                    store_split(Hhi, Hlo, off, hh[0][0], hh[0][1], hh[0][2], hh[0][3]);
+                    store_split(Hhi, Hlo, off + 4096, hh[1][0], hh[1][1], hh[1][2], hh[1][3]);
+                    if (lane == 0) {  // row 64: the bias channel h' = 1 (row % 8 == 0: chunk g is not permuted)
+                        const uint32_t o64 = 8 * 1024 + (uint32_t)(g << 4);
+                        *reinterpret_cast<float4*>(Hhi + o64) =
+                            make_float4(1.f, nv > 1 ? 1.f : 0.f, nv > 2 ? 1.f : 0.f, nv > 3 ? 1.f : 0.f);
+                        *reinterpret_cast<float4*>(Hlo + o64) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else if (g < 2 * ksteps) {  // zero K-quad completing the last 8-edge step (or an isolated node)
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int sl = 0; sl < NCOL; ++sl) {
+                        *reinterpret_cast<float4*>(Fhi + off + sl * 4096) = z;
+                        *reinterpret_cast<float4*>(Flo + off + sl * 4096) = z;
+                    }
+                    *reinterpret_cast<float4*>(Hhi + off) = z;
+                    *reinterpret_cast<float4*>(Hlo + off) = z;
+                    *reinterpret_cast<float4*>(Hhi + off + 4096) = z;
+                    *reinterpret_cast<float4*>(Hlo + off + 4096) = z;
+                    if (lane == 0) {
+                        const uint32_t o64 = 8 * 1024 + (uint32_t)(g << 4);
+                        *reinterpret_cast<float4*>(Hhi + o64) = z;
+                        *reinterpret_cast<float4*>(Hlo + o64) = z;
+                    }
+                }
+                umma::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&full[s]);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma::make_idesc_tf32(128, kAccCols);
+        int it = 0;
+        uint32_t na = 0;  // node counter of this CTA: accumulator set = na & 1
+        for (int r = r_begin; r < r_end; ++r, ++na) {
+            const int i = row0 + r;
+            const int deg = rowptr[i + 1] - rowptr[i];
+            const int nchunks = deg > 32 ? (deg + 31) >> 5 : 1;
+            const uint32_t set = na & 1u;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int n = min(32, deg - 32 * c);
+                const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
+                const int s = it % kSlots;
+                umma::mbar_wait(&full[s], ((uint32_t)it / kSlots) & 1u);
+                if (c == 0) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) umma::mbar_wait(&tempty[set * NT + t], ((na >> 1) & 1u) ^ 1u);
+                }
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    const uint32_t slot = umma::smem_u32(slots + s * SH::SLOT_BYTES);
+                    const uint32_t hhi = umma::desc_lo_kmajor_sw128(slot), hlo = umma::desc_lo_kmajor_sw128(slot + kHBytes);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const uint32_t d = tmem_base + (set * NT + t) * kAccCols;
+                        const uint32_t fhi = umma::desc_lo_kmajor_sw128(slot + 2 * kHBytes + SH::trow0(t) * 128);
+                        const uint32_t flo = umma::desc_lo_kmajor_sw128(slot + 2 * kHBytes + SH::F_BYTES + SH::trow0(t) * 128);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t k2 = 2u * ks;  // 32 bytes per K step, in 16-byte descriptor units
+                            umma::mma_tf32_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
+                                              umma::make_desc(hhi + k2, umma::kDescHiKmajorSw128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                            umma::mma_tf32_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
+                                              umma::make_desc(hlo + k2, umma::kDescHiKmajorSw128), idesc, 1u);
+                            umma::mma_tf32_ss(d, umma::make_desc(flo + k2, umma::kDescHiKmajorSw128),
+                                              umma::make_desc(hhi + k2, umma::kDescHiKmajorSw128), idesc, 1u);
+                        }
+                        if (c == nchunks - 1) umma::commit(&tfull[set * NT + t]);
+                    }
+                    umma::commit(&empty[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (set 0: warps 0-3, set 1: warps 4-7)
+        const uint32_t es = warp >> 2, wq = warp & 3;
+        uint32_t na = 0;
+        for (int r = r_begin; r < r_end; ++r, ++na) {
+            if ((na & 1u) != es) continue;
+            const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const uint32_t b = es * NT + t;
+                const bool live = (int)wq < SH::tgroups(t);  // this warp's 32 feature columns exist
+                // operand row of channel k' for this warp's column group: base + k' * kstride
+                float* dst;
+                size_t kstride;
+                if (t == 0) {
+                    dst = a0 + ((size_t)wq * rows_pad + r) * 32;
+                    kstride = (size_t)SH::NSL0 * rows_pad * 32;
+                } else if (t == 1 && wq == 0) {
+                    dst = a0 + ((size_t)NS * rows_pad + r) * 32;
+                    kstride = (size_t)SH::NSL0 * rows_pad * 32;
+                } else {
+                    const int comp = t == 1 ? (int)wq - 1 : (int)wq;
+                    dst = a1 + (size_t)comp * a1_comp_stride + ((size_t)(t == 1 ? 0 : 1) * rows_pad + r) * 32;
+                    kstride = (size_t)SH::NSL1 * rows_pad * 32;
+                }
+                dst += swz;
+                umma::mbar_wait(&tfull[b], (na >> 1) & 1u);
+                umma::fence_after_sync();
+                const uint32_t taddr = tmem_base + ((32u * wq) << 16) + b * kAccCols;
+                if (live) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        umma::tmem_ld32(taddr + 32u * half, v);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)(32 * half + k) * kstride, __uint_as_float(v[k]));
+                    }
+                    const uint32_t vb = umma::tmem_ld1(taddr + 64u);
+                    umma::wait_ld();
+                    __stcs(dst + (size_t)64 * kstride, __uint_as_float(vb));
+                }
+                umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&tempty[b]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) umma::tmem_dealloc<512>(tmem_base);
+}
+
+// ---- path 0e(x)1e->1e gather -----------------------------------------------------------------------------------------------
+//   p2_i[c, w] = sum_{e -> i} rhat_e[c] * sum_k' h'_e[k'] * Y_j(e)[k', w]        (one warp per node, lanes over w)
+__global__ void __launch_bounds__(256)
+conv_p2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ h,
+               const float* __restrict__ rhat, const float* __restrict__ y, int row0, int nrows, float* __restrict__ p2,
+               int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nrows) return;
+    const int i = row0 + r;
+    const int e0 = rowptr[i], e1 = rowptr[i + 1];
+    const float invd = 1.0f / (float)(e1 > e0 ? e1 - e0 : 1);
+    if (lane == 0) inv_deg[i] = invd;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    for (int e = e0; e < e1; ++e) {
+        const int j = col[e];
+        const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+        const float* he = h + (size_t)e * JAMUN_EDGE_HID;
+        const float h0 = he[lane], h1 = he[32 + lane];
+        const float* yj = y + (size_t)j * YLD + lane;
+        float acc[4] = {yj[JAMUN_EDGE_HID * JAMUN_V], 0.f, 0.f, 0.f};  // bias channel
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k & 3] = fmaf(__shfl_sync(0xffffffffu, h0, k), yj[k * JAMUN_V], acc[k & 3]);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k & 3] = fmaf(__shfl_sync(0xffffffffu, h1, k), yj[(32 + k) * JAMUN_V], acc[k & 3]);
+        const float tsum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        px = fmaf(rh.x, tsum, px);
+        py = fmaf(rh.y, tsum, py);
+        pz = fmaf(rh.z, tsum, pz);
+    }
+    const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
+    float* out = p2 + (size_t)i * p2_ld + lane;
+    out[0] = px * sc;
+    out[JAMUN_V] = py * sc;
+    out[2 * JAMUN_V] = pz * sc;
+}
+
+template <int S_IN, int V_IN>
+int launch_tc(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
+              int rows_pad, float* a0, float* a1, size_t comp, cudaStream_t s) {
+    using SH = Shape<S_IN, V_IN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_build_tc_kernel<S_IN, V_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SH::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            jb::set_error("conv_build_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return JAMUN_ECUDA;
+        }
+        attr_set = true;
+    }
+    const int blocks = nrows < jb::kNumSMs ? nrows : jb::kNumSMs;
+    conv_build_tc_kernel<S_IN, V_IN><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows, rows_pad,
+                                                                              a0, a1, comp);
+    return JAMUN_OK;
+}
+
+}  // namespace
+
+namespace jb {
+// Tensor-core aggregate builder + path-2 gather; same contract as jamun_conv_build_a (called from there).
+int conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h, const float* rhat,
+                  const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride, float* p2,
+                  int p2_ld, float p2_scale, float* inv_deg, cudaStream_t s) {
+    conv_p2_kernel<<<(nrows * 32 + 255) / 256, 256, 0, s>>>(rowptr, col, h, rhat, y, row0, nrows, p2, p2_ld, p2_scale, inv_deg);
+    if (s_in == JAMUN_S && v_in == JAMUN_V)
+        return launch_tc<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, s);
+    if (s_in == JAMUN_S0 && v_in == 0)
+        return launch_tc<JAMUN_S0, 0>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, 0, s);
+    jb::set_error("conv_build_tc: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
+    return JAMUN_EINVAL;
+}
+}  // namespace jb

@@ -95,6 +95,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
+}
+
 // ---- descriptors -------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart (SBO),
 // LBO = 1 (ignored for swizzled K-major), version 1 (Blackwell), layout type 2.

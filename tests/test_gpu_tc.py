@@ -133,3 +133,46 @@ def test_gemm_column_blocks_and_addend():
                     addend_ptrs=[addc.data_ptr()], addend_ld=[32])
     ref2 = 0.5 * (A.double() @ W[:, :32].double() + add.double())
     assert (out2.cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
+
+
+@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31]])
+def test_build_tc_matches_ffma_builder(models, sizes, monkeypatch):
+    """Tensor-core aggregate builder (3xTF32, tcgen05) writes the same A operand / path-2 sums as the FFMA2 builder."""
+    from jamun_b200 import data, engine, ops, synthetic
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors(sizes)
+    gen = torch.Generator().manual_seed(1)
+    y = (t["pos"] + 0.04 * torch.randn(t["pos"].shape, generator=gen)).cuda()
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    ctx = prod.sigma_context(0.04)
+    plan = prod.arch_module.plan(ctx.c_noise, "cuda")
+    ybar, p = ops.center_scale(y, topo.chain_ptr, ctx.c_in)
+    topo.build_csr(ybar, ctx.r_cut)
+    mu, step = plan.radial_grid(ctx.r_cut)
+    ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
+    N = p.shape[0]
+    for l, d_in in ((0, 56), (1, 216)):
+        b = plan.blocks[l]
+        x = torch.randn(N, d_in, generator=gen).cuda()
+        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        res = {}
+        if topo.a_ws is None:
+            engine.conv_tc(topo, b, x, torch.empty(N, 248, device="cuda"))  # allocates the operand workspace
+        for variant in ("1", "20"):
+            monkeypatch.setenv("JAMUN_BUILD_VARIANT", variant)
+            out = torch.full((N, 248), float("nan"), device="cuda")
+            topo.a_ws.fill_(float("nan"))
+            engine.conv_tc(topo, b, x, out)
+            torch.cuda.synchronize()
+            nst = 65 * ((d_in > 56) * 11 + (d_in == 56) * 2)
+            res[variant] = (topo.a_ws[: nst * topo.chunk_rows * 32].clone(), out)
+        a_ref, out_ref = res["1"]
+        a_tc, out_tc = res["20"]
+        live = ~torch.isnan(a_ref)
+        assert torch.equal(torch.isnan(a_tc), ~live), "different set of operand elements written"
+        scale = a_ref[live].abs().max().item()
+        err = (a_tc[live] - a_ref[live]).abs().max().item()
+        assert err <= 2e-6 * max(1.0, scale), f"block {l}: A operand err {err} scale {scale}"
+        err_o = (out_tc - out_ref).abs().max().item()
+        assert err_o <= 2e-5 * max(1.0, out_ref.abs().max().item()), f"block {l}: conv err {err_o}"
