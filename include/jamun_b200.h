@@ -114,6 +114,21 @@ int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, co
                        const float* rhat, const float* y, const int* chain_of, const int* chain_ptr, int src_max,
                        int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride,
                        float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream);
+/* Tensor-core form of jamun_conv_build_a's aggregate (same a0 / a1 operands, 3xTF32 products accumulated in
+ * tensor memory: elements agree with the FP32 builder to ~1e-6 relative).  Per receiver node the aggregate is the
+ * small GEMM F^T.H over its in-edges (K <= 33), run as tcgen05.mma by a persistent warp-specialised kernel.
+ * Writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL.  Does not compute the 0e(x)1e->1e gather: pair it with
+ * jamun_conv_p2 (which may run concurrently on another stream). */
+int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                        const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                        long long a1_comp_stride, float* inv_deg, jamun_stream_t stream);
+
+/* Path 0e(x)1e->1e of the convolution, transform-then-aggregate:
+ * p2[i, c*32+w] = sc * sum_{e->i} rhat_e[c] * sum_k' h'_e[k'] * y[col[e], k'*32+w],  sc = p2_scale/max(1,deg) (p2_scale != 0)
+ * or 1 (raw sums).  y: [N, 2176] rows from the per-node transform GEMM.  Also writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL. */
+int jamun_conv_p2(const int* rowptr, const int* col, const float* h, const float* rhat, const float* y, int row0,
+                  int nrows, float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream);
+
 int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
@@ -125,8 +140,10 @@ int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, co
  * arch/e3conv.py:131-133).  y = Lin_self(Gate(conv)) + Lin_skip(x_in);
  * x_new = mix ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next (if s_next).
  * Weights pre-scaled by 1/sqrt(fan_in): wself_s:[120,120] wself_v:[32,32] wskip_s:[s_in,120]
- * wskip_v:[32,32] or NULL.  skip_w, s_next: [152] per-irrep or NULL. */
-int jamun_block_tail(const float* conv, const float* x_in, int s_in, int v_in, const float* x_res,
+ * wskip_v:[32,32] or NULL.  skip_w, s_next: [152] per-irrep or NULL.
+ * vadd: [N, 96] or NULL -- added to the 1e part of conv before the gate (the 0e(x)1e->1e path when it was
+ * gathered by jamun_conv_p2 on another stream instead of through the GEMM epilogue). */
+int jamun_block_tail(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, const float* x_res,
                      const float* wself_s, const float* wself_v, const float* wskip_s, const float* wskip_v,
                      const float* skip_w, const float* s_next, float c_act, float c_gate, int N,
                      float* x_new, float* x_scaled, jamun_stream_t stream);

@@ -33,10 +33,12 @@ _PROTOS = {
     "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
     "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
+    "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
+    "jamun_conv_p2": ([c_f, c_f, c_f, c_f, c_f, I, I, c_f, I, F, c_f, c_f], I),
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
-    "jamun_block_tail": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
+    "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_head": ([c_f, c_f, c_f, c_f, F, I, c_f, c_f], I),
     "jamun_walk_step": ([c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, C.POINTER(WalkParams), c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
     "jamun_walk_advance": ([c_f, I, c_f], I),

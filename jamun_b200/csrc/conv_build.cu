@@ -21,12 +21,6 @@
 #include <stdlib.h>
 #include "common.cuh"
 
-namespace jb {
-int conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h, const float* rhat,
-                  const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride, float* p2,
-                  int p2_ld, float p2_scale, float* inv_deg, cudaStream_t s);
-}
-
 namespace {
 using namespace jb;
 
@@ -388,13 +382,6 @@ extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int*
                                                                        a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
     const char* venv = getenv("JAMUN_BUILD_VARIANT");  // tuning knob for experiments
     const int variant = venv ? atoi(venv) : 1;
-    if (variant == 20) {  // tensor-core aggregate (conv_build_tc.cu)
-        const int rc = jb::conv_build_tc(x, s_in, v_in, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, a1_comp_stride, p2,
-                                         p2_ld, p2_scale, inv_deg, s);
-        if (rc != JAMUN_OK) return rc;
-        JB_CHECK_LAUNCH();
-        return JAMUN_OK;
-    }
     const bool cached = max_degree <= MAXD;
     // block-staged kernel when every 8-node block's source range fits in shared memory (2 CTAs per SM)
     if (cached && src_max > 0 && chain_of && chain_ptr && row0 % 8 == 0 && variant == 8) {

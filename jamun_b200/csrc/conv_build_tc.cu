@@ -21,6 +21,7 @@
 // Two operand slots and two sets of three 80-column accumulators keep the roles overlapped; the kernel is persistent
 // with one CTA per SM (222 KB of shared memory) and is bound by the HBM write of A (91.5 KB per node).
 // The path 0e(x)1e->1e gather (p2) is conv_p2_kernel below.
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -53,6 +54,10 @@ struct Shape {
     __host__ __device__ static constexpr int trow0(int t) { return t == 0 ? 0 : t == 1 ? NS * 32 : NS * 32 + 128; }
 };
 
+__device__ unsigned long long g_tc_trace[64 * 16];
+#define TC_TRACE(slot_, k_)                                                                      \
+    if (TRACE && blockIdx.x == 0 && lane == 0 && (slot_) < 64) g_tc_trace[(slot_) * 16 + (k_)] = clock64()
+
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void store_split(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, float a, float b,
@@ -62,11 +67,11 @@ __device__ __forceinline__ void store_split(unsigned char* hi_tile, unsigned cha
     *reinterpret_cast<float4*>(lo_tile + off) = make_float4(a - ah, b - bh, c - ch, d - dh);
 }
 
-template <int S_IN, int V_IN>
+template <int S_IN, int V_IN, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                      const float* __restrict__ h, const float* __restrict__ rhat, int row0, int nrows, int rows_pad,
-                     float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride) {
+                     float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride, float* __restrict__ inv_deg) {
     using SH = Shape<S_IN, V_IN>;
     constexpr int NS = SH::NS, NCOL = SH::NCOL, NT = SH::NT;
     constexpr int kBufs = 2 * NT;
@@ -98,25 +103,51 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
     umma::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int per = (nrows + gridDim.x - 1) / gridDim.x;
-    const int r_begin = blockIdx.x * per;
-    const int r_end = min(nrows, r_begin + per);
+    // rows are dealt round-robin: at any moment the CTAs work on ~gridDim.x consecutive rows, so the 128-byte lines they
+    // write into each operand stage are neighbours (DRAM page locality of the 1.6 GB output stream)
+    const int r_begin = blockIdx.x, r_step = gridDim.x, r_end = nrows;
 
     if (warp > kMmaWarp) {
         // ------------------------------------------------------------------ producers
         const int g = warp - kMmaWarp - 1;
         const uint32_t off = (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)((g ^ (lane & 7)) << 4);
         int it = 0;
-        for (int r = r_begin; r < r_end; ++r) {
-            const int i = row0 + r;
-            const int e0 = rowptr[i];
-            const int deg = rowptr[i + 1] - e0;
+        // index prefetch: row extents two rows ahead, this warp's four source indices one row ahead -- the gathers of a
+        // row then start without the rowptr -> col -> x chain of dependent L2 round trips
+        int e0_n = 0, deg_n = 0, e0_nn = 0, deg_nn = 0;
+        int jn[4] = {0, 0, 0, 0};
+        if (r_begin < r_end) {
+            e0_n = rowptr[row0 + r_begin];
+            deg_n = rowptr[row0 + r_begin + 1] - e0_n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jn[q] = 4 * g + q < deg_n ? col[e0_n + 4 * g + q] : 0;
+        }
+        if (r_begin + r_step < r_end) {
+            e0_nn = rowptr[row0 + r_begin + r_step];
+            deg_nn = rowptr[row0 + r_begin + r_step + 1] - e0_nn;
+        }
+        for (int r = r_begin; r < r_end; r += r_step) {
+            const int e0 = e0_n, deg = deg_n;
+            int jc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jc[q] = jn[q];
+            e0_n = e0_nn, deg_n = deg_nn;
+            if (r + r_step < r_end) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) jn[q] = 4 * g + q < deg_n ? col[e0_n + 4 * g + q] : 0;
+            }
+            if (r + 2 * r_step < r_end) {
+                e0_nn = rowptr[row0 + r + 2 * r_step];
+                deg_nn = rowptr[row0 + r + 2 * r_step + 1] - e0_nn;
+            }
             const int nchunks = deg > 32 ? (deg + 31) >> 5 : 1;
+            if (g == 0 && lane == 0 && inv_deg) inv_deg[row0 + r] = 1.0f / (float)(deg > 0 ? deg : 1);
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int n = min(32, deg - 32 * c);
                 const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
+                if (g == 0) TC_TRACE(it, 0);
                 const int s = it % kSlots;
-                umma::mbar_wait(&empty[s], (((uint32_t)it / kSlots) & 1u) ^ 1u);
+                const uint32_t empty_parity = (((uint32_t)it / kSlots) & 1u) ^ 1u;  // waited on just before the stores
                 unsigned char* slot = slots + s * SH::SLOT_BYTES;
                 unsigned char* Hhi = slot;
                 unsigned char* Hlo = slot + kHBytes;
@@ -125,36 +156,51 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                 if (4 * g < n) {
                     const int nv = min(4, n - 4 * g);
                     const int eb = e0 + 32 * c + 4 * g;
-                    float f[NCOL][4];
-                    float hh[2][4];
+                    // phase 1: every gather of the four in-edges is issued before any use (missing edges re-read edge 0
+                    // and are masked below), so the warp pays one L2 round trip per item, not one per edge
+                    float xs[NS][4], xv[V_IN > 0 ? 3 : 1][4], hh[2][4];
+                    float4 rh[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (q < nv) {
-                            const int e = eb + q;
-                            const int j = col[e];
-                            const float* xr = x + (size_t)j * SH::D_IN;
+                        const bool ok = q < nv;
+                        const int e = ok ? eb + q : eb;
+                        const int j = (c == 0 && ok) ? jc[q] : col[e];
+                        const float* xr = x + (size_t)j * SH::D_IN;
 #pragma unroll
-                            for (int sl = 0; sl < NS; ++sl) f[sl][q] = (lane + 32 * sl < S_IN) ? xr[lane + 32 * sl] : 0.f;
-                            if constexpr (V_IN > 0) {
-                                const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
-                                const float vx = xr[S_IN + lane], vy = xr[S_IN + V_IN + lane], vz = xr[S_IN + 2 * V_IN + lane];
-                                f[NS][q] = vx * rh.x + vy * rh.y + vz * rh.z;
-                                f[NS + 1][q] = vx * kInvSqrt3;
-                                f[NS + 2][q] = vy * kInvSqrt3;
-                                f[NS + 3][q] = vz * kInvSqrt3;
-                                f[NS + 4][q] = (vy * rh.z - vz * rh.y) * kInvSqrt2;
-                                f[NS + 5][q] = (vz * rh.x - vx * rh.z) * kInvSqrt2;
-                                f[NS + 6][q] = (vx * rh.y - vy * rh.x) * kInvSqrt2;
-                            }
-                            const float* he = h + (size_t)e * JAMUN_EDGE_HID;
-                            hh[0][q] = he[lane];
-                            hh[1][q] = he[32 + lane];
-                        } else {
-#pragma unroll
-                            for (int sl = 0; sl < NCOL; ++sl) f[sl][q] = 0.f;
-                            hh[0][q] = hh[1][q] = 0.f;
+                        for (int sl = 0; sl < NS; ++sl) xs[sl][q] = xr[(lane + 32 * sl < S_IN) ? lane + 32 * sl : lane];
+                        if constexpr (V_IN > 0) {
+                            rh[q] = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+                            xv[0][q] = xr[S_IN + lane];
+                            xv[1][q] = xr[S_IN + V_IN + lane];
+                            xv[2][q] = xr[S_IN + 2 * V_IN + lane];
                         }
+                        const float* he = h + (size_t)e * JAMUN_EDGE_HID;
+                        hh[0][q] = he[lane];
+                        hh[1][q] = he[32 + lane];
                     }
+                    // phase 2: features
+                    float f[NCOL][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float m = q < nv ? 1.f : 0.f;
+#pragma unroll
+                        for (int sl = 0; sl < NS; ++sl) f[sl][q] = (lane + 32 * sl < S_IN) ? m * xs[sl][q] : 0.f;
+                        if constexpr (V_IN > 0) {
+                            const float vx = m * xv[0][q], vy = m * xv[1][q], vz = m * xv[2][q];
+                            f[NS][q] = vx * rh[q].x + vy * rh[q].y + vz * rh[q].z;
+                            f[NS + 1][q] = vx * kInvSqrt3;
+                            f[NS + 2][q] = vy * kInvSqrt3;
+                            f[NS + 3][q] = vz * kInvSqrt3;
+                            f[NS + 4][q] = (vy * rh[q].z - vz * rh[q].y) * kInvSqrt2;
+                            f[NS + 5][q] = (vz * rh[q].x - vx * rh[q].z) * kInvSqrt2;
+                            f[NS + 6][q] = (vx * rh[q].y - vy * rh[q].x) * kInvSqrt2;
+                        }
+                        hh[0][q] *= m;
+                        hh[1][q] *= m;
+                    }
+                    if (g == 0) TC_TRACE(it, 1);
+                    umma::mbar_wait(&empty[s], empty_parity);  // gathers above overlap the MMAs still reading this slot
+                    if (g == 0) TC_TRACE(it, 2);
 #pragma unroll
                     for (int sl = 0; sl < NCOL; ++sl) store_split(Fhi, Flo, off + sl * 4096, f[sl][0], f[sl][1], f[sl][2], f[sl][3]);
                     store_split(Hhi, Hlo, off, hh[0][0], hh[0][1], hh[0][2], hh[0][3]);
@@ -166,6 +212,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                         *reinterpret_cast<float4*>(Hlo + o64) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 } else if (g < 2 * ksteps) {  // zero K-quad completing the last 8-edge step (or an isolated node)
+                    umma::mbar_wait(&empty[s], empty_parity);
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int sl = 0; sl < NCOL; ++sl) {
@@ -181,10 +228,13 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                         *reinterpret_cast<float4*>(Hhi + o64) = z;
                         *reinterpret_cast<float4*>(Hlo + o64) = z;
                     }
+                } else {
+                    umma::mbar_wait(&empty[s], empty_parity);  // idle warps stay in step: one arrival per warp per phase
                 }
                 umma::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&full[s]);
+                if (g == 0) TC_TRACE(it, 3);
             }
         }
     } else if (warp == kMmaWarp) {
@@ -192,7 +242,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
         constexpr uint32_t idesc = umma::make_idesc_tf32(128, kAccCols);
         int it = 0;
         uint32_t na = 0;  // node counter of this CTA: accumulator set = na & 1
-        for (int r = r_begin; r < r_end; ++r, ++na) {
+        for (int r = r_begin; r < r_end; r += r_step, ++na) {
             const int i = row0 + r;
             const int deg = rowptr[i + 1] - rowptr[i];
             const int nchunks = deg > 32 ? (deg + 31) >> 5 : 1;
@@ -201,11 +251,14 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                 const int n = min(32, deg - 32 * c);
                 const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
                 const int s = it % kSlots;
+                TC_TRACE(it, 4);
                 umma::mbar_wait(&full[s], ((uint32_t)it / kSlots) & 1u);
+                TC_TRACE(it, 5);
                 if (c == 0) {
 #pragma unroll
                     for (int t = 0; t < NT; ++t) umma::mbar_wait(&tempty[set * NT + t], ((na >> 1) & 1u) ^ 1u);
                 }
+                TC_TRACE(it, 6);
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
                     const uint32_t slot = umma::smem_u32(slots + s * SH::SLOT_BYTES);
@@ -229,13 +282,14 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                     umma::commit(&empty[s]);
                 }
                 __syncwarp();
+                TC_TRACE(it, 7);
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (set 0: warps 0-3, set 1: warps 4-7)
         const uint32_t es = warp >> 2, wq = warp & 3;
         uint32_t na = 0;
-        for (int r = r_begin; r < r_end; ++r, ++na) {
+        for (int r = r_begin; r < r_end; r += r_step, ++na) {
             if ((na & 1u) != es) continue;
             const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);
 #pragma unroll
@@ -257,7 +311,9 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                     kstride = (size_t)SH::NSL1 * rows_pad * 32;
                 }
                 dst += swz;
+                if (wq == 0 && t == 0) TC_TRACE(na, 8);
                 umma::mbar_wait(&tfull[b], (na >> 1) & 1u);
+                if (wq == 0) TC_TRACE(na, 9 + t);
                 umma::fence_after_sync();
                 const uint32_t taddr = tmem_base + ((32u * wq) << 16) + b * kAccCols;
                 if (live) {
@@ -276,6 +332,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&tempty[b]);
+                if (wq == 0) TC_TRACE(na, 12 + t);
             }
         }
     }
@@ -296,7 +353,7 @@ conv_p2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, cons
     const int i = row0 + r;
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
     const float invd = 1.0f / (float)(e1 > e0 ? e1 - e0 : 1);
-    if (lane == 0) inv_deg[i] = invd;
+    if (lane == 0 && inv_deg) inv_deg[i] = invd;
     float px = 0.f, py = 0.f, pz = 0.f;
     for (int e = e0; e < e1; ++e) {
         const int j = col[e];
@@ -321,39 +378,67 @@ conv_p2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, cons
     out[2 * JAMUN_V] = pz * sc;
 }
 
-template <int S_IN, int V_IN>
+template <int S_IN, int V_IN, bool TRACE>
 int launch_tc(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
-              int rows_pad, float* a0, float* a1, size_t comp, cudaStream_t s) {
+              int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, cudaStream_t s) {
     using SH = Shape<S_IN, V_IN>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_build_tc_kernel<S_IN, V_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_build_tc_kernel<S_IN, V_IN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SH::SMEM_BYTES);
         if (e != cudaSuccess) {
-            jb::set_error("conv_build_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            jb::set_error("jamun_conv_build_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return JAMUN_ECUDA;
         }
         attr_set = true;
     }
     const int blocks = nrows < jb::kNumSMs ? nrows : jb::kNumSMs;
-    conv_build_tc_kernel<S_IN, V_IN><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows, rows_pad,
-                                                                              a0, a1, comp);
+    conv_build_tc_kernel<S_IN, V_IN, TRACE><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows,
+                                                                                     rows_pad, a0, a1, comp, inv_deg);
     return JAMUN_OK;
 }
 
 }  // namespace
 
-namespace jb {
-// Tensor-core aggregate builder + path-2 gather; same contract as jamun_conv_build_a (called from there).
-int conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h, const float* rhat,
-                  const float* y, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride, float* p2,
-                  int p2_ld, float p2_scale, float* inv_deg, cudaStream_t s) {
-    conv_p2_kernel<<<(nrows * 32 + 255) / 256, 256, 0, s>>>(rowptr, col, h, rhat, y, row0, nrows, p2, p2_ld, p2_scale, inv_deg);
-    if (s_in == JAMUN_S && v_in == JAMUN_V)
-        return launch_tc<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, s);
-    if (s_in == JAMUN_S0 && v_in == 0)
-        return launch_tc<JAMUN_S0, 0>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, 0, s);
-    jb::set_error("conv_build_tc: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
-    return JAMUN_EINVAL;
+// a0: [65*nslots0][rows_pad][32]; a1: 3 x [65*2][rows_pad][32] (component stride a1_comp_stride floats; unused when v_in == 0)
+extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                                   const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                                   long long a1_comp_stride, float* inv_deg, jamun_stream_t stream) {
+    JB_CHECK_ARG(x && rowptr && col && h && rhat && a0, "null argument");
+    JB_CHECK_ARG(nrows <= rows_pad, "nrows exceeds rows_pad");
+    JB_CHECK_ARG(((size_t)a0 & 127) == 0 && ((size_t)rhat & 15) == 0, "a0 must be 128-byte, rhat 16-byte aligned");
+    if (nrows == 0) return JAMUN_OK;
+    cudaStream_t s = jb::as_stream(stream);
+    int rc;
+    if (s_in == JAMUN_S && v_in == JAMUN_V) {
+        JB_CHECK_ARG(a1 && ((size_t)a1 & 127) == 0, "a1 (128-byte aligned) required for vector inputs");
+        const char* t = getenv("JAMUN_TC_TRACE");  // debug: per-item role timestamps of CTA 0 (jamun_debug_tc_trace)
+        rc = (t && atoi(t)) ? launch_tc<JAMUN_S, JAMUN_V, true>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
+                                                                (size_t)a1_comp_stride, inv_deg, s)
+                            : launch_tc<JAMUN_S, JAMUN_V, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
+                                                                 (size_t)a1_comp_stride, inv_deg, s);
+    } else if (s_in == JAMUN_S0 && v_in == 0) {
+        rc = launch_tc<JAMUN_S0, 0, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, 0, inv_deg, s);
+    } else {
+        jb::set_error("jamun_conv_build_tc: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
+        return JAMUN_EINVAL;
+    }
+    if (rc != JAMUN_OK) return rc;
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
 }
-}  // namespace jb
+
+extern "C" int jamun_conv_p2(const int* rowptr, const int* col, const float* h, const float* rhat, const float* y, int row0,
+                             int nrows, float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream) {
+    JB_CHECK_ARG(rowptr && col && h && rhat && y && p2, "null argument");
+    if (nrows == 0) return JAMUN_OK;
+    conv_p2_kernel<<<(nrows * 32 + 255) / 256, 256, 0, jb::as_stream(stream)>>>(rowptr, col, h, rhat, y, row0, nrows, p2, p2_ld,
+                                                                                p2_scale, inv_deg);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+// debug: per-item role timestamps of CTA 0 (JAMUN_TC_TRACE=1)
+extern "C" int jamun_debug_tc_trace(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(g_tc_trace)) == cudaSuccess ? 0 : 1;
+}

@@ -173,7 +173,8 @@ conv_simt_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, co
 // ---- tail: Gate -> self-interaction Linear, + skip Linear(x_in), noise-conditional skip / next-layer scaling
 template <int S_IN, int V_IN>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-block_tail_kernel(const float* __restrict__ conv, const float* __restrict__ x_in, const float* __restrict__ x_res,
+block_tail_kernel(const float* __restrict__ conv, const float* __restrict__ vadd, const float* __restrict__ x_in,
+                  const float* __restrict__ x_res,
                   const float* __restrict__ wself_s, const float* __restrict__ wself_v,
                   const float* __restrict__ wskip_s, const float* __restrict__ wskip_v,
                   const float* __restrict__ skip_w, const float* __restrict__ s_next, float c_act, float c_gate,
@@ -198,7 +199,11 @@ block_tail_kernel(const float* __restrict__ conv, const float* __restrict__ x_in
             }
             const float gate = c_gate * sigmoidf_acc(o[S + lane]);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) Gs[r * HID + S + c * V + lane] = o[SO + c * V + lane] * gate;
+            for (int c = 0; c < 3; ++c) {
+                float v = o[SO + c * V + lane];
+                if (vadd) v += vadd[(size_t)i * (3 * V) + c * V + lane];  // 0e(x)1e->1e part gathered separately (jamun_conv_p2)
+                Gs[r * HID + S + c * V + lane] = v * gate;
+            }
             for (int t = lane; t < D_IN; t += 32) Xs[r * D_IN + t] = x_in[(size_t)i * D_IN + t];
         } else {
             for (int t = lane; t < HID; t += 32) Gs[r * HID + t] = 0.f;
@@ -379,7 +384,7 @@ extern "C" int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* row
     return JAMUN_OK;
 }
 
-extern "C" int jamun_block_tail(const float* conv, const float* x_in, int s_in, int v_in, const float* x_res,
+extern "C" int jamun_block_tail(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, const float* x_res,
                                 const float* wself_s, const float* wself_v, const float* wskip_s, const float* wskip_v,
                                 const float* skip_w, const float* s_next, float c_act, float c_gate, int N,
                                 float* x_new, float* x_scaled, jamun_stream_t stream) {
@@ -392,13 +397,13 @@ extern "C" int jamun_block_tail(const float* conv, const float* x_in, int s_in, 
         JB_CHECK_ARG(wskip_v, "wskip_v required for vector inputs");
         constexpr size_t smem = (size_t)WARPS * NPW * (JAMUN_HID + JAMUN_HID) * sizeof(float);
         if (int rc = set_smem(block_tail_kernel<JAMUN_S, JAMUN_V>, smem)) return rc;
-        block_tail_kernel<JAMUN_S, JAMUN_V><<<blocks, WARPS * 32, smem, s>>>(conv, x_in, x_res, wself_s, wself_v, wskip_s,
+        block_tail_kernel<JAMUN_S, JAMUN_V><<<blocks, WARPS * 32, smem, s>>>(conv, vadd, x_in, x_res, wself_s, wself_v, wskip_s,
                                                                             wskip_v, skip_w, s_next, c_act, c_gate, N,
                                                                             x_new, x_scaled);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
         constexpr size_t smem = (size_t)WARPS * NPW * (JAMUN_HID + JAMUN_S0) * sizeof(float);
         if (int rc = set_smem(block_tail_kernel<JAMUN_S0, 0>, smem)) return rc;
-        block_tail_kernel<JAMUN_S0, 0><<<blocks, WARPS * 32, smem, s>>>(conv, x_in, x_res, wself_s, wself_v, wskip_s,
+        block_tail_kernel<JAMUN_S0, 0><<<blocks, WARPS * 32, smem, s>>>(conv, vadd, x_in, x_res, wself_s, wself_v, wskip_s,
                                                                        wskip_v, skip_w, s_next, c_act, c_gate, N, x_new,
                                                                        x_scaled);
     } else {

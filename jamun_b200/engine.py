@@ -21,6 +21,9 @@ from .irreps import Irreps
 # "tc": aggregate builder + tcgen05 3xTF32 GEMM (product path); "simt": the exact-fp32 CUDA-core kernel (kept for
 # A/B validation of the tensor-core path, selectable with JAMUN_B200_CONV=simt)
 CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
+# aggregate builder of the tensor-core path: "tc" = tcgen05 per-node products (jamun_conv_build_tc) with the 0e(x)1e->1e
+# gather (jamun_conv_p2) on a side stream; "ffma" = the FP32-pipe builder jamun_conv_build_a (exact fp32 aggregate)
+BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
 Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
 
@@ -103,6 +106,9 @@ class Topology:
         max_rows = max(128, (self.WORKSPACE_BYTES // per_row) // 128 * 128)
         self.chunk_rows = min(rows_pad, max_rows)
         self.a_ws = None  # allocated on first use
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.p2_pending = False
         self.y0 = None
         self.y0_key = None
 
@@ -194,7 +200,9 @@ class E3ConvPlan:
 
 def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None) -> None:
     """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
-    13 column blocks) -> jamun_conv_build_a (aggregate of the other paths + gather of Y, CUDA cores) -> jamun_gemm_tf32x3."""
+    17 column blocks) -> aggregate A of the other paths (jamun_conv_build_tc: per-node tcgen05 products; or the FP32-pipe
+    jamun_conv_build_a) -> contraction jamun_gemm_tf32x3.  With the tensor-core builder the gather of Y (jamun_conv_p2) runs
+    on a side stream: call conv_tc_join() before consuming `out` and add its result to out[:, 152:] (block_tail does)."""
     s_in, v_in = b["s_in"], b["v_in"]
     ns = (s_in + 31) // 32
     nsl0, nsl1 = ns + (1 if v_in else 0), (2 if v_in else 0)
@@ -225,23 +233,52 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
     base = topo.a_ws.data_ptr()
     a1_off = st0 * rp * 32
     comp = st1 * rp * 32
+    build_impl = os.environ.get("JAMUN_B200_BUILD", BUILD_IMPL)
+    if build_impl == "tc":
+        # the 0e(x)1e->1e gather needs only Y and h: it runs on the side stream under the builder and the contraction, and
+        # its result joins in block_tail (hidden blocks: topo.p2 as the `vadd` operand; initial block: written in place)
+        main = torch.cuda.current_stream()
+        topo.ev_fork.record(main)
+        with torch.cuda.stream(topo.side_stream):
+            topo.side_stream.wait_event(topo.ev_fork)
+            if v_in:
+                ops.conv_p2(topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, 0, N, topo.p2.data_ptr(), 96, b["alpha1"])
+            else:
+                ops.conv_p2(topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, 0, N, out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"])
+            topo.ev_join.record(topo.side_stream)
+        topo.p2_pending = True
     for row0 in range(0, N, rp):
         nrows = min(rp, N - row0)
+        if build_impl == "tc":
+            ops.conv_build_tc(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, row0, nrows, rp, base,
+                              base + 4 * a1_off if v_in else None, comp, topo.inv_deg)
         if v_in:
-            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base,
-                             base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg)
+            if build_impl != "tc":
+                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base,
+                                 base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg)
             a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
             b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
             p2 = topo.p2.data_ptr() + 4 * row0 * 96
+            addend = None if build_impl == "tc" else [None, p2, p2 + 4 * 32, p2 + 4 * 64]
             ops.gemm_tf32x3(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
                             [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
                             out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN,
-                            addend_ptrs=[None, p2, p2 + 4 * 32, p2 + 4 * 64], addend_ld=[0, 96, 96, 96])
-        else:  # initial block: the 1e output is the path-2 gather alone, written in place by the builder
-            ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base, None, 0,
-                             out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
+                            addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96])
+        else:  # initial block: the 1e output is the path-2 gather alone, written in place
+            if build_impl != "tc":
+                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base, None, 0,
+                                 out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
             ops.gemm_tf32x3([base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
                             topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
+
+
+def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:
+    """Join the side-stream gather started by conv_tc; returns the [N, 96] addend for block_tail (hidden blocks) or None."""
+    if not getattr(topo, "p2_pending", False):
+        return None
+    torch.cuda.current_stream().wait_event(topo.ev_join)
+    topo.p2_pending = False
+    return topo.p2 if b["v_in"] else None
 
 
 def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,
@@ -260,17 +297,19 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
     x_in, x_res = topo.x0, None
     nb = len(plan.blocks)
     for l, b in enumerate(plan.blocks):
+        vadd = None
         ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
         if CONV_IMPL == "simt":
             ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
                          b["alpha0"], b["alpha1"], topo.conv)
         else:
             conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None)
+            vadd = conv_tc_join(topo, b)
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None
         s_next = plan.scales[l] if l < nb - 1 else None
         ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"],
-                       b["wskip_v"], skip_w, s_next, b["c_act"], b["c_gate"], x_new, x_scaled if l < nb - 1 else None)
+                       b["wskip_v"], skip_w, s_next, b["c_act"], b["c_gate"], x_new, x_scaled if l < nb - 1 else None, vadd=vadd)
         x_in, x_res = x_scaled, x_new
     ops.head(x_res, plan.head_w1s, plan.head_w1v, plan.head_w2, plan.head_cgate, g_out)
     return g_out

@@ -124,6 +124,23 @@ def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, y, chain_of, cha
     _count()
 
 
+def conv_build_tc(x, s_in: int, v_in: int, rowptr, col, h, rhat, row0: int, nrows: int, rows_pad: int, a0_ptr: int, a1_ptr: int,
+                  a1_comp_stride: int, inv_deg=None):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_build_tc(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), row0, nrows,
+                                        rows_pad, a0_ptr, a1_ptr, int(a1_comp_stride), _ptr(inv_deg), _stream())
+    _lib.check(rc, "jamun_conv_build_tc")
+    _count()
+
+
+def conv_p2(rowptr, col, h, rhat, y, row0: int, nrows: int, p2_ptr: int, p2_ld: int, p2_scale: float, inv_deg=None):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_p2(_ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), _ptr(y), row0, nrows, p2_ptr, p2_ld,
+                                  float(p2_scale), _ptr(inv_deg), _stream())
+    _lib.check(rc, "jamun_conv_p2")
+    _count()
+
+
 def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
     rc = _lib.lib().jamun_pack_rows(_ptr(x), x.shape[1], col0, ncols, x.shape[0], rows_pad, _ptr(a), _stream())
     _lib.check(rc, "jamun_pack_rows")
@@ -145,9 +162,9 @@ def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: 
 
 
 def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
-               c_act: float, c_gate: float, x_new, x_scaled):
+               c_act: float, c_gate: float, x_new, x_scaled, vadd=None):
     N = conv.shape[0]
-    rc = _lib.lib().jamun_block_tail(_ptr(conv), _ptr(x_in), s_in, v_in, _ptr(x_res), _ptr(wself_s), _ptr(wself_v),
+    rc = _lib.lib().jamun_block_tail(_ptr(conv), _ptr(vadd), _ptr(x_in), s_in, v_in, _ptr(x_res), _ptr(wself_s), _ptr(wself_v),
                                      _ptr(wskip_s), _ptr(wskip_v), _ptr(skip_w), _ptr(s_next), float(c_act),
                                      float(c_gate), N, _ptr(x_new), _ptr(x_scaled), _stream())
     _lib.check(rc, "jamun_block_tail")

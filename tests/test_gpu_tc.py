@@ -102,6 +102,9 @@ def test_conv_tc_matches_simt_and_fp64(models, sizes):
         ops.conv_fwd(x, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"], b["alpha0"], b["alpha1"], ref)
         got = torch.full((N, 248), float("nan"), device="cuda")
         engine.conv_tc(topo, b, x, got)
+        vadd = engine.conv_tc_join(topo, b)  # 0e(x)1e->1e part gathered on the side stream, normally added by block_tail
+        if vadd is not None:
+            got[:, 152:] += vadd
         torch.cuda.synchronize()
         err = (got - ref).abs().max().item()
         scale = ref.abs().max().item()
@@ -159,16 +162,20 @@ def test_build_tc_matches_ffma_builder(models, sizes, monkeypatch):
         res = {}
         if topo.a_ws is None:
             engine.conv_tc(topo, b, x, torch.empty(N, 248, device="cuda"))  # allocates the operand workspace
-        for variant in ("1", "20"):
-            monkeypatch.setenv("JAMUN_BUILD_VARIANT", variant)
+            engine.conv_tc_join(topo, b)
+        for variant in ("ffma", "tc"):
+            monkeypatch.setenv("JAMUN_B200_BUILD", variant)
             out = torch.full((N, 248), float("nan"), device="cuda")
             topo.a_ws.fill_(float("nan"))
             engine.conv_tc(topo, b, x, out)
+            vadd = engine.conv_tc_join(topo, b)
+            if vadd is not None:
+                out[:, 152:] += vadd
             torch.cuda.synchronize()
             nst = 65 * ((d_in > 56) * 11 + (d_in == 56) * 2)
             res[variant] = (topo.a_ws[: nst * topo.chunk_rows * 32].clone(), out)
-        a_ref, out_ref = res["1"]
-        a_tc, out_tc = res["20"]
+        a_ref, out_ref = res["ffma"]
+        a_tc, out_tc = res["tc"]
         live = ~torch.isnan(a_ref)
         assert torch.equal(torch.isnan(a_tc), ~live), "different set of operand elements written"
         scale = a_ref[live].abs().max().item()
