@@ -74,6 +74,11 @@ int jamun_radius_csr(const float* pos, const int* chain_of, const int* chain_ptr
 /* Edge featurisation (arch/e3conv.py:110-127): for each CSR edge, rhat = (p[src]-p[dst])/|.| (so
  * sh = [1, sqrt3*rhat]) and the 32 Gaussian radial bases exp(-((d-mu_k)/step)^2)/1.12.
  * rhat: [cap,4] (x,y,z,d)  rb: [cap, JAMUN_NBASIS]  mu: [JAMUN_NBASIS]. */
+/* Out-edge lists: src_eid[src_rowptr[j] .. src_rowptr[j+1]) = positions e of the receiver-major edge list with
+ * col[e] == j (order within a source unspecified).  scratch: [N+1] ints. */
+int jamun_csr_by_source(const int* rowptr, const int* col, int N, int cap, int* scratch, int* src_rowptr, int* src_eid,
+                        jamun_stream_t stream);
+
 int jamun_edge_geom(const float* p, const int* rowptr, const int* col, const int* edst, int N, int cap,
                     const float* mu, float step, float* rhat, float* rb, jamun_stream_t stream);
 
@@ -124,10 +129,13 @@ int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, c
                         long long a1_comp_stride, float* inv_deg, jamun_stream_t stream);
 
 /* Path 0e(x)1e->1e of the convolution, transform-then-aggregate:
- * p2[i, c*32+w] = sc * sum_{e->i} rhat_e[c] * sum_k' h'_e[k'] * y[col[e], k'*32+w],  sc = p2_scale/max(1,deg) (p2_scale != 0)
- * or 1 (raw sums).  y: [N, 2176] rows from the per-node transform GEMM.  Also writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL. */
-int jamun_conv_p2(const int* rowptr, const int* col, const float* h, const float* rhat, const float* y, int row0,
-                  int nrows, float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream);
+ * p2[i, c*32+w] = sc * sum_{e->i} rhat_e[c] * T_e[w],  T_e[w] = sum_k' h'_e[k'] * y[col[e], k'*32+w],
+ * sc = p2_scale/max(1,deg) (p2_scale != 0) or 1 (raw sums).  y: [N, 2176] rows from the per-node transform GEMM.
+ * T is evaluated source-major (src_rowptr / src_eid from jamun_csr_by_source) into t_edge: [cap, 32] scratch.
+ * Also writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL. */
+int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, const float* h, const float* rhat,
+                  const float* y, int N, float* t_edge, float* p2, int p2_ld, float p2_scale, float* inv_deg,
+                  jamun_stream_t stream);
 
 int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,

@@ -341,35 +341,90 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
     if (warp == kMmaWarp) umma::tmem_dealloc<512>(tmem_base);
 }
 
-// ---- path 0e(x)1e->1e gather -----------------------------------------------------------------------------------------------
-//   p2_i[c, w] = sum_{e -> i} rhat_e[c] * sum_k' h'_e[k'] * Y_j(e)[k', w]        (one warp per node, lanes over w)
+// ---- path 0e(x)1e->1e ------------------------------------------------------------------------------------------------------
+//   p2_i[c, w] = sum_{e -> i} rhat_e[c] * T_e[w],     T_e[w] = sum_k' h'_e[k'] * Y_j(e)[k', w]
+// T is evaluated source-major: one warp per source node j keeps its transformed row Y_j (65 x 32) in registers and walks
+// j's out-edges (CSR by source), so Y is read once (158 MB) instead of once per edge (2.4 GB of L2 gathers); the per-edge
+// channels h_e are warp-uniform 16-byte loads.  The receiver-side sum is a contiguous pass over T (edges are receiver-major).
+constexpr int kP2Chunk = 16;  // out-edges whose radial channels are staged per pass
+constexpr int kP2Warps = 4;
+__global__ void __launch_bounds__(32 * kP2Warps, 5)
+conv_p2_edge_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ src_eid, const float* __restrict__ h,
+                    const float* __restrict__ y, int N, float* __restrict__ t_edge) {
+    __shared__ __align__(16) float hs[kP2Warps][kP2Chunk][JAMUN_EDGE_HID];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= N) return;
+    const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
+    if (s0 == s1) return;
+    int eid = (lane < kP2Chunk && s0 + lane < s1) ? src_eid[s0 + lane] : 0;
+    float yr[JAMUN_EDGE_HID + 1];
+    const float* yj = y + (size_t)j * YLD + lane;
+#pragma unroll
+    for (int k = 0; k <= JAMUN_EDGE_HID; ++k) yr[k] = yj[k * JAMUN_V];
+    const int half = lane >> 4, l16 = lane & 15;
+    for (int c0 = s0; c0 < s1; c0 += kP2Chunk) {
+        const int cnt = min(kP2Chunk, s1 - c0);
+        // stage the chunk's channel rows with 16-byte async copies (two 256-byte rows per instruction, no registers held):
+        // the whole chunk is in flight together, one L2 round trip per chunk
+#pragma unroll
+        for (int q2 = 0; q2 < kP2Chunk / 2; ++q2) {
+            const int q = 2 * q2 + half;
+            const int e = __shfl_sync(0xffffffffu, eid, q);
+            if (q < cnt) {
+                const uint32_t dst = umma::smem_u32(&hs[wib][q][4 * l16]);
+                const float* src = h + (size_t)e * JAMUN_EDGE_HID + 4 * l16;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int eid_cur = eid;
+        if (c0 + kP2Chunk < s1) eid = (lane < kP2Chunk && c0 + kP2Chunk + lane < s1) ? src_eid[c0 + kP2Chunk + lane] : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        for (int q = 0; q < cnt; q += 2) {  // two edges per pass: 8 independent FMA chains (row q+1 of a ragged tail is stale, unused)
+            const float4* ha = reinterpret_cast<const float4*>(hs[wib][q]);
+            const float4* hb = reinterpret_cast<const float4*>(hs[wib][q + 1 < kP2Chunk ? q + 1 : q]);
+            float a[4] = {yr[JAMUN_EDGE_HID], 0.f, 0.f, 0.f};  // bias channel h' = 1
+            float b[4] = {yr[JAMUN_EDGE_HID], 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k4 = 0; k4 < JAMUN_EDGE_HID / 4; ++k4) {
+                const float4 wa = ha[k4], wb = hb[k4];
+                a[0] = fmaf(wa.x, yr[4 * k4], a[0]);
+                b[0] = fmaf(wb.x, yr[4 * k4], b[0]);
+                a[1] = fmaf(wa.y, yr[4 * k4 + 1], a[1]);
+                b[1] = fmaf(wb.y, yr[4 * k4 + 1], b[1]);
+                a[2] = fmaf(wa.z, yr[4 * k4 + 2], a[2]);
+                b[2] = fmaf(wb.z, yr[4 * k4 + 2], b[2]);
+                a[3] = fmaf(wa.w, yr[4 * k4 + 3], a[3]);
+                b[3] = fmaf(wb.w, yr[4 * k4 + 3], b[3]);
+            }
+            const int ea = __shfl_sync(0xffffffffu, eid_cur, q);
+            const int eb = __shfl_sync(0xffffffffu, eid_cur, (q + 1) & (kP2Chunk - 1));
+            t_edge[(size_t)ea * JAMUN_V + lane] = (a[0] + a[1]) + (a[2] + a[3]);
+            if (q + 1 < cnt) t_edge[(size_t)eb * JAMUN_V + lane] = (b[0] + b[1]) + (b[2] + b[3]);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(256)
-conv_p2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ h,
-               const float* __restrict__ rhat, const float* __restrict__ y, int row0, int nrows, float* __restrict__ p2,
-               int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
+conv_p2_reduce_kernel(const int* __restrict__ rowptr, const float* __restrict__ rhat, const float* __restrict__ t_edge, int N,
+                      float* __restrict__ p2, int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
     const int lane = threadIdx.x & 31;
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= nrows) return;
-    const int i = row0 + r;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= N) return;
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
     const float invd = 1.0f / (float)(e1 > e0 ? e1 - e0 : 1);
     if (lane == 0 && inv_deg) inv_deg[i] = invd;
     float px = 0.f, py = 0.f, pz = 0.f;
+#pragma unroll 4
     for (int e = e0; e < e1; ++e) {
-        const int j = col[e];
         const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
-        const float* he = h + (size_t)e * JAMUN_EDGE_HID;
-        const float h0 = he[lane], h1 = he[32 + lane];
-        const float* yj = y + (size_t)j * YLD + lane;
-        float acc[4] = {yj[JAMUN_EDGE_HID * JAMUN_V], 0.f, 0.f, 0.f};  // bias channel
-#pragma unroll
-        for (int k = 0; k < 32; ++k) acc[k & 3] = fmaf(__shfl_sync(0xffffffffu, h0, k), yj[k * JAMUN_V], acc[k & 3]);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) acc[k & 3] = fmaf(__shfl_sync(0xffffffffu, h1, k), yj[(32 + k) * JAMUN_V], acc[k & 3]);
-        const float tsum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        px = fmaf(rh.x, tsum, px);
-        py = fmaf(rh.y, tsum, py);
-        pz = fmaf(rh.z, tsum, pz);
+        const float t = t_edge[(size_t)e * JAMUN_V + lane];
+        px = fmaf(rh.x, t, px);
+        py = fmaf(rh.y, t, py);
+        pz = fmaf(rh.z, t, pz);
     }
     const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
     float* out = p2 + (size_t)i * p2_ld + lane;
@@ -428,12 +483,15 @@ extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int
     return JAMUN_OK;
 }
 
-extern "C" int jamun_conv_p2(const int* rowptr, const int* col, const float* h, const float* rhat, const float* y, int row0,
-                             int nrows, float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream) {
-    JB_CHECK_ARG(rowptr && col && h && rhat && y && p2, "null argument");
-    if (nrows == 0) return JAMUN_OK;
-    conv_p2_kernel<<<(nrows * 32 + 255) / 256, 256, 0, jb::as_stream(stream)>>>(rowptr, col, h, rhat, y, row0, nrows, p2, p2_ld,
-                                                                                p2_scale, inv_deg);
+extern "C" int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, const float* h, const float* rhat,
+                             const float* y, int N, float* t_edge, float* p2, int p2_ld, float p2_scale, float* inv_deg,
+                             jamun_stream_t stream) {
+    JB_CHECK_ARG(rowptr && src_rowptr && src_eid && h && rhat && y && t_edge && p2, "null argument");
+    if (N == 0) return JAMUN_OK;
+    cudaStream_t s = jb::as_stream(stream);
+    const int blocks = (int)(((size_t)N * 32 + 255) / 256);
+    conv_p2_edge_kernel<<<(N + kP2Warps - 1) / kP2Warps, 32 * kP2Warps, 0, s>>>(src_rowptr, src_eid, h, y, N, t_edge);
+    conv_p2_reduce_kernel<<<blocks, 256, 0, s>>>(rowptr, rhat, t_edge, N, p2, p2_ld, p2_scale, inv_deg);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -176,6 +176,20 @@ __global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restr
     }
 }
 
+// ---- CSR by source: for every node j the ids (positions in the receiver-major edge list) of its out-edges -----------
+__global__ void count_sources_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int N, int* __restrict__ counts) {
+    const int E = rowptr[N];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) atomicAdd(&counts[col[e]], 1);
+}
+__global__ void fill_sources_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int N,
+                                    const int* __restrict__ src_rowptr, int* __restrict__ cursor, int* __restrict__ src_eid) {
+    const int E = rowptr[N];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int j = col[e];
+        src_eid[src_rowptr[j] + atomicAdd(&cursor[j], 1)] = e;
+    }
+}
+
 // ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0rt[k][o] rb[e][k] + b0eff[flag][o]) --------
 // A [E x 32] . [32 x 64] product on the FP32 pipe.  One CTA of 128 threads owns a tile of 128 edges: the tile's radial
 // basis (16 KB, contiguous) and the transposed weight (8 KB) arrive by two bulk async copies; each thread keeps an
@@ -315,6 +329,22 @@ extern "C" int jamun_radius_csr(const float* pos, const int* chain_of, const int
                                                    nullptr, rowptr, col, edst, ebond);
         JB_CHECK_LAUNCH();
     }
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_csr_by_source(const int* rowptr, const int* col, int N, int cap, int* scratch, int* src_rowptr, int* src_eid,
+                                   jamun_stream_t stream) {
+    JB_CHECK_ARG(rowptr && col && scratch && src_rowptr && src_eid, "null argument");
+    cudaStream_t s = jb::as_stream(stream);
+    if (N == 0 || cap == 0) return JAMUN_OK;
+    int blocks = (cap + 255) / 256;
+    if (blocks > jb::kNumSMs * 8) blocks = jb::kNumSMs * 8;
+    cudaMemsetAsync(scratch, 0, (size_t)(N + 1) * sizeof(int), s);
+    count_sources_kernel<<<blocks, 256, 0, s>>>(rowptr, col, N, scratch);
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(scratch, src_rowptr, N);
+    cudaMemsetAsync(scratch, 0, (size_t)(N + 1) * sizeof(int), s);
+    fill_sources_kernel<<<blocks, 256, 0, s>>>(rowptr, col, N, src_rowptr, scratch, src_eid);
+    JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
 

@@ -85,6 +85,8 @@ class Topology:
         # CSR + edge workspaces
         self.rowptr = torch.zeros(N + 1, **i32)
         self.scratch = torch.zeros(N + 1, **i32)
+        self.src_rowptr = torch.zeros(N + 1, **i32)  # out-edge lists (CSR by source) for the source-major path-2 pass
+        self.src_eid = torch.zeros(self.cap, **i32)
         self.col = torch.zeros(self.cap, **i32)
         self.edst = torch.zeros(self.cap, **i32)
         self.ebond = torch.zeros(self.cap, dtype=torch.uint8, device=dev)
@@ -118,6 +120,7 @@ class Topology:
         mnn = -1 if self.max_num_neighbors is None else int(self.max_num_neighbors)
         ops.radius_csr(pos, self.chain_of, self.chain_ptr, r2, mnn, self.bond_rowptr, self.bond_src, self.scratch,
                        self.rowptr, self.col, self.edst, self.ebond)
+        ops.csr_by_source(self.rowptr, self.col, self.scratch, self.src_rowptr, self.src_eid)
 
     def set_csr_from_edge_index(self, edge_index: torch.Tensor, bond_mask: torch.Tensor):
         """Compatibility path for callers that hand E3Conv.forward an explicit edge list."""
@@ -132,6 +135,7 @@ class Topology:
         rp = torch.zeros(self.N + 1, dtype=torch.long, device=self.device)
         rp[1:] = torch.cumsum(torch.bincount(ei[1], minlength=self.N), 0)
         self.rowptr.copy_(rp.to(torch.int32))
+        ops.csr_by_source(self.rowptr, self.col, self.scratch, self.src_rowptr, self.src_eid)
 
     def edge_index(self):
         """Materialise (edge_index [2,E] int64, bond_mask [E] int64) from the CSR -- host sync; tests/API only."""
@@ -215,6 +219,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         topo.xs_op = torch.empty(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
         topo.y = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
         topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
+        topo.t_edge = torch.empty(topo.cap, 32, dtype=torch.float32, device=topo.device)
     # per-node transform of the scalar inputs.  For the initial block the input (atom embedding x noise scale) does not depend
     # on positions, so its transform is computed once per (topology, plan) and kept.
     y_buf = topo.y
@@ -238,14 +243,17 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         # the 0e(x)1e->1e gather needs only Y and h: it runs on the side stream under the builder and the contraction, and
         # its result joins in block_tail (hidden blocks: topo.p2 as the `vadd` operand; initial block: written in place)
         main = torch.cuda.current_stream()
+        side = main if os.environ.get("JAMUN_B200_P2_STREAM", "side") == "main" else topo.side_stream
         topo.ev_fork.record(main)
-        with torch.cuda.stream(topo.side_stream):
-            topo.side_stream.wait_event(topo.ev_fork)
+        with torch.cuda.stream(side):
+            side.wait_event(topo.ev_fork)
             if v_in:
-                ops.conv_p2(topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, 0, N, topo.p2.data_ptr(), 96, b["alpha1"])
+                ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, topo.p2.data_ptr(), 96,
+                            b["alpha1"])
             else:
-                ops.conv_p2(topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, 0, N, out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"])
-            topo.ev_join.record(topo.side_stream)
+                ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge,
+                            out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"])
+            topo.ev_join.record(side)
         topo.p2_pending = True
     for row0 in range(0, N, rp):
         nrows = min(rp, N - row0)

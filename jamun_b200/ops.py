@@ -133,12 +133,21 @@ def conv_build_tc(x, s_in: int, v_in: int, rowptr, col, h, rhat, row0: int, nrow
     _count()
 
 
-def conv_p2(rowptr, col, h, rhat, y, row0: int, nrows: int, p2_ptr: int, p2_ld: int, p2_scale: float, inv_deg=None):
+def conv_p2(rowptr, src_rowptr, src_eid, h, rhat, y, t_edge, p2_ptr: int, p2_ld: int, p2_scale: float, inv_deg=None):
     i32 = torch.int32
-    rc = _lib.lib().jamun_conv_p2(_ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), _ptr(y), row0, nrows, p2_ptr, p2_ld,
-                                  float(p2_scale), _ptr(inv_deg), _stream())
+    N = rowptr.numel() - 1
+    rc = _lib.lib().jamun_conv_p2(_ptr(rowptr, i32), _ptr(src_rowptr, i32), _ptr(src_eid, i32), _ptr(h), _ptr(rhat), _ptr(y), N,
+                                  _ptr(t_edge), p2_ptr, p2_ld, float(p2_scale), _ptr(inv_deg), _stream())
     _lib.check(rc, "jamun_conv_p2")
-    _count()
+    _count(2)
+
+
+def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_csr_by_source(_ptr(rowptr, i32), _ptr(col, i32), rowptr.numel() - 1, col.numel(), _ptr(scratch, i32),
+                                        _ptr(src_rowptr, i32), _ptr(src_eid, i32), _stream())
+    _lib.check(rc, "jamun_csr_by_source")
+    _count(3)
 
 
 def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
