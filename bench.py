@@ -309,13 +309,15 @@ def run_native(args):
     _engine.conv_tc(topo, blk, x_in, topo.conv)
     nrows = min(rp, atoms)
     base = topo.a_ws.data_ptr()
-    build_ms = time_kernel(lambda: ops.conv_build_a(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, topo.y, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, 0, nrows, rp,
-                                                    base, base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg))
-    p2 = topo.p2.data_ptr()
+    _engine.conv_tc_join(topo, blk)
+    build_ms = time_kernel(lambda: ops.conv_build_tc(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, 0, nrows, rp, base,
+                                                     base + 4 * a1_off, comp, topo.inv_deg))
+    p2_ms = time_kernel(lambda: ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, topo.y, topo.t_edge,
+                                            topo.p2.data_ptr(), 96, blk["alpha1"]))
     gemm_ms = time_kernel(lambda: ops.gemm_tf32x3(
         [base] + [base + 4 * (a1_off + c * comp) for c in range(3)], [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3,
         [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216], [1.0] * 4, nrows, rp,
-        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248, addend_ptrs=[None, p2, p2 + 128, p2 + 256], addend_ld=[0, 96, 96, 96]))
+        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
     rows_all = (atoms + 127) // 128 * 128
     ygemm_ms = time_kernel(lambda: ops.gemm_tf32x3([topo.xs_op.data_ptr()], [blk["wy_img"].data_ptr()], [4], [128], [128], [0], [1.0],
                                                    atoms, rows_all, None, topo.y.data_ptr(), _engine.Y_LD, col_blocks=17,
@@ -331,10 +333,12 @@ def run_native(args):
                 "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
                 "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
                 "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
-                "second_kernel": {"kernel": "conv_build_kernel<120,32> (aggregate + path-2 gather, CUDA cores, writes the A operand)",
+                "second_kernel": {"kernel": "conv_build_tc_kernel<120,32> (per-node aggregate F^T.H on tcgen05, 3xTF32; writes the A operand)",
                                   "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
                                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                  "fma_TFLOPs": nrows * deg * 2 * (65 * (152 + 3 * 64) + 65 * 32) / (build_ms * 1e-3) / 1e12},
+                                  "tensor_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 64) / (build_ms * 1e-3) / 1e12},
+                "fourth_kernel": {"kernel": "conv_p2_edge_kernel + conv_p2_reduce_kernel (0e(x)1e->1e, source-major)",
+                                  "ms_per_launch": p2_ms, "fma_TFLOPs": nrows * deg * 2 * 65 * 32 / (p2_ms * 1e-3) / 1e12},
                 "third_kernel": {"kernel": "gemm_tf32x3_kernel, 17 column-block passes, A-stationary (per-node transform Y = x_s.W, N=2080)",
                                  "ms_per_launch": ygemm_ms, "achieved": atoms * 2.0 * 120 * 2080 / (ygemm_ms * 1e-3) / 1e12,
                                  "unit": "TFLOP/s"}}
@@ -346,7 +350,7 @@ def run_native(args):
                 "config": {"workload": f"{args.workload} uncapped peptides, {len(sizes)} chains/GPU ({atoms} atoms/GPU), "
                                        f"{args.inner} BAOAB walk-jump steps per bench step, sigma=0.04, default e3conv denoiser "
                                        f"(random init, output_gain=1)",
-                           "l2": "inputs larger than L2: every denoiser evaluation streams a 3.5 GB conv operand per layer "
+                           "l2": "inputs larger than L2: every denoiser evaluation streams a 1.7 GB conv operand per layer "
                                  "(>> 126 MB L2) and every step advances y, so nothing is served from a warm cache",
                            "parallelism": f"chains sharded x{world}, final NCCL all_gather of samples"},
                 "clocks": clk, "gpu_launches": launches,
