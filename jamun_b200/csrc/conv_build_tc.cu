@@ -109,9 +109,20 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
 
     if (warp > kMmaWarp) {
         // ------------------------------------------------------------------ producers
-        const int g = warp - kMmaWarp - 1;
-        const uint32_t off = (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u + (uint32_t)((g ^ (lane & 7)) << 4);
-        int it = 0;
+        // The (item, K-quad) tasks of consecutive items are dealt round-robin to the 8 warps: an item with 16 in-edges
+        // occupies 4 warps while the other 4 already gather the next item.  tb = index (mod 8) of the item's first task;
+        // this warp owns K-quad kq = (w - tb) mod 8 of the item if kq < ntasks.
+        const int w = warp - kMmaWarp - 1;
+        const uint32_t off_lane = (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u;
+        int it = 0, tb = 0;
+        auto tasks_of = [](int deg) {  // K-quads (incl. zero padding) over all chunks of a node
+            int t = 0;
+            for (int c = 0; c == 0 || 32 * c < deg; ++c) {
+                const int n = min(32, deg - 32 * c);
+                t += 2 * (n > 8 ? (n + 7) >> 3 : 1);
+            }
+            return t;
+        };
         // index prefetch: row extents two rows ahead, this warp's four source indices one row ahead -- the gathers of a
         // row then start without the rowptr -> col -> x chain of dependent L2 round trips
         int e0_n = 0, deg_n = 0, e0_nn = 0, deg_nn = 0;
@@ -120,7 +131,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             e0_n = rowptr[row0 + r_begin];
             deg_n = rowptr[row0 + r_begin + 1] - e0_n;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) jn[q] = 4 * g + q < deg_n ? col[e0_n + 4 * g + q] : 0;
+            for (int q = 0; q < 4; ++q) jn[q] = 4 * w + q < deg_n ? col[e0_n + 4 * w + q] : 0;
         }
         if (r_begin + r_step < r_end) {
             e0_nn = rowptr[row0 + r_begin + r_step];
@@ -133,18 +144,23 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             for (int q = 0; q < 4; ++q) jc[q] = jn[q];
             e0_n = e0_nn, deg_n = deg_nn;
             if (r + r_step < r_end) {
+                const int kn = (w - tb - tasks_of(deg)) & 7;  // this warp's K-quad in the next node's first chunk
 #pragma unroll
-                for (int q = 0; q < 4; ++q) jn[q] = 4 * g + q < deg_n ? col[e0_n + 4 * g + q] : 0;
+                for (int q = 0; q < 4; ++q) jn[q] = 4 * kn + q < deg_n ? col[e0_n + 4 * kn + q] : 0;
             }
             if (r + 2 * r_step < r_end) {
                 e0_nn = rowptr[row0 + r + 2 * r_step];
                 deg_nn = rowptr[row0 + r + 2 * r_step + 1] - e0_nn;
             }
             const int nchunks = deg > 32 ? (deg + 31) >> 5 : 1;
-            if (g == 0 && lane == 0 && inv_deg) inv_deg[row0 + r] = 1.0f / (float)(deg > 0 ? deg : 1);
+            if (w == 0 && lane == 0 && inv_deg) inv_deg[row0 + r] = 1.0f / (float)(deg > 0 ? deg : 1);
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const int n = min(32, deg - 32 * c);
                 const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
+                const int ntasks = 2 * ksteps;
+                const int g = (w - tb) & 7;  // K-quad owned by this warp (none if g >= ntasks)
+                tb = (tb + ntasks) & 7;
+                const uint32_t off = off_lane + (uint32_t)((g ^ (lane & 7)) << 4);
                 if (g == 0) TC_TRACE(it, 0);
                 const int s = it % kSlots;
                 const uint32_t empty_parity = (((uint32_t)it / kSlots) & 1u) ^ 1u;  // waited on just before the stores
@@ -229,7 +245,9 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                         *reinterpret_cast<float4*>(Hlo + o64) = z;
                     }
                 } else {
-                    umma::mbar_wait(&empty[s], empty_parity);  // idle warps stay in step: one arrival per warp per phase
+                    // no task in this item: still observe the slot's phase and arrive -- every warp takes part in every phase,
+                    // which keeps all parity waits within one phase of their barrier
+                    umma::mbar_wait(&empty[s], empty_parity);
                 }
                 umma::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
