@@ -156,6 +156,18 @@ int jamun_block_tail(const float* conv, const float* vadd, const float* x_in, in
                      const float* skip_w, const float* s_next, float c_act, float c_gate, int N,
                      float* x_new, float* x_scaled, jamun_stream_t stream);
 
+/* The same block tail as three launches with the two Linears on the tensor cores:
+ * jamun_tail_pack  Gate(conv (+vadd)) and x_in -> stage-major operands for jamun_gemm_tf32x3:
+ *                  a_s: [4 + ceil(s_in/32)][rows_pad][32] (activated scalars | input scalars, zero padded per 32),
+ *                  a_v: 3 components x [1 + (v_in>0)][rows_pad][32] (gated vectors | input vectors), stride a_v_comp_stride;
+ * jamun_gemm_tf32x3 with B = [W_self ; W_skip] images (K zero-padded per 32) -> y [N, 216];
+ * jamun_tail_mix   x_new = skip_w ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next. */
+int jamun_tail_pack(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, float c_act,
+                    float c_gate, int N, int rows_pad, float* a_s, float* a_v, long long a_v_comp_stride,
+                    jamun_stream_t stream);
+int jamun_tail_mix(const float* y, const float* x_res, const float* skip_w, const float* s_next, int N, float* x_new,
+                   float* x_scaled, jamun_stream_t stream);
+
 /* Output head (e3tools/nn/_mlp.py:37-114, arch/e3conv.py:134-135): Linear -> Gate -> Linear(1x1e) * gain.
  * w1_s: [120,152] w1_v:[32,32] pre-scaled; w2: [32] pre-scaled by gain/sqrt(32).  g: [N,3]. */
 int jamun_head(const float* x, const float* w1_s, const float* w1_v, const float* w2, float c_gate, int N,

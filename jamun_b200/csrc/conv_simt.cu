@@ -304,6 +304,65 @@ block_tail_kernel(const float* __restrict__ conv, const float* __restrict__ vadd
     }
 }
 
+// ---- block tail on the tensor cores: Gate -> operand packer, [gate | x_in] . [W_self ; W_skip] by jamun_gemm_tf32x3, mix ----
+// tail_pack: per node, the activated scalars (120 -> 4 stages of 32, zero padded), the block input scalars (NS stages), and per
+// component the gated vectors (1 stage) and the block input vectors (1 stage) in the GEMM's stage-major chunk-swizzled layout.
+template <int S_IN, int V_IN>
+__global__ void __launch_bounds__(256)
+tail_pack_kernel(const float* __restrict__ conv, const float* __restrict__ vadd, const float* __restrict__ x_in, float c_act,
+                 float c_gate, int N, int rows_pad, float* __restrict__ a_s, float* __restrict__ a_v, size_t comp_stride) {
+    constexpr int D_IN = S_IN + 3 * V_IN, S = JAMUN_S, V = JAMUN_V, NS = (S_IN + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= N) return;
+    const int swz = (((lane >> 2) ^ (i & 7)) << 2) | (lane & 3);
+    const float* o = conv + (size_t)i * JAMUN_GATE_IN;
+    const float* xi = x_in + (size_t)i * D_IN;
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const int t = 32 * st + lane;
+        float v = 0.f;
+        if (t < S) {
+            v = o[t];
+            v = c_act * (v > 0.f ? v : 0.01f * v);
+        }
+        a_s[((size_t)st * rows_pad + i) * 32 + swz] = v;
+    }
+#pragma unroll
+    for (int st = 0; st < NS; ++st) {
+        const int t = 32 * st + lane;
+        a_s[((size_t)(4 + st) * rows_pad + i) * 32 + swz] = t < S_IN ? xi[t] : 0.f;
+    }
+    const float gate = c_gate * sigmoidf_acc(o[S + lane]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = o[SO + c * V + lane];
+        if (vadd) v += vadd[(size_t)i * (3 * V) + c * V + lane];
+        float* av = a_v + c * comp_stride;
+        av[(size_t)i * 32 + swz] = v * gate;
+        if (V_IN > 0) av[((size_t)rows_pad + i) * 32 + swz] = xi[S_IN + c * V_IN + lane];
+    }
+}
+
+// tail_mix: noise-conditional skip (x_new = x_res*w + y*(1-w)) and the next block's input scaling
+__global__ void __launch_bounds__(256)
+tail_mix_kernel(const float* __restrict__ y, const float* __restrict__ x_res, const float* __restrict__ skip_w,
+                const float* __restrict__ s_next, int N, float* __restrict__ x_new, float* __restrict__ x_scaled) {
+    constexpr int S = JAMUN_S, V = JAMUN_V, HID = JAMUN_HID;
+    const size_t total = (size_t)N * HID;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % HID);
+        const int cw = w < S ? w : S + (w - S) % V;  // per-irrep weight index
+        float v = y[idx];
+        if (skip_w) {
+            const float sw = skip_w[cw];
+            v = x_res[idx] * sw + v * (1.0f - sw);
+        }
+        x_new[idx] = v;
+        if (x_scaled) x_scaled[idx] = s_next ? v * s_next[cw] : v;
+    }
+}
+
 // ---- head: Linear(hidden -> 152x0e+32x1e) -> Gate -> Linear(-> 1x1e) * gain.  Only the 32 gate scalars and the
 // gated vectors reach the output, so the 120 activated scalars are never formed.
 __global__ void __launch_bounds__(WARPS * 32)
@@ -410,6 +469,40 @@ extern "C" int jamun_block_tail(const float* conv, const float* vadd, const floa
         jb::set_error("jamun_block_tail: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;
     }
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_tail_pack(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, float c_act,
+                               float c_gate, int N, int rows_pad, float* a_s, float* a_v, long long a_v_comp_stride,
+                               jamun_stream_t stream) {
+    JB_CHECK_ARG(conv && x_in && a_s && a_v && N <= rows_pad, "bad argument");
+    if (N == 0) return JAMUN_OK;
+    const int blocks = (int)(((size_t)N * 32 + 255) / 256);
+    cudaStream_t s = jb::as_stream(stream);
+    if (s_in == JAMUN_S && v_in == JAMUN_V) {
+        tail_pack_kernel<JAMUN_S, JAMUN_V><<<blocks, 256, 0, s>>>(conv, vadd, x_in, c_act, c_gate, N, rows_pad, a_s, a_v,
+                                                                  (size_t)a_v_comp_stride);
+    } else if (s_in == JAMUN_S0 && v_in == 0) {
+        tail_pack_kernel<JAMUN_S0, 0><<<blocks, 256, 0, s>>>(conv, vadd, x_in, c_act, c_gate, N, rows_pad, a_s, a_v,
+                                                             (size_t)a_v_comp_stride);
+    } else {
+        jb::set_error("jamun_tail_pack: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
+        return JAMUN_EINVAL;
+    }
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_tail_mix(const float* y, const float* x_res, const float* skip_w, const float* s_next, int N, float* x_new,
+                              float* x_scaled, jamun_stream_t stream) {
+    JB_CHECK_ARG(y && x_new, "null argument");
+    JB_CHECK_ARG(!skip_w || x_res, "skip_w needs x_res");
+    if (N == 0) return JAMUN_OK;
+    size_t total = (size_t)N * JAMUN_HID;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > jb::kNumSMs * 16) blocks = jb::kNumSMs * 16;
+    tail_mix_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(y, x_res, skip_w, s_next, N, x_new, x_scaled);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -183,6 +183,14 @@ class E3ConvPlan:
                 wy_pad = torch.zeros(wy.shape[0], Y_LD, dtype=wy.dtype, device=wy.device)
                 wy_pad[:, :wy.shape[1]] = wy
                 blk["wy_img"] = packing.pack_b_column_blocks(wy_pad, 128)
+                # block tail as one GEMM: [activated scalars (128) | input scalars (32 NS)] . [W_self ; W_skip], same for vectors
+                ns_in = (blk["s_in"] + 31) // 32
+                ws = torch.zeros(128 + 32 * ns_in, 120, dtype=torch.float32, device=dev)
+                ws[:120] = blk["wself_s"]
+                ws[128:128 + blk["s_in"]] = blk["wskip_s"]
+                blk["tail_bs_img"] = packing.pack_b_images(ws, 128)
+                wv = blk["wself_v"] if blk["wskip_v"] is None else torch.cat([blk["wself_v"], blk["wskip_v"]], dim=0)
+                blk["tail_bv_img"] = packing.pack_b_images(wv.contiguous(), 32)
                 self.blocks.append(blk)
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
@@ -289,6 +297,33 @@ def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:
     return topo.p2 if b["v_in"] else None
 
 
+TAIL_IMPL = os.environ.get("JAMUN_B200_TAIL", "tc")  # "tc": pack -> tcgen05 GEMM -> mix;  "simt": one exact-fp32 kernel
+
+
+def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_scaled, vadd) -> None:
+    """Gate + self-interaction + skip Linear + noise-conditional skip/scale (ConvBlock.forward after the conv)."""
+    if os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) != "tc" or topo.a_ws is None:
+        ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"], b["wskip_v"], skip_w,
+                       s_next, b["c_act"], b["c_gate"], x_new, x_scaled, vadd=vadd)
+        return
+    N = topo.N
+    rows_all = (N + 127) // 128 * 128
+    ns_in = (b["s_in"] + 31) // 32
+    st_s, st_v = 4 + ns_in, 2 if b["v_in"] else 1
+    need = (st_s + 3 * st_v) * rows_all * 32
+    assert need <= topo.a_ws.numel(), "operand workspace too small for the block tail"
+    if getattr(topo, "ytail", None) is None:
+        topo.ytail = torch.empty(N, ops.HID, dtype=torch.float32, device=topo.device)
+    base = topo.a_ws.data_ptr()  # the conv operand is dead once the contraction has run
+    a_v = base + 4 * st_s * rows_all * 32
+    comp = st_v * rows_all * 32
+    ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
+    ops.gemm_tf32x3([base] + [a_v + 4 * c * comp for c in range(3)], [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3,
+                    [st_s, st_v, st_v, st_v], [128, 32, 32, 32], [120, 32, 32, 32], [0, 120, 152, 184], [1.0] * 4, N, rows_all, None,
+                    topo.ytail.data_ptr(), ops.HID)
+    ops.tail_mix(topo.ytail, x_res, skip_w, s_next, x_new, x_scaled)
+
+
 def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,
                    mu: Optional[torch.Tensor] = None, step: Optional[float] = None) -> torch.Tensor:
     """One evaluation of the network on scaled positions p over topo's current CSR -> g_out [N,3]."""
@@ -316,8 +351,7 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None
         s_next = plan.scales[l] if l < nb - 1 else None
-        ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"],
-                       b["wskip_v"], skip_w, s_next, b["c_act"], b["c_gate"], x_new, x_scaled if l < nb - 1 else None, vadd=vadd)
+        block_tail(topo, b, x_in, x_res, skip_w, s_next, x_new, x_scaled if l < nb - 1 else None, vadd)
         x_in, x_res = x_scaled, x_new
     ops.head(x_res, plan.head_w1s, plan.head_w1v, plan.head_w2, plan.head_cgate, g_out)
     return g_out

@@ -180,6 +180,21 @@ def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_
     _count()
 
 
+def tail_pack(conv, vadd, x_in, s_in: int, v_in: int, c_act: float, c_gate: float, rows_pad: int, a_s_ptr: int, a_v_ptr: int,
+              a_v_comp_stride: int):
+    rc = _lib.lib().jamun_tail_pack(_ptr(conv), _ptr(vadd), _ptr(x_in), s_in, v_in, float(c_act), float(c_gate), conv.shape[0],
+                                    rows_pad, a_s_ptr, a_v_ptr, int(a_v_comp_stride), _stream())
+    _lib.check(rc, "jamun_tail_pack")
+    _count()
+
+
+def tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled):
+    rc = _lib.lib().jamun_tail_mix(_ptr(y), _ptr(x_res), _ptr(skip_w), _ptr(s_next), y.shape[0], _ptr(x_new), _ptr(x_scaled),
+                                   _stream())
+    _lib.check(rc, "jamun_tail_mix")
+    _count()
+
+
 def head(x, w1_s, w1_v, w2, c_gate: float, g):
     rc = _lib.lib().jamun_head(_ptr(x), _ptr(w1_s), _ptr(w1_v), _ptr(w2), float(c_gate), x.shape[0], _ptr(g), _stream())
     _lib.check(rc, "jamun_head")

@@ -183,3 +183,38 @@ def test_build_tc_matches_ffma_builder(models, sizes, monkeypatch):
         assert err <= 2e-6 * max(1.0, scale), f"block {l}: A operand err {err} scale {scale}"
         err_o = (out_tc - out_ref).abs().max().item()
         assert err_o <= 2e-5 * max(1.0, out_ref.abs().max().item()), f"block {l}: conv err {err_o}"
+
+
+def test_block_tail_tc_matches_simt(models, monkeypatch):
+    """Block tail as pack -> tcgen05 GEMM -> mix == the exact-fp32 kernel, initial and hidden block, with and without skip/scale."""
+    from jamun_b200 import data, engine, ops, synthetic
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors([22, 15, 9, 30, 40])
+    topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+    ctx = prod.sigma_context(0.04)
+    plan = prod.arch_module.plan(ctx.c_noise, "cuda")
+    N = topo.N
+    gen = torch.Generator().manual_seed(5)
+    topo.a_ws = torch.empty(65 * 11 * topo.chunk_rows * 32, device="cuda")
+    for l, d_in in ((0, 56), (1, 216), (5, 216)):
+        b = plan.blocks[l]
+        topo.conv.copy_(torch.randn(N, 248, generator=gen))
+        x_in = torch.randn(N, d_in, generator=gen).cuda()
+        x_res = torch.randn(N, 216, generator=gen).cuda() if l > 0 else None
+        vadd = torch.randn(N, 96, generator=gen).cuda() if l > 0 else None
+        skip_w = plan.skips[l - 1] if l > 0 else None
+        s_next = plan.scales[l] if l < len(plan.blocks) - 1 else None
+        outs = {}
+        for impl in ("simt", "tc"):
+            monkeypatch.setenv("JAMUN_B200_TAIL", impl)
+            x_new = torch.full((N, 216), float("nan"), device="cuda")
+            x_sc = torch.full((N, 216), float("nan"), device="cuda") if s_next is not None else None
+            engine.block_tail(topo, b, x_in, x_res, skip_w, s_next, x_new, x_sc, vadd)
+            torch.cuda.synchronize()
+            outs[impl] = (x_new, x_sc)
+        for a, c in zip(outs["simt"], outs["tc"]):
+            if a is None:
+                continue
+            assert not torch.isnan(c).any()
+            assert (a - c).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
