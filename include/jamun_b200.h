@@ -161,12 +161,14 @@ int jamun_block_tail(const float* conv, const float* vadd, const float* x_in, in
  *                  a_s: [4 + ceil(s_in/32)][rows_pad][32] (activated scalars | input scalars, zero padded per 32),
  *                  a_v: 3 components x [1 + (v_in>0)][rows_pad][32] (gated vectors | input vectors), stride a_v_comp_stride;
  * jamun_gemm_tf32x3 with B = [W_self ; W_skip] images (K zero-padded per 32) -> y [N, 216];
- * jamun_tail_mix   x_new = skip_w ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next. */
+ * jamun_tail_mix   x_new = skip_w ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next;  xs_op (or NULL): the 120 scalars of
+ *                  x_scaled as the [4][rows_pad][32] operand of the next block's per-node transform (= jamun_pack_rows;
+ *                  positions 120..127 of the last stage are not written: keep them zero). */
 int jamun_tail_pack(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, float c_act,
                     float c_gate, int N, int rows_pad, float* a_s, float* a_v, long long a_v_comp_stride,
                     jamun_stream_t stream);
 int jamun_tail_mix(const float* y, const float* x_res, const float* skip_w, const float* s_next, int N, float* x_new,
-                   float* x_scaled, jamun_stream_t stream);
+                   float* x_scaled, float* xs_op, int rows_pad, jamun_stream_t stream);
 
 /* Output head (e3tools/nn/_mlp.py:37-114, arch/e3conv.py:134-135): Linear -> Gate -> Linear(1x1e) * gain.
  * w1_s: [120,152] w1_v:[32,32] pre-scaled; w2: [32] pre-scaled by gain/sqrt(32).  g: [N,3]. */

@@ -347,7 +347,8 @@ tail_pack_kernel(const float* __restrict__ conv, const float* __restrict__ vadd,
 // tail_mix: noise-conditional skip (x_new = x_res*w + y*(1-w)) and the next block's input scaling
 __global__ void __launch_bounds__(256)
 tail_mix_kernel(const float* __restrict__ y, const float* __restrict__ x_res, const float* __restrict__ skip_w,
-                const float* __restrict__ s_next, int N, float* __restrict__ x_new, float* __restrict__ x_scaled) {
+                const float* __restrict__ s_next, int N, float* __restrict__ x_new, float* __restrict__ x_scaled,
+                float* __restrict__ xs_op, int rows_pad) {
     constexpr int S = JAMUN_S, V = JAMUN_V, HID = JAMUN_HID;
     const size_t total = (size_t)N * HID;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -359,7 +360,14 @@ tail_mix_kernel(const float* __restrict__ y, const float* __restrict__ x_res, co
             v = x_res[idx] * sw + v * (1.0f - sw);
         }
         x_new[idx] = v;
-        if (x_scaled) x_scaled[idx] = s_next ? v * s_next[cw] : v;
+        if (x_scaled) {
+            const float vs = s_next ? v * s_next[cw] : v;
+            x_scaled[idx] = vs;
+            if (xs_op && w < S) {  // scalars of the next block's input, already in the GEMM's stage-major operand layout
+                const int i = (int)(idx / HID), p = w & 31;
+                xs_op[((size_t)(w >> 5) * rows_pad + i) * 32 + ((((p >> 2) ^ (i & 7)) << 2) | (p & 3))] = vs;
+            }
+        }
     }
 }
 
@@ -495,14 +503,14 @@ extern "C" int jamun_tail_pack(const float* conv, const float* vadd, const float
 }
 
 extern "C" int jamun_tail_mix(const float* y, const float* x_res, const float* skip_w, const float* s_next, int N, float* x_new,
-                              float* x_scaled, jamun_stream_t stream) {
+                              float* x_scaled, float* xs_op, int rows_pad, jamun_stream_t stream) {
     JB_CHECK_ARG(y && x_new, "null argument");
     JB_CHECK_ARG(!skip_w || x_res, "skip_w needs x_res");
     if (N == 0) return JAMUN_OK;
     size_t total = (size_t)N * JAMUN_HID;
     int blocks = (int)((total + 255) / 256);
     if (blocks > jb::kNumSMs * 16) blocks = jb::kNumSMs * 16;
-    tail_mix_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(y, x_res, skip_w, s_next, N, x_new, x_scaled);
+    tail_mix_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(y, x_res, skip_w, s_next, N, x_new, x_scaled, xs_op, rows_pad);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

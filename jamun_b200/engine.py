@@ -111,6 +111,7 @@ class Topology:
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.p2_pending = False
+        self.xs_op_of = None  # the tensor whose scalars currently sit packed in xs_op (written by tail_mix)
         self.y0 = None
         self.y0_key = None
 
@@ -224,7 +225,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
     rows_all = (N + 127) // 128 * 128
     if topo.a_ws is None:
         topo.a_ws = torch.empty(65 * (5 + 3 * 2) * rp * 32, dtype=torch.float32, device=topo.device)
-        topo.xs_op = torch.empty(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
+        topo.xs_op = torch.zeros(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
         topo.y = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
         topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
         topo.t_edge = torch.empty(topo.cap, 32, dtype=torch.float32, device=topo.device)
@@ -240,7 +241,9 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
             topo.y0_key = y_const_key
         y_buf = topo.y0
     else:
-        ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
+        if topo.xs_op_of is not x:  # else the previous block's tail_mix has already written the packed scalars of x
+            ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
+        topo.xs_op_of = None
         ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0], N, rows_all, None,
                         topo.y.data_ptr(), Y_LD, col_blocks=17, b_block_floats=ns * 2 * 128 * 32)
     base = topo.a_ws.data_ptr()
@@ -321,7 +324,9 @@ def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_sc
     ops.gemm_tf32x3([base] + [a_v + 4 * c * comp for c in range(3)], [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3,
                     [st_s, st_v, st_v, st_v], [128, 32, 32, 32], [120, 32, 32, 32], [0, 120, 152, 184], [1.0] * 4, N, rows_all, None,
                     topo.ytail.data_ptr(), ops.HID)
-    ops.tail_mix(topo.ytail, x_res, skip_w, s_next, x_new, x_scaled)
+    pack = x_scaled is not None and getattr(topo, "xs_op", None) is not None
+    ops.tail_mix(topo.ytail, x_res, skip_w, s_next, x_new, x_scaled, topo.xs_op if pack else None, rows_all)
+    topo.xs_op_of = x_scaled if pack else None
 
 
 def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: float, g_out: torch.Tensor,

@@ -188,9 +188,9 @@ def tail_pack(conv, vadd, x_in, s_in: int, v_in: int, c_act: float, c_gate: floa
     _count()
 
 
-def tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled):
+def tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled, xs_op=None, rows_pad: int = 0):
     rc = _lib.lib().jamun_tail_mix(_ptr(y), _ptr(x_res), _ptr(skip_w), _ptr(s_next), y.shape[0], _ptr(x_new), _ptr(x_scaled),
-                                   _stream())
+                                   _ptr(xs_op), rows_pad, _stream())
     _lib.check(rc, "jamun_tail_mix")
     _count()
 
