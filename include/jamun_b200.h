@@ -87,6 +87,11 @@ int jamun_edge_geom(const float* p, const int* rowptr, const int* col, const int
  * b0eff: [2, 64] = bias + W0[:, :32] . embed_bondedness[flag].  h: [cap, 64]. */
 int jamun_edge_radial_hidden(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
                              const float* w0r, const float* b0eff, float* h, jamun_stream_t stream);
+/* All layers in one pass over the edges (the radial basis is read once): w0r_all [layers, 32, 64], b0eff_all
+ * [layers, 2, 64], h_all [layers, cap, 64]. */
+int jamun_edge_radial_hidden_all(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                                 const float* w0r_all, const float* b0eff_all, int layers, float* h_all,
+                                 jamun_stream_t stream);
 
 /* Conv.forward (e3tools/nn/_conv.py:96-119): gather, per-edge-weighted FullyConnectedTensorProduct,
  * scatter-mean -- evaluated in the aggregate-then-transform form: per receiver

@@ -202,31 +202,43 @@ __global__ void __launch_bounds__(128, 4) edge_radial_hidden_kernel(const float*
                                                                     const int* __restrict__ rowptr, int N,
                                                                     const float* __restrict__ w0rt,
                                                                     const float* __restrict__ b0eff,
-                                                                    float* __restrict__ h) {
+                                                                    float* __restrict__ h, int L, size_t h_stride) {
+    // L layers share the edge tile: layer l uses w0rt + l*2048, b0eff + l*128 and writes h + l*h_stride; the weight images
+    // are double-buffered (layer l+2 streams in while layer l+1 computes)
+    constexpr uint32_t kWBytes = JAMUN_NBASIS * JAMUN_EDGE_HID * 4u;
     __shared__ __align__(128) float s_rb[kRhTile * JAMUN_NBASIS];
-    __shared__ __align__(128) float s_w[JAMUN_NBASIS * JAMUN_EDGE_HID];
-    __shared__ float s_b[2 * JAMUN_EDGE_HID];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(128) float s_w2[2][JAMUN_NBASIS * JAMUN_EDGE_HID];
+    __shared__ float s_b2[2][2 * JAMUN_EDGE_HID];
+    __shared__ __align__(8) uint64_t bar[2];
     const int E = rowptr[N];
     const int e0 = blockIdx.x * kRhTile;
     if (e0 >= E) return;
     const int nvalid = min(kRhTile, E - e0);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        umma::mbar_init(&bar, 1);
+        umma::mbar_init(&bar[0], 1);
+        umma::mbar_init(&bar[1], 1);
         umma::fence_barrier_init();
     }
-    s_b[tid] = b0eff[tid];
     __syncthreads();
     if (tid == 0) {
-        const uint32_t rb_bytes = (uint32_t)nvalid * JAMUN_NBASIS * 4u, w_bytes = JAMUN_NBASIS * JAMUN_EDGE_HID * 4u;
-        umma::mbar_arrive_expect_tx(&bar, rb_bytes + w_bytes);
-        umma::bulk_g2s(s_rb, rb + (size_t)e0 * JAMUN_NBASIS, rb_bytes, &bar);
-        umma::bulk_g2s(s_w, w0rt, w_bytes, &bar);
+        const uint32_t rb_bytes = (uint32_t)nvalid * JAMUN_NBASIS * 4u;
+        umma::mbar_arrive_expect_tx(&bar[0], rb_bytes + kWBytes);
+        umma::bulk_g2s(s_rb, rb + (size_t)e0 * JAMUN_NBASIS, rb_bytes, &bar[0]);
+        umma::bulk_g2s(s_w2[0], w0rt, kWBytes, &bar[0]);
+        if (L > 1) {
+            umma::mbar_arrive_expect_tx(&bar[1], kWBytes);
+            umma::bulk_g2s(s_w2[1], w0rt + JAMUN_NBASIS * JAMUN_EDGE_HID, kWBytes, &bar[1]);
+        }
     }
-    umma::mbar_wait(&bar, 0);
-
     const int og = tid & 7, eg = tid >> 3;  // channels {4 og .. +3} and {32 + 4 og .. +3};  edges 8 eg .. 8 eg + 7
+    for (int l = 0; l < L; ++l) {
+    const float* s_w = s_w2[l & 1];
+    float* s_b = s_b2[l & 1];
+    s_b[tid] = b0eff[(size_t)l * 2 * JAMUN_EDGE_HID + tid];
+    umma::mbar_wait(&bar[l & 1], (uint32_t)(l >> 1) & 1u);
+    __syncthreads();
+    float* hl = h + (size_t)l * h_stride;
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -268,11 +280,17 @@ __global__ void __launch_bounds__(128, 4) edge_radial_hidden_kernel(const float*
             hi.y = jb::siluf_acc(acc[i][5] + bias[33]);
             hi.z = jb::siluf_acc(acc[i][6] + bias[34]);
             hi.w = jb::siluf_acc(acc[i][7] + bias[35]);
-            float4* dst = reinterpret_cast<float4*>(h + (size_t)e * JAMUN_EDGE_HID) + og;
+            float4* dst = reinterpret_cast<float4*>(hl + (size_t)e * JAMUN_EDGE_HID) + og;
             dst[0] = lo;
             dst[8] = hi;
         }
     }
+    __syncthreads();  // this layer's weight image and bias rows are free
+    if (tid == 0 && l + 2 < L) {
+        umma::mbar_arrive_expect_tx(&bar[l & 1], kWBytes);
+        umma::bulk_g2s(s_w2[l & 1], w0rt + (size_t)(l + 2) * JAMUN_NBASIS * JAMUN_EDGE_HID, kWBytes, &bar[l & 1]);
+    }
+    }  // layers
 }
 
 // ---- layout conversion ---------------------------------------------------------------------------------
@@ -367,7 +385,19 @@ extern "C" int jamun_edge_radial_hidden(const float* rb, const unsigned char* eb
     if (N == 0 || cap == 0) return JAMUN_OK;
     // one CTA per 128-edge tile of the capacity; the live edge count is device-side (rowptr[N]), surplus CTAs exit
     int blocks = (cap + kRhTile - 1) / kRhTile;
-    edge_radial_hidden_kernel<<<blocks, 128, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h);
+    edge_radial_hidden_kernel<<<blocks, 128, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, h, 1, 0);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_edge_radial_hidden_all(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                                            const float* w0r_all, const float* b0eff_all, int layers, float* h_all,
+                                            jamun_stream_t stream) {
+    JB_CHECK_ARG(rb && ebond && rowptr && w0r_all && b0eff_all && h_all && layers >= 1, "bad argument");
+    if (N == 0 || cap == 0) return JAMUN_OK;
+    int blocks = (cap + kRhTile - 1) / kRhTile;
+    edge_radial_hidden_kernel<<<blocks, 128, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r_all, b0eff_all, h_all, layers,
+                                                                         (size_t)cap * JAMUN_EDGE_HID);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -193,6 +193,8 @@ class E3ConvPlan:
                 wv = blk["wself_v"] if blk["wskip_v"] is None else torch.cat([blk["wself_v"], blk["wskip_v"]], dim=0)
                 blk["tail_bv_img"] = packing.pack_b_images(wv.contiguous(), 32)
                 self.blocks.append(blk)
+            self.w0r_all = torch.stack([b["w0r"] for b in self.blocks]).contiguous()      # [L, 32, 64]
+            self.b0eff_all = torch.stack([b["b0eff"] for b in self.blocks]).contiguous()  # [L, 2, 64]
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
             self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
@@ -344,9 +346,13 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
         topo.x0_key = key
     x_in, x_res = topo.x0, None
     nb = len(plan.blocks)
+    # radial hidden of every layer in one pass over the edges (h_all: [L, cap, 64])
+    if getattr(topo, "h_all", None) is None or topo.h_all.shape[0] != nb:
+        topo.h_all = torch.zeros(nb, topo.cap, ops.EDGE_HID, dtype=torch.float32, device=topo.device)
+    ops.edge_radial_hidden_all(topo.rb, topo.ebond, topo.rowptr, plan.w0r_all, plan.b0eff_all, topo.h_all)
     for l, b in enumerate(plan.blocks):
         vadd = None
-        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        topo.h = topo.h_all[l]
         if CONV_IMPL == "simt":
             ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
                          b["alpha0"], b["alpha1"], topo.conv)

@@ -103,6 +103,15 @@ def edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h):
     _count()
 
 
+def edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all):
+    N, cap, layers = rowptr.numel() - 1, ebond.numel(), w0r_all.shape[0]
+    assert h_all.shape[0] == layers and h_all.shape[1] == cap
+    rc = _lib.lib().jamun_edge_radial_hidden_all(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap,
+                                                 _ptr(w0r_all), _ptr(b0eff_all), layers, _ptr(h_all), _stream())
+    _lib.check(rc, "jamun_edge_radial_hidden_all")
+    _count()
+
+
 def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: float, alpha1: float, out):
     N = x.shape[0]
     assert x.shape[1] == s_in + 3 * v_in and out.shape == (N, GATE_IN)

@@ -75,7 +75,7 @@ def test_gemm_hi_lo_exactness():
     assert torch.equal(out, A @ B)
 
 
-@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31]])
+@pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31], [260, 2, 131]])
 def test_conv_tc_matches_simt_and_fp64(models, sizes):
     """Two-launch tensor-core conv == exact-fp32 SIMT conv (same operands) to ~1e-6, for the initial and a hidden block."""
     import kernel_model as KM
