@@ -248,11 +248,20 @@ class Denoiser(_Base):
                 y = mean_center(y)
             if align_noisy_input:
                 y = align_A_to_B_batched(y, x)
-        xhat = self.xhat(y, sigma)
+        xhat = self.xhat_with_grad(y, sigma) if (torch.is_grad_enabled() and self.training) else self.xhat(y, sigma)
         return xhat, y
 
+    def xhat_with_grad(self, y, sigma: Union[float, torch.Tensor]):
+        """xhat with an autograd graph to the parameters (training; library path -- see jamun_b200/train.py)."""
+        from .. import train
+
+        topo = self.topology_for(y)
+        out = y.clone("pos")
+        out.pos = train.xhat_positions(self, y.pos, topo, sigma)
+        return out
+
     def compute_loss(self, x, xhat, sigma):
-        """Loss values (forward only in this round: xhat carries no autograd graph)."""
+        """Per-graph loss (differentiable w.r.t. xhat.pos; denoiser.py:251-287)."""
         from ..utils import mean_center
 
         if self.mean_center:
@@ -274,9 +283,15 @@ class Denoiser(_Base):
         return self.compute_loss(x, xhat, sigma)
 
     def training_step(self, batch, batch_idx: int):
-        raise NotImplementedError(
-            "jamun_b200 round 1 ships the forward (sampling) kernels; the backward kernels of the conv/linear "
-            "stack (SURVEY 8 row a16) are not built yet, so training_step cannot produce gradients.")
+        """denoiser.py:299-319.  Gradients come from torch autograd over jamun_b200/train.py (the backward kernels of the conv
+        stack are not written yet); the forward of validation/sampling stays on the CUDA kernels."""
+        sigma = self.sigma_distribution.sample().to(self.device)
+        loss, aux = self.noise_and_compute_loss(batch, sigma, align_noisy_input=self.align_noisy_input_during_training)
+        aux["loss"] = loss
+        for key in aux:
+            aux[key] = aux[key].mean()
+            self.log(f"train/{key}", aux[key], prog_bar=False, batch_size=batch.num_graphs, sync_dist=False)
+        return {"sigma": sigma, **aux}
 
     def validation_step(self, batch, batch_idx: int):
         sigma = self.sigma_distribution.sample().to(self.device)
