@@ -109,8 +109,7 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  *     The path 0e(x)1e->1e is gathered from y[N, 2176] = x_s . W (pre-transformed source rows, 65*32 used columns) into p2[N, p2_ld]:
  *     p2[i, c*32+w] = sum_e rhat_e[c] sum_k' h'_e[k'] y[src_e, k'*32+w], multiplied by p2_scale/deg when p2_scale != 0.
  *     max_degree: an upper bound of the in-degree of every node (<= 64 selects the shared-memory-cached fast kernel).
- *     chain_of/chain_ptr/src_max (optional): src_max = the largest number of nodes in the chains spanned by any aligned
- *     block of 8 consecutive nodes; when it fits, the block-staged kernel (sources of x / Y in shared memory) is used.
+ *     This is the FP32-pipe builder (exact fp32 aggregate); jamun_conv_build_tc + jamun_conv_p2 below is the default.
  * (2) jamun_gemm_tf32x3: out[r, out_col[s] + n] = row_scale[r] * alpha[s] * sum_K A_s[r,K] B_s[K,n] for up to 4 segments,
  *     tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy), accumulators in TMEM.  b[s] is the weight operand
  *     pre-packed per stage as (hi | lo) images in the UMMA K-major SWIZZLE_128B shared-memory layout
@@ -121,8 +120,7 @@ int jamun_conv_fwd(const float* x, int s_in, int v_in, const int* rowptr, const 
  * (3) jamun_pack_rows: copies columns [col0, col0+ncols) of a row-major matrix into the GEMM's stage-major, chunk-swizzled
  *     A layout ([ceil(ncols/32)][rows_pad][32], zero padded). */
 int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                       const float* rhat, const float* y, const int* chain_of, const int* chain_ptr, int src_max,
-                       int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride,
+                       const float* rhat, const float* y, int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride,
                        float* p2, int p2_ld, float p2_scale, float* inv_deg, jamun_stream_t stream);
 /* Tensor-core form of jamun_conv_build_a's aggregate (same a0 / a1 operands, 3xTF32 products accumulated in
  * tensor memory: elements agree with the FP32 builder to ~1e-6 relative).  Per receiver node the aggregate is the

@@ -33,7 +33,7 @@ _PROTOS = {
     "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden_all": ([c_f, c_f, c_f, I, I, c_f, c_f, I, c_f, c_f], I),
     "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
-    "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
+    "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
     "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
     "jamun_conv_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, c_f, I, F, c_f, c_f], I),
     "jamun_csr_by_source": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),

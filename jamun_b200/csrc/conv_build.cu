@@ -29,9 +29,8 @@ constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr int YLD = 17 * 128;  // row stride of Y: (64+1)*32 = 2080 columns padded to 17 column blocks of 128
 constexpr int MAXD = 64;  // in-edges per node whose per-edge invariants are cached in shared memory
 
-// ROLE 0: scalar operand slots + path-2 gather;  ROLE 1: vector operand slots;  ROLE 2: both (one warp does everything)
-template <int S_IN, int V_IN, int RK, int MINB, bool CACHED, int ROLE, int BT = 256, int EUNROLL = 0>
-__global__ void __launch_bounds__(BT, MINB)
+template <int S_IN, int V_IN, int RK, int MINB, bool CACHED>
+__global__ void __launch_bounds__(256, MINB)
 conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int row0,
                   int nrows, int rows_pad, float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride,
@@ -42,7 +41,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     constexpr int NS = (S_IN + 31) / 32;
     constexpr int NSL0 = NS + (V_IN > 0 ? 1 : 0), NSL1 = V_IN > 0 ? 2 : 0;
     // per warp, per in-edge: {x row offset, y row offset, rx, ry}, {rz, -, -, -} (CACHED: every node has <= MAXD in-edges)
-    __shared__ float4 meta_s[CACHED ? BT / 32 : 1][CACHED ? MAXD : 1][2];
+    __shared__ float4 meta_s[CACHED ? 8 : 1][CACHED ? MAXD : 1][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // row within the chunk
     if (r >= nrows) return;
@@ -50,7 +49,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     const int e0 = rowptr[i], e1 = rowptr[i + 1];
     const int deg = e1 - e0;
     const float invd = 1.0f / (float)(deg > 0 ? deg : 1);
-    constexpr bool DO_S = ROLE != 1, DO_V = ROLE != 0 && V_IN > 0;
+    constexpr bool DO_S = true, DO_V = V_IN > 0;
     if (lane == 0 && DO_S) inv_deg[i] = invd;
     if (CACHED) {
         for (int t = lane; t < deg; t += 32) {
@@ -85,7 +84,7 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
         }
         const float* hk = hrow + kb * RK;
         const float* yk = yl + kb * RK * JAMUN_V;
-#pragma unroll(EUNROLL == 0 ? 2 : EUNROLL)
+#pragma unroll 2
         for (int t = 0; t < deg; ++t, hk += JAMUN_EDGE_HID) {
             int xoff, yoff;
             float rx, ry, rz;
@@ -191,161 +190,6 @@ conv_build_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, c
     }
 }
 
-// ---- block-staged variant for small chains ---------------------------------------------------------------------------------
-// A CTA owns 8 consecutive nodes; all their sources lie in the chains those nodes belong to, a contiguous node range
-// [lo, hi) of at most src_max nodes (host-computed bound).  The CTA stages the source rows of x once and, per channel block,
-// the Y slices of those sources in shared memory, so the per-edge gathers of the 8 warps become shared-memory reads (the
-// global-load version is bound by L1 wavefront throughput: every warp re-reads the same rows 17 times).
-template <int S_IN, int V_IN, bool STAGE_X>
-__global__ void __launch_bounds__(256, 2)
-conv_build_staged_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
-                         const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y,
-                         const int* __restrict__ chain_of, const int* __restrict__ chain_ptr, int src_max, int row0, int nrows,
-                         int rows_pad, float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride,
-                         float* __restrict__ p2, int p2_ld, float p2_scale, float* __restrict__ inv_deg) {
-    constexpr int RK = 4;
-    constexpr int NKB = JAMUN_EDGE_HID / RK;
-    constexpr int D_IN = S_IN + 3 * V_IN;
-    constexpr int NS = (S_IN + 31) / 32;
-    constexpr int NSL0 = NS + (V_IN > 0 ? 1 : 0), NSL1 = V_IN > 0 ? 2 : 0;
-    constexpr int YS = RK * JAMUN_V;  // floats per source per channel block
-    extern __shared__ __align__(16) float dsm[];
-    float4 (*meta_s)[MAXD][2] = reinterpret_cast<float4 (*)[MAXD][2]>(dsm);
-    float* ys = dsm + 8 * MAXD * 8;
-    float* xs_s = ys + (size_t)src_max * YS;
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int rb0 = blockIdx.x * 8;
-    const int r = rb0 + wib;
-    const bool valid = r < nrows;
-    const int i_first = row0 + rb0, i_last = row0 + min(rb0 + 7, nrows - 1);
-    const int lo = chain_ptr[chain_of[i_first]], hi = chain_ptr[chain_of[i_last] + 1];
-    const int n_src = hi - lo;
-    const int i = row0 + r;
-    int e0 = 0, deg = 0;
-    if (valid) {
-        e0 = rowptr[i];
-        deg = rowptr[i + 1] - e0;
-    }
-    const float invd = 1.0f / (float)(deg > 0 ? deg : 1);
-    if (valid && lane == 0) inv_deg[i] = invd;
-    for (int t = lane; t < deg; t += 32) {
-        const int j = col[e0 + t];
-        const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(e0 + t));
-        const int xo = STAGE_X ? (j - lo) * D_IN : j * D_IN;
-        meta_s[wib][t][0] = make_float4(__int_as_float(xo), __int_as_float((j - lo) * YS), rh.x, rh.y);
-        meta_s[wib][t][1] = make_float4(rh.z, 0.f, 0.f, 0.f);
-    }
-    if (STAGE_X) {
-        const float4* src = reinterpret_cast<const float4*>(x + (size_t)lo * D_IN);
-        float4* dst = reinterpret_cast<float4*>(xs_s);
-        for (int t = tid; t < n_src * (D_IN / 4); t += 256) dst[t] = __ldg(src + t);
-    }
-    const bool s_live = 4 * lane < NS * 32;
-    const bool s_load = 4 * lane < S_IN;
-    const int swz = (((lane >> 2) ^ (r & 7)) << 2) | (lane & 3);
-    const int swz4 = ((lane & 7) ^ (r & 7)) << 2;
-    const float* xbase = STAGE_X ? xs_s : x;
-    const float* xl = xbase + (s_load ? 4 * lane : 0);
-    const float* xv = xbase + S_IN + lane;
-    const float* hrow = h + (size_t)e0 * JAMUN_EDGE_HID;
-    float pacc[3] = {0.f, 0.f, 0.f};
-
-    for (int kb = 0; kb <= NKB; ++kb) {
-        const bool bias = kb == NKB;
-        __syncthreads();  // everyone is done with the previous Y slice (and, first time, x / meta are staged)
-        {
-            const int per = bias ? JAMUN_V / 4 : YS / 4;  // float4 per source in this slice
-            const float* ysrc = y + (size_t)lo * YLD + (size_t)kb * YS;
-            for (int t = tid; t < n_src * per; t += 256) {
-                const int sidx = t / per, q = t - sidx * per;
-                reinterpret_cast<float4*>(ys + (size_t)sidx * YS)[q] = __ldg(reinterpret_cast<const float4*>(ysrc + (size_t)sidx * YLD) + q);
-            }
-        }
-        __syncthreads();
-        float s0[RK][4];
-        float aq[RK], av[RK][3], ax[RK][3];
-#pragma unroll
-        for (int k = 0; k < RK; ++k) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) s0[k][t] = 0.f;
-            aq[k] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) av[k][c] = ax[k][c] = 0.f;
-        }
-        const float* hk = hrow + kb * RK;
-        for (int t = 0; t < deg; ++t, hk += JAMUN_EDGE_HID) {
-            const float4 m0 = meta_s[wib][t][0], m1 = meta_s[wib][t][1];
-            const int xoff = __float_as_int(m0.x), yoff = __float_as_int(m0.y);
-            const float rx = m0.z, ry = m0.w, rz = m1.x;
-            float4 hq4 = make_float4(1.f, 0.f, 0.f, 0.f);
-            if (!bias) hq4 = *reinterpret_cast<const float4*>(hk);
-            const float hq[RK] = {hq4.x, hq4.y, hq4.z, hq4.w};
-            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s_load) xs = *reinterpret_cast<const float4*>(xl + xoff);
-            const float* yj = ys + yoff + lane;
-            float tsum;
-            if (!bias) {
-                float ta = hq[0] * yj[0], tb = 0.f;
-                ffma2v(ta, tb, hq[1], hq[2], yj[JAMUN_V], yj[2 * JAMUN_V]);
-                ta = fmaf(hq[3], yj[3 * JAMUN_V], ta);
-                tsum = ta + tb;
-            } else {
-                tsum = yj[0];
-            }
-            ffma2(pacc[0], pacc[1], tsum, rx, ry);
-            pacc[2] = fmaf(rz, tsum, pacc[2]);
-            float vx = 0.f, vy = 0.f, vz = 0.f, q = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-            if (V_IN > 0) {
-                const float* vj = xv + xoff;
-                vx = vj[0];
-                vy = vj[V_IN];
-                vz = vj[2 * V_IN];
-                q = vx * rx + vy * ry + vz * rz;
-                cx = vy * rz - vz * ry;
-                cy = vz * rx - vx * rz;
-                cz = vx * ry - vy * rx;
-            }
-#pragma unroll
-            for (int k = 0; k < RK; ++k) {
-                ffma2(s0[k][0], s0[k][1], hq[k], xs.x, xs.y);
-                ffma2(s0[k][2], s0[k][3], hq[k], xs.z, xs.w);
-                if (V_IN > 0) {
-                    ffma2(aq[k], av[k][0], hq[k], q, vx);
-                    ffma2(av[k][1], av[k][2], hq[k], vy, vz);
-                    ffma2(ax[k][0], ax[k][1], hq[k], cx, cy);
-                    ax[k][2] = fmaf(hq[k], cz, ax[k][2]);
-                }
-            }
-        }
-        if (valid) {
-            const int nk = bias ? 1 : RK;
-#pragma unroll
-            for (int k = 0; k < RK; ++k) {
-                if (k >= nk) break;
-                const int kp = kb * RK + k;
-                if (s_live) {
-                    float* ps = a0 + ((size_t)(kp * NSL0 + (lane >> 3)) * rows_pad + r) * 32 + swz4;
-                    __stcs(reinterpret_cast<float4*>(ps), make_float4(s0[k][0], s0[k][1], s0[k][2], s0[k][3]));
-                }
-                if (V_IN > 0) {
-                    __stcs(a0 + ((size_t)(kp * NSL0 + NS) * rows_pad + r) * 32 + swz, aq[k]);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float* p1 = a1 + c * a1_comp_stride + ((size_t)(kp * NSL1) * rows_pad + r) * 32 + swz;
-                        __stcs(p1, av[k][c] * kInvSqrt3);
-                        __stcs(p1 + (size_t)rows_pad * 32, ax[k][c] * kInvSqrt2);
-                    }
-                }
-            }
-        }
-    }
-    if (valid) {
-        const float sc = p2_scale != 0.f ? p2_scale * invd : 1.0f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) p2[(size_t)i * p2_ld + c * JAMUN_V + lane] = pacc[c] * sc;
-    }
-}
-
 // x[rows, ld] columns [col0, col0+ncols) -> stage-major chunk-swizzled A operand, zero padded to 32-column stages
 __global__ void pack_rows_kernel(const float* __restrict__ x, int ld, int col0, int ncols, int rows, int rows_pad,
                                  float* __restrict__ a) {
@@ -367,8 +211,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, int ld, int col0, 
 // a0: [65*nslots0][rows_pad][32]; a1: 3 x [65*2][rows_pad][32] (component stride a1_comp_stride floats; unused when v_in == 0);
 // y: [N, 65*32] pre-transformed source rows; p2: [N, p2_ld] path-2 sums (see the kernel for p2_scale).
 extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                                  const float* rhat, const float* y, const int* chain_of, const int* chain_ptr, int src_max,
-                                  int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                                  const float* rhat, const float* y, int max_degree, int row0, int nrows, int rows_pad, float* a0, float* a1,
                                   long long a1_comp_stride, float* p2, int p2_ld, float p2_scale, float* inv_deg,
                                   jamun_stream_t stream) {
     JB_CHECK_ARG(x && rowptr && col && h && rhat && y && a0 && p2 && inv_deg, "null argument");
@@ -377,74 +220,17 @@ extern "C" int jamun_conv_build_a(const float* x, int s_in, int v_in, const int*
     if (nrows == 0) return JAMUN_OK;
     const int blocks = (nrows * 32 + 255) / 256;
     cudaStream_t s = jb::as_stream(stream);
-#define JB_LAUNCH_BUILD(S_, V_, RK_, MB_, C_, R_)                                                                             \
-    conv_build_kernel<S_, V_, RK_, MB_, C_, R_><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0,  \
-                                                                       a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
-    const char* venv = getenv("JAMUN_BUILD_VARIANT");  // tuning knob for experiments
-    const int variant = venv ? atoi(venv) : 1;
-    const bool cached = max_degree <= MAXD;
-    // block-staged kernel when every 8-node block's source range fits in shared memory (2 CTAs per SM)
-    if (cached && src_max > 0 && chain_of && chain_ptr && row0 % 8 == 0 && variant == 8) {
-        const int d_in = s_in + 3 * v_in;
-        const size_t base = 8 * MAXD * 8 * sizeof(float) + (size_t)src_max * 4 * JAMUN_V * sizeof(float);
-        const size_t with_x = base + (size_t)src_max * d_in * sizeof(float);
-        const size_t budget = 110 * 1024;
-        const int sblocks = (nrows + 7) / 8;
-        if (base <= budget && ((s_in == JAMUN_S && v_in == JAMUN_V) || (s_in == JAMUN_S0 && v_in == 0))) {
-            const bool sx = with_x <= budget;
-            const size_t smem = sx ? with_x : base;
-#define JB_LAUNCH_STAGED(S_, V_, X_)                                                                                         \
-    do {                                                                                                                      \
-        cudaFuncSetAttribute(conv_build_staged_kernel<S_, V_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        conv_build_staged_kernel<S_, V_, X_><<<sblocks, 256, smem, s>>>(x, rowptr, col, h, rhat, y, chain_of, chain_ptr,      \
-                                                                        src_max, row0, nrows, rows_pad, a0, a1,               \
-                                                                        (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg); \
-    } while (0)
-            if (s_in == JAMUN_S) {
-                JB_CHECK_ARG(a1, "a1 required for vector inputs");
-                if (sx) JB_LAUNCH_STAGED(JAMUN_S, JAMUN_V, true);
-                else JB_LAUNCH_STAGED(JAMUN_S, JAMUN_V, false);
-            } else {
-                if (sx) JB_LAUNCH_STAGED(JAMUN_S0, 0, true);
-                else JB_LAUNCH_STAGED(JAMUN_S0, 0, false);
-            }
-#undef JB_LAUNCH_STAGED
-            JB_CHECK_LAUNCH();
-            return JAMUN_OK;
-        }
-    }
+#define JB_LAUNCH_BUILD(S_, V_, RK_, MB_, C_)                                                                                 \
+    conv_build_kernel<S_, V_, RK_, MB_, C_><<<blocks, 256, 0, s>>>(x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1,    \
+                                                                   (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg)
+    const bool cached = max_degree <= MAXD;  // per-edge invariants fit the per-warp shared-memory cache
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
         JB_CHECK_ARG(a1, "a1 required for vector inputs");
-        if (!cached) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, false, 2);
-        else if (variant == 1) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, true, 2);
-        else if (variant == 3)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 5, true, 2, 128><<<(nrows * 32 + 127) / 128, 128, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 4)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 4, true, 2, 128><<<(nrows * 32 + 127) / 128, 128, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 6)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 3, true, 2, 256, 1><<<blocks, 256, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 7)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 6, true, 2, 128, 1><<<(nrows * 32 + 127) / 128, 128, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 10)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 2, true, 2, 256, 4><<<blocks, 256, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 5)
-            conv_build_kernel<JAMUN_S, JAMUN_V, 4, 7, true, 2, 96><<<(nrows * 32 + 95) / 96, 96, 0, s>>>(
-                x, rowptr, col, h, rhat, y, row0, nrows, rows_pad, a0, a1, (size_t)a1_comp_stride, p2, p2_ld, p2_scale, inv_deg);
-        else if (variant == 2) {  // split roles, 4 channels per pass
-            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 4, true, 0);
-            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 4, true, 1);
-        } else {                  // split roles, 8 channels per pass
-            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 3, true, 0);
-            JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 8, 2, true, 1);
-        }
+        if (cached) JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, true);
+        else JB_LAUNCH_BUILD(JAMUN_S, JAMUN_V, 4, 2, false);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        if (!cached) JB_LAUNCH_BUILD(JAMUN_S0, 0, 4, 2, false, 2);
-        else JB_LAUNCH_BUILD(JAMUN_S0, 0, 8, 3, true, 2);
+        if (cached) JB_LAUNCH_BUILD(JAMUN_S0, 0, 8, 3, true);
+        else JB_LAUNCH_BUILD(JAMUN_S0, 0, 4, 2, false);
     } else {
         jb::set_error("jamun_conv_build_a: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;

@@ -70,13 +70,6 @@ class Topology:
         self.cap = max(cap, 1)
         bond_in = int(torch.bincount(ei[1], minlength=max(N, 1)).max().item()) if ei.shape[1] else 0
         nbr = int(counts.max().item()) - 1 if N else 0
-        # largest number of nodes in the chains spanned by any aligned block of 8 consecutive nodes (builder staging bound)
-        if N:
-            first = bvec[0::8]
-            last = bvec[torch.clamp(torch.arange(7, N + 7, 8), max=N - 1)]
-            self.src_max = int((ptr[last + 1] - ptr[first]).max().item())
-        else:
-            self.src_max = 0
         self.max_degree = (nbr if max_num_neighbors is None else min(nbr, max_num_neighbors + 1)) + bond_in  # in-degree bound
         i32 = dict(dtype=torch.int32, device=dev)
         self.idx = []
@@ -275,7 +268,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
                               base + 4 * a1_off if v_in else None, comp, topo.inv_deg)
         if v_in:
             if build_impl != "tc":
-                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base,
+                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base,
                                  base + 4 * a1_off, comp, topo.p2.data_ptr(), 96, 0.0, topo.inv_deg)
             a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
             b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
@@ -287,7 +280,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
                             addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96])
         else:  # initial block: the 1e output is the path-2 gather alone, written in place
             if build_impl != "tc":
-                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.chain_of, topo.chain_ptr, topo.src_max, topo.max_degree, row0, nrows, rp, base, None, 0,
+                ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base, None, 0,
                                  out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
             ops.gemm_tf32x3([base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
                             topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)

@@ -123,11 +123,11 @@ def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: floa
     return out
 
 
-def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, y, chain_of, chain_ptr, src_max: int, max_degree: int, row0: int, nrows: int, rows_pad: int, a0_ptr: int,
+def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, y, max_degree: int, row0: int, nrows: int, rows_pad: int, a0_ptr: int,
                  a1_ptr: int, a1_comp_stride: int, p2_ptr: int, p2_ld: int, p2_scale: float, inv_deg):
     i32 = torch.int32
     rc = _lib.lib().jamun_conv_build_a(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), _ptr(y),
-                                       _ptr(chain_of, i32), _ptr(chain_ptr, i32), int(src_max), int(max_degree), row0, nrows, rows_pad, a0_ptr, a1_ptr, int(a1_comp_stride), p2_ptr, p2_ld,
+                                       int(max_degree), row0, nrows, rows_pad, a0_ptr, a1_ptr, int(a1_comp_stride), p2_ptr, p2_ld,
                                        float(p2_scale), _ptr(inv_deg), _stream())
     _lib.check(rc, "jamun_conv_build_a")
     _count()
