@@ -218,3 +218,40 @@ def test_block_tail_tc_matches_simt(models, monkeypatch):
                 continue
             assert not torch.isnan(c).any()
             assert (a - c).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("build", ["tc", "ffma"])
+def test_conv_tc_row_chunks(models, monkeypatch, build):
+    """Batches larger than the operand workspace are processed in row chunks: chunked == unchunked."""
+    from jamun_b200 import data, engine, ops, synthetic
+
+    o32, o64, prod = models
+    monkeypatch.setenv("JAMUN_B200_BUILD", build)
+    t = synthetic.make_tensors([57, 3, 1, 40, 40, 17, 64, 65, 31, 90])
+    gen = torch.Generator().manual_seed(2)
+    y = (t["pos"] + 0.04 * torch.randn(t["pos"].shape, generator=gen)).cuda()
+    ctx = prod.sigma_context(0.04)
+    plan = prod.arch_module.plan(ctx.c_noise, "cuda")
+    outs = []
+    for chunk in (None, 128):
+        topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
+        if chunk is not None:
+            topo.chunk_rows = chunk
+        ybar, p = ops.center_scale(y, topo.chain_ptr, ctx.c_in)
+        topo.build_csr(ybar, ctx.r_cut)
+        mu, step = plan.radial_grid(ctx.r_cut)
+        ops.edge_geom(p, topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
+        N = p.shape[0]
+        assert chunk is None or N > 2 * chunk
+        b = plan.blocks[1]
+        x = torch.randn(N, 216, generator=torch.Generator().manual_seed(9)).cuda()
+        ops.edge_radial_hidden(topo.rb, topo.ebond, topo.rowptr, b["w0r"], b["b0eff"], topo.h)
+        got = torch.full((N, 248), float("nan"), device="cuda")
+        engine.conv_tc(topo, b, x, got)
+        vadd = engine.conv_tc_join(topo, b)
+        if vadd is not None:
+            got[:, 152:] += vadd
+        torch.cuda.synchronize()
+        outs.append(got)
+    assert not torch.isnan(outs[1]).any()
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-6 * max(1.0, outs[0].abs().max().item())
