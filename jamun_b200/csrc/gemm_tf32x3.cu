@@ -13,6 +13,7 @@
 //              to the stage's "empty" mbarriers.
 // Up to four K-segments, each with its own A, B, N and TMEM accumulator columns, run back to back in one launch
 // (conv: one 0e segment with N=160 and three 1e segments with N=32).
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -46,6 +47,7 @@ struct Params {
     long long b_block_floats;
     int col_blocks;
     const float* row_scale;  // [rows] or null
+    int coalesce;            // stationary mode: transpose output blocks through shared memory (full-line stores)
 };
 
 struct __align__(1024) Smem {
@@ -55,6 +57,8 @@ struct __align__(1024) Smem {
     uint32_t tmem_base;
 };
 
+// COALESCE: epilogue variant for wide outputs in stationary mode (kept out of the contraction instantiation: +40 registers)
+template <bool COALESCE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P) {
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,6 +145,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                 uint32_t v[32];
                 umma::tmem_ld32(tmem + lane_base + (uint32_t)(sg.d_col + db * 128 + c0), v);
                 umma::wait_ld();
+                if (COALESCE && stationary && !sg.addend && sg.n_valid == sg.n_pad && (P.out_ld & 3) == 0) {
+                    // wide outputs (per-node transform): transpose the warp's 32 x 32 block through shared memory (the A ring's
+                    // slots 4-5 are never used in stationary mode) so that every store instruction writes four full 128-byte
+                    // lines instead of 32 scattered 16-byte pieces
+                    const int lane = threadIdx.x & 31;
+                    float* stg = reinterpret_cast<float*>(S.a[4]) + warp * 1024;
+                    const float sc = sg.alpha * rs_own;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                            make_float4(__uint_as_float(v[4 * q]) * sc, __uint_as_float(v[4 * q + 1]) * sc,
+                                        __uint_as_float(v[4 * q + 2]) * sc, __uint_as_float(v[4 * q + 3]) * sc);
+                    __syncwarp();
+                    const int ch = lane & 7;
+                    float* obase = sg.out + sg.out_col + cb * sg.n_valid + c0 + 4 * ch;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
+                        const int row = tile_row0 + (warp & 3) * 32 + rl;
+                        const float4 val = *reinterpret_cast<const float4*>(stg + rl * 32 + ((ch ^ (rl & 7)) << 2));
+                        if (row < P.rows) *reinterpret_cast<float4*>(obase + (size_t)row * P.out_ld) = val;
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 // thread = row: 8 x 16-byte stores per 32-column chunk (few instructions; the 8 pieces of a 128-byte line
                 // merge in L2)
                 const int row = tile_row0 + r;
@@ -268,6 +297,10 @@ extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* c
     if (rows == 0) return JAMUN_OK;
     Params P{};
     P.nseg = nseg;
+    {
+        const char* e = getenv("JAMUN_GEMM_COALESCE");
+        P.coalesce = e ? atoi(e) : 1;
+    }
     P.rows = rows;
     P.rows_pad = rows_pad;
     P.out_ld = out_ld;
@@ -285,12 +318,15 @@ extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* c
     JB_CHECK_ARG(dcol <= kACol0, "accumulators exceed 256 TMEM columns");
     const size_t smem = sizeof(Smem) + 1024;
     static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool wide = P.coalesce && col_blocks > 1;
+    cudaError_t e = wide ? cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         jb::set_error("jamun_gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return JAMUN_ECUDA;
     }
-    gemm_tf32x3_kernel<<<rows_pad / 128, kThreads, smem, jb::as_stream(stream)>>>(P);
+    if (wide) gemm_tf32x3_kernel<true><<<rows_pad / 128, kThreads, smem, jb::as_stream(stream)>>>(P);
+    else gemm_tf32x3_kernel<false><<<rows_pad / 128, kThreads, smem, jb::as_stream(stream)>>>(P);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
