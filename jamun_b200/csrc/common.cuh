@@ -44,6 +44,8 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_acc(float x) { return x / (1.0f + expf(-x)); }
+// SFU version (ex2.approx + rcp.approx): ~3e-7 relative, 4x fewer instructions; used where SiLU is evaluated per edge and channel
+__device__ __forceinline__ float siluf_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // Blackwell packed fp32 FMA (SASS FFMA2): two FMAs per issue slot; ptxas folds the {a,a} pack into a scalar operand.
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {

@@ -21,8 +21,12 @@ namespace {
 using namespace jb;
 
 constexpr int kTSlots = 4;                 // A slots in TMEM
-constexpr int kASlots = 6;                 // raw fp32 A tiles in shared memory (bulk-copied from HBM)
-constexpr int kBSlots = 3;                 // weight images in shared memory
+#ifndef JAMUN_GEMM_ASLOTS
+#define JAMUN_GEMM_ASLOTS 6
+#define JAMUN_GEMM_BSLOTS 3
+#endif
+constexpr int kASlots = JAMUN_GEMM_ASLOTS;  // raw fp32 A tiles in shared memory (bulk-copied from HBM)
+constexpr int kBSlots = JAMUN_GEMM_BSLOTS;  // weight images in shared memory
 constexpr int kBK = 32;                    // K per stage (one 128-byte swizzle row of tf32)
 constexpr int kMaxN = 160;
 constexpr int kATileBytes = 128 * kBK * 4;    // 16 KB

@@ -272,14 +272,14 @@ __global__ void __launch_bounds__(128, 4) edge_radial_hidden_kernel(const float*
             const int e = e0 + el;
             const float* bias = s_b + (ebond[e] ? JAMUN_EDGE_HID : 0) + 4 * og;
             float4 lo, hi;
-            lo.x = jb::siluf_acc(acc[i][0] + bias[0]);
-            lo.y = jb::siluf_acc(acc[i][1] + bias[1]);
-            lo.z = jb::siluf_acc(acc[i][2] + bias[2]);
-            lo.w = jb::siluf_acc(acc[i][3] + bias[3]);
-            hi.x = jb::siluf_acc(acc[i][4] + bias[32]);
-            hi.y = jb::siluf_acc(acc[i][5] + bias[33]);
-            hi.z = jb::siluf_acc(acc[i][6] + bias[34]);
-            hi.w = jb::siluf_acc(acc[i][7] + bias[35]);
+            lo.x = jb::siluf_fast(acc[i][0] + bias[0]);
+            lo.y = jb::siluf_fast(acc[i][1] + bias[1]);
+            lo.z = jb::siluf_fast(acc[i][2] + bias[2]);
+            lo.w = jb::siluf_fast(acc[i][3] + bias[3]);
+            hi.x = jb::siluf_fast(acc[i][4] + bias[32]);
+            hi.y = jb::siluf_fast(acc[i][5] + bias[33]);
+            hi.z = jb::siluf_fast(acc[i][6] + bias[34]);
+            hi.w = jb::siluf_fast(acc[i][7] + bias[35]);
             float4* dst = reinterpret_cast<float4*>(hl + (size_t)e * JAMUN_EDGE_HID) + og;
             dst[0] = lo;
             dst[8] = hi;
