@@ -26,6 +26,25 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().jamun_abi_version() == 1
 
 
+def test_abi_argument_checks_return_codes_and_messages():
+    """Entry points validate their arguments before touching the device: JAMUN_EINVAL (1) + text in jamun_last_error()."""
+    from jamun_b200 import _lib
+
+    lib = _lib.lib()
+    fake = 0x1000  # never dereferenced: the checks below fail before any launch
+    rc = lib.jamun_conv_build_tc(fake, 7, 3, fake, fake, fake, fake, 0, 4, 128, fake, fake, 0, None, None)
+    assert rc != 0 and b"unsupported input irreps 7x0e+3x1e" in lib.jamun_last_error()
+    rc = lib.jamun_conv_build_tc(None, 120, 32, fake, fake, fake, fake, 0, 4, 128, fake, fake, 0, None, None)
+    assert rc != 0 and b"null argument" in lib.jamun_last_error()
+    rc = lib.jamun_conv_build_tc(fake, 120, 32, fake, fake, fake, fake, 0, 256, 128, fake, fake, 0, None, None)
+    assert rc != 0 and b"nrows exceeds rows_pad" in lib.jamun_last_error()
+    rc = lib.jamun_tail_pack(fake, None, fake, 9, 9, 1.0, 1.0, 4, 128, fake, fake, 0, None)
+    assert rc != 0 and b"unsupported input irreps" in lib.jamun_last_error()
+    # empty problems are accepted without a launch
+    assert lib.jamun_conv_p2(fake, fake, fake, fake, fake, fake, 0, fake, fake, 96, 1.0, None, None) == 0
+    assert lib.jamun_tail_mix(fake, None, None, None, 0, fake, None, None, 0, None) == 0
+
+
 def test_walk_params_struct_matches_header():
     from jamun_b200 import _lib
 
