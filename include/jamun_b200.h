@@ -135,7 +135,8 @@ int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, c
  * p2[i, c*32+w] = sc * sum_{e->i} rhat_e[c] * T_e[w],  T_e[w] = sum_k' h'_e[k'] * y[col[e], k'*32+w],
  * sc = p2_scale/max(1,deg) (p2_scale != 0) or 1 (raw sums).  y: [N, 2176] rows from the per-node transform GEMM.
  * T is evaluated source-major (src_rowptr / src_eid from jamun_csr_by_source) into t_edge: [cap, 32] scratch.
- * Also writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL. */
+ * Also writes inv_deg[i] = 1/max(1,deg) when inv_deg != NULL.  p2 == NULL: only t_edge is computed (the receiver-side sum
+ * is then taken by jamun_tail_pack). */
 int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, const float* h, const float* rhat,
                   const float* y, int N, float* t_edge, float* p2, int p2_ld, float p2_scale, float* inv_deg,
                   jamun_stream_t stream);
@@ -163,12 +164,15 @@ int jamun_block_tail(const float* conv, const float* vadd, const float* x_in, in
  * jamun_tail_pack  Gate(conv (+vadd)) and x_in -> stage-major operands for jamun_gemm_tf32x3:
  *                  a_s: [4 + ceil(s_in/32)][rows_pad][32] (activated scalars | input scalars, zero padded per 32),
  *                  a_v: 3 components x [1 + (v_in>0)][rows_pad][32] (gated vectors | input vectors), stride a_v_comp_stride;
+ *                  t_edge != NULL: adds p2_scale/deg * sum_{e->i} rhat_e[c] t_edge[e, w] to the 1e part (jamun_conv_p2 with
+ *                  p2 == NULL); conv_has_v == 0: the 1e columns of conv are not read (initial block);
  * jamun_gemm_tf32x3 with B = [W_self ; W_skip] images (K zero-padded per 32) -> y [N, 216];
  * jamun_tail_mix   x_new = skip_w ? x_res*w + y*(1-w) : y;  x_scaled = x_new * s_next;  xs_op (or NULL): the 120 scalars of
  *                  x_scaled as the [4][rows_pad][32] operand of the next block's per-node transform (= jamun_pack_rows;
  *                  positions 120..127 of the last stage are not written: keep them zero). */
 int jamun_tail_pack(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, float c_act,
                     float c_gate, int N, int rows_pad, float* a_s, float* a_v, long long a_v_comp_stride,
+                    const int* rowptr, const float* rhat, const float* t_edge, float p2_scale, int conv_has_v,
                     jamun_stream_t stream);
 int jamun_tail_mix(const float* y, const float* x_res, const float* skip_w, const float* s_next, int N, float* x_new,
                    float* x_scaled, float* xs_op, int rows_pad, jamun_stream_t stream);

@@ -41,7 +41,7 @@ _PROTOS = {
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
     "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
-    "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f], I),
+    "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f, c_f, c_f, F, I, c_f], I),
     "jamun_tail_mix": ([c_f, c_f, c_f, c_f, I, c_f, c_f, c_f, I, c_f], I),
     "jamun_head": ([c_f, c_f, c_f, c_f, F, I, c_f, c_f], I),
     "jamun_walk_step": ([c_f, c_f, c_f, c_f, c_f, c_f, c_f, I, C.POINTER(WalkParams), c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),

@@ -504,12 +504,12 @@ extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int
 extern "C" int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, const float* h, const float* rhat,
                              const float* y, int N, float* t_edge, float* p2, int p2_ld, float p2_scale, float* inv_deg,
                              jamun_stream_t stream) {
-    JB_CHECK_ARG(rowptr && src_rowptr && src_eid && h && rhat && y && t_edge && p2, "null argument");
+    JB_CHECK_ARG(rowptr && src_rowptr && src_eid && h && rhat && y && t_edge, "null argument");
     if (N == 0) return JAMUN_OK;
     cudaStream_t s = jb::as_stream(stream);
     const int blocks = (int)(((size_t)N * 32 + 255) / 256);
     conv_p2_edge_kernel<<<(N + kP2Warps - 1) / kP2Warps, 32 * kP2Warps, 0, s>>>(src_rowptr, src_eid, h, y, N, t_edge);
-    conv_p2_reduce_kernel<<<blocks, 256, 0, s>>>(rowptr, rhat, t_edge, N, p2, p2_ld, p2_scale, inv_deg);
+    if (p2) conv_p2_reduce_kernel<<<blocks, 256, 0, s>>>(rowptr, rhat, t_edge, N, p2, p2_ld, p2_scale, inv_deg);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -310,7 +310,9 @@ block_tail_kernel(const float* __restrict__ conv, const float* __restrict__ vadd
 template <int S_IN, int V_IN>
 __global__ void __launch_bounds__(256)
 tail_pack_kernel(const float* __restrict__ conv, const float* __restrict__ vadd, const float* __restrict__ x_in, float c_act,
-                 float c_gate, int N, int rows_pad, float* __restrict__ a_s, float* __restrict__ a_v, size_t comp_stride) {
+                 float c_gate, int N, int rows_pad, float* __restrict__ a_s, float* __restrict__ a_v, size_t comp_stride,
+                 const int* __restrict__ rowptr, const float* __restrict__ rhat, const float* __restrict__ t_edge, float p2_scale,
+                 int conv_has_v) {
     constexpr int D_IN = S_IN + 3 * V_IN, S = JAMUN_S, V = JAMUN_V, NS = (S_IN + 31) / 32;
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -334,9 +336,25 @@ tail_pack_kernel(const float* __restrict__ conv, const float* __restrict__ vadd,
         a_s[((size_t)(4 + st) * rows_pad + i) * 32 + swz] = t < S_IN ? xi[t] : 0.f;
     }
     const float gate = c_gate * sigmoidf_acc(o[S + lane]);
+    // receiver-side sum of the 0e(x)1e->1e path over this node's (contiguous) in-edges: sum_e rhat_e[c] * T_e[w]
+    float p2v[3] = {0.f, 0.f, 0.f};
+    if (t_edge) {
+        const int e0 = rowptr[i], e1 = rowptr[i + 1];
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+            const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+            const float t = t_edge[(size_t)e * V + lane];
+            p2v[0] = fmaf(rh.x, t, p2v[0]);
+            p2v[1] = fmaf(rh.y, t, p2v[1]);
+            p2v[2] = fmaf(rh.z, t, p2v[2]);
+        }
+        const float sc = p2_scale / (float)(e1 > e0 ? e1 - e0 : 1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p2v[c] *= sc;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float v = o[SO + c * V + lane];
+        float v = (conv_has_v ? o[SO + c * V + lane] : 0.f) + p2v[c];
         if (vadd) v += vadd[(size_t)i * (3 * V) + c * V + lane];
         float* av = a_v + c * comp_stride;
         av[(size_t)i * 32 + swz] = v * gate;
@@ -483,17 +501,20 @@ extern "C" int jamun_block_tail(const float* conv, const float* vadd, const floa
 
 extern "C" int jamun_tail_pack(const float* conv, const float* vadd, const float* x_in, int s_in, int v_in, float c_act,
                                float c_gate, int N, int rows_pad, float* a_s, float* a_v, long long a_v_comp_stride,
+                               const int* rowptr, const float* rhat, const float* t_edge, float p2_scale, int conv_has_v,
                                jamun_stream_t stream) {
     JB_CHECK_ARG(conv && x_in && a_s && a_v && N <= rows_pad, "bad argument");
+    JB_CHECK_ARG(!t_edge || (rowptr && rhat), "t_edge needs rowptr and rhat");
     if (N == 0) return JAMUN_OK;
     const int blocks = (int)(((size_t)N * 32 + 255) / 256);
     cudaStream_t s = jb::as_stream(stream);
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
         tail_pack_kernel<JAMUN_S, JAMUN_V><<<blocks, 256, 0, s>>>(conv, vadd, x_in, c_act, c_gate, N, rows_pad, a_s, a_v,
-                                                                  (size_t)a_v_comp_stride);
+                                                                  (size_t)a_v_comp_stride, rowptr, rhat, t_edge, p2_scale,
+                                                                  conv_has_v);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
         tail_pack_kernel<JAMUN_S0, 0><<<blocks, 256, 0, s>>>(conv, vadd, x_in, c_act, c_gate, N, rows_pad, a_s, a_v,
-                                                             (size_t)a_v_comp_stride);
+                                                             (size_t)a_v_comp_stride, rowptr, rhat, t_edge, p2_scale, conv_has_v);
     } else {
         jb::set_error("jamun_tail_pack: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;

@@ -206,7 +206,7 @@ class E3ConvPlan:
         return values[1:-1].to(self.device).contiguous(), step
 
 
-def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None) -> None:
+def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False) -> None:
     """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
     17 column blocks) -> aggregate A of the other paths (jamun_conv_build_tc: per-node tcgen05 products; or the FP32-pipe
     jamun_conv_build_a) -> contraction jamun_gemm_tf32x3.  With the tensor-core builder the gather of Y (jamun_conv_p2) runs
@@ -253,7 +253,9 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         topo.ev_fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(topo.ev_fork)
-            if v_in:
+            if defer_reduce:  # only T_e; the receiver-side sum is taken by jamun_tail_pack (block_tail)
+                ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, None, 0, 0.0)
+            elif v_in:
                 ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, topo.p2.data_ptr(), 96,
                             b["alpha1"])
             else:
@@ -261,6 +263,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
                             out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"])
             topo.ev_join.record(side)
         topo.p2_pending = True
+        topo.p2_deferred = bool(defer_reduce)
     for row0 in range(0, N, rp):
         nrows = min(rp, N - row0)
         if build_impl == "tc":
@@ -292,6 +295,8 @@ def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:
         return None
     torch.cuda.current_stream().wait_event(topo.ev_join)
     topo.p2_pending = False
+    if getattr(topo, "p2_deferred", False):
+        return "deferred"  # block_tail hands t_edge to jamun_tail_pack
     return topo.p2 if b["v_in"] else None
 
 
@@ -300,7 +305,11 @@ TAIL_IMPL = os.environ.get("JAMUN_B200_TAIL", "tc")  # "tc": pack -> tcgen05 GEM
 
 def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_scaled, vadd) -> None:
     """Gate + self-interaction + skip Linear + noise-conditional skip/scale (ConvBlock.forward after the conv)."""
+    deferred = isinstance(vadd, str)
+    if deferred:
+        vadd = None
     if os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) != "tc" or topo.a_ws is None:
+        assert not deferred, "the deferred path-2 sum needs the tensor-core block tail"
         ops.block_tail(topo.conv, x_in, b["s_in"], b["v_in"], x_res, b["wself_s"], b["wself_v"], b["wskip_s"], b["wskip_v"], skip_w,
                        s_next, b["c_act"], b["c_gate"], x_new, x_scaled, vadd=vadd)
         return
@@ -315,7 +324,11 @@ def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_sc
     base = topo.a_ws.data_ptr()  # the conv operand is dead once the contraction has run
     a_v = base + 4 * st_s * rows_all * 32
     comp = st_v * rows_all * 32
-    ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
+    if deferred:
+        ops.tail_pack(topo.conv, None, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp,
+                      rowptr=topo.rowptr, rhat=topo.rhat, t_edge=topo.t_edge, p2_scale=b["alpha1"], conv_has_v=bool(b["v_in"]))
+    else:
+        ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
     ops.gemm_tf32x3([base] + [a_v + 4 * c * comp for c in range(3)], [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3,
                     [st_s, st_v, st_v, st_v], [128, 32, 32, 32], [120, 32, 32, 32], [0, 120, 152, 184], [1.0] * 4, N, rows_all, None,
                     topo.ytail.data_ptr(), ops.HID)
@@ -350,7 +363,8 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
             ops.conv_fwd(x_in, b["s_in"], b["v_in"], topo.rowptr, topo.col, topo.h, topo.rhat, b["m0"], b["m1"],
                          b["alpha0"], b["alpha1"], topo.conv)
         else:
-            conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None)
+            tail_tc = os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) == "tc" and os.environ.get("JAMUN_B200_BUILD", BUILD_IMPL) == "tc"
+            conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None, defer_reduce=tail_tc)
             vadd = conv_tc_join(topo, b)
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None

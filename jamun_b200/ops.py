@@ -148,7 +148,7 @@ def conv_p2(rowptr, src_rowptr, src_eid, h, rhat, y, t_edge, p2_ptr: int, p2_ld:
     rc = _lib.lib().jamun_conv_p2(_ptr(rowptr, i32), _ptr(src_rowptr, i32), _ptr(src_eid, i32), _ptr(h), _ptr(rhat), _ptr(y), N,
                                   _ptr(t_edge), p2_ptr, p2_ld, float(p2_scale), _ptr(inv_deg), _stream())
     _lib.check(rc, "jamun_conv_p2")
-    _count(2)
+    _count(2 if p2_ptr else 1)
 
 
 def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
@@ -190,9 +190,10 @@ def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_
 
 
 def tail_pack(conv, vadd, x_in, s_in: int, v_in: int, c_act: float, c_gate: float, rows_pad: int, a_s_ptr: int, a_v_ptr: int,
-              a_v_comp_stride: int):
+              a_v_comp_stride: int, rowptr=None, rhat=None, t_edge=None, p2_scale: float = 0.0, conv_has_v: bool = True):
     rc = _lib.lib().jamun_tail_pack(_ptr(conv), _ptr(vadd), _ptr(x_in), s_in, v_in, float(c_act), float(c_gate), conv.shape[0],
-                                    rows_pad, a_s_ptr, a_v_ptr, int(a_v_comp_stride), _stream())
+                                    rows_pad, a_s_ptr, a_v_ptr, int(a_v_comp_stride), _ptr(rowptr, torch.int32), _ptr(rhat),
+                                    _ptr(t_edge), float(p2_scale), int(conv_has_v), _stream())
     _lib.check(rc, "jamun_tail_pack")
     _count()
 

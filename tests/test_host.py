@@ -38,7 +38,7 @@ def test_abi_argument_checks_return_codes_and_messages():
     assert rc != 0 and b"null argument" in lib.jamun_last_error()
     rc = lib.jamun_conv_build_tc(fake, 120, 32, fake, fake, fake, fake, 0, 256, 128, fake, fake, 0, None, None)
     assert rc != 0 and b"nrows exceeds rows_pad" in lib.jamun_last_error()
-    rc = lib.jamun_tail_pack(fake, None, fake, 9, 9, 1.0, 1.0, 4, 128, fake, fake, 0, None)
+    rc = lib.jamun_tail_pack(fake, None, fake, 9, 9, 1.0, 1.0, 4, 128, fake, fake, 0, None, None, None, 0.0, 1, None)
     assert rc != 0 and b"unsupported input irreps" in lib.jamun_last_error()
     # empty problems are accepted without a launch
     assert lib.jamun_conv_p2(fake, fake, fake, fake, fake, fake, 0, fake, fake, 96, 1.0, None, None) == 0
