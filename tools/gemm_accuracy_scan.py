@@ -1,5 +1,7 @@
+"""Debug aid: accuracy of jamun_gemm_tf32x3 against fp64 over a few shapes (growth of the tensor-core accumulation error with K)."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_tc import _run_gemm
 for rows, K, N, n_pad in [(1000, 1280, 16, 16), (1000, 1280, 32, 32), (256, 1280, 16, 16), (128, 32, 16, 16), (128, 32, 48, 48), (512, 9984, 152, 160), (512, 12480, 32, 32)]:
     gen = torch.Generator().manual_seed(1)
