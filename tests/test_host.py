@@ -257,3 +257,28 @@ def test_jamun_alias_resolves_reference_targets():
         mod, name = path.rsplit(".", 1)
         assert getattr(importlib.import_module(mod), name) is obj, path
     assert pickle.loads(pickle.dumps(jamun_b200.default_arch())).func is jamun_b200.model.arch.E3Conv
+
+
+def test_training_conv_formulation_matches_kernel_model():
+    """jamun_b200/train.py evaluates the conv as a degree-padded batched GEMM; its helpers are device-agnostic torch code, so the
+    algebra is checked here against the per-edge reference emulation (the full training path itself is CUDA-only)."""
+    import kernel_model as KM
+    from jamun_b200 import train
+
+    gen = torch.Generator().manual_seed(11)
+    N, E = 13, 70
+    dst = torch.sort(torch.randint(0, N - 1, (E,), generator=gen)).values  # node N-1 stays isolated
+    src = torch.randint(0, N, (E,), generator=gen)
+    rowptr = torch.zeros(N + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
+    rhat = torch.nn.functional.normalize(torch.randn(E, 3, generator=gen, dtype=torch.float64), dim=1)
+    h = torch.randn(E, 64, generator=gen, dtype=torch.float64)
+    eid_pad, deg = train._padded_edge_index(rowptr, E)
+    assert int(deg[-1]) == 0 and eid_pad.shape[0] == N
+    for s_in, v_in in ((56, 0), (120, 32)):
+        x = torch.randn(N, s_in + 3 * v_in, generator=gen, dtype=torch.float64)
+        pk = dict(m0=torch.randn(65, s_in + v_in, 152, generator=gen, dtype=torch.float64),
+                  m1=torch.randn(65, s_in + 2 * v_in, 32, generator=gen, dtype=torch.float64), alpha0=0.7, alpha1=1.3)
+        got = train._conv(x, s_in, v_in, src, eid_pad, deg, h, rhat, pk)
+        want = KM.conv(x, s_in, v_in, src, dst, h, rhat, pk["m0"], pk["m1"], 0.7, 1.3, N)
+        assert torch.allclose(got, want, rtol=1e-10, atol=1e-10)

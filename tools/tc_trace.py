@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from jamun_b200 import _lib, data, engine, factory, ops, synthetic
 prod = factory.default_denoiser().cuda()
-t = synthetic.make_tensors(synthetic.workload_sizes("2AA", 1024), n_res=2)
+WL = sys.argv[1] if len(sys.argv) > 1 else "2AA"
+t = synthetic.make_tensors(synthetic.workload_sizes(WL, 64 if WL == "protein1000" else 1024), n_res={"2AA": 2, "4AA": 4, "protein1000": 100}[WL])
 gen = torch.Generator().manual_seed(1)
 y = (t["pos"] + 0.04 * torch.randn(t["pos"].shape, generator=gen)).cuda()
 topo = engine.Topology(data.Batch.from_tensors(t), "cuda")
