@@ -413,3 +413,74 @@ def test_sampler_end_to_end_with_callbacks(models):
     graphs = rec.samples[0]
     assert len(graphs) == 3 and graphs[0]["xhat_traj"].shape == (22, 3, 3) and graphs[2]["sample"].shape == (9, 3)
     assert all(torch.isfinite(gph["xhat"]).all() for gph in graphs)
+
+
+def test_full_size_properties(models, monkeypatch):
+    """BASELINE.json's headline size (1024 uncapped 2AA chains, 18 k atoms: every kernel runs multi-wave / persistent with
+    all 148 SMs busy) through size-independent properties: (1) the tensor-core pipeline equals the exact-fp32 CUDA-core
+    pipeline; (2) a chain's result does not depend on which other chains share the batch (oracle on a 12-chain slice,
+    bit-level neighbour lists included); (3) rotating + translating the input rotates the output."""
+    from jamun_b200 import data, engine, synthetic
+    from oracle import jamun_oracle as O
+
+    o32, o64, prod = models
+    sizes = synthetic.workload_sizes("2AA", 1024)
+    t = synthetic.make_tensors(sizes)
+    gen = torch.Generator().manual_seed(17)
+    y = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=gen)
+    batch = data.Batch.from_tensors(t).to("cuda")
+
+    def run(pos):
+        yb = batch.clone("pos")
+        yb.pos = pos.cuda().contiguous()
+        return prod.xhat(yb, SIGMA).pos.cpu()
+
+    x = run(y)
+    assert torch.isfinite(x).all()
+    # (1) exact-fp32 conv + block-tail kernels at the same size
+    monkeypatch.setattr(engine, "CONV_IMPL", "simt")
+    monkeypatch.setenv("JAMUN_B200_TAIL", "simt")
+    x_simt = run(y)
+    monkeypatch.setattr(engine, "CONV_IMPL", "tc")
+    monkeypatch.delenv("JAMUN_B200_TAIL")
+    assert torch.allclose(x, x_simt, rtol=1e-4, atol=1e-5), (x - x_simt).abs().max()
+    # (2) the last 12 chains alone, against the oracle
+    k = 12
+    n_tail = sum(sizes[-k:])
+    t_tail = synthetic.make_tensors(sizes[-k:], first_chain_id=len(sizes) - k)
+    assert torch.equal(t_tail["pos"], t["pos"][-n_tail:])
+    with torch.no_grad():
+        ref = o32.xhat(make_oracle_batch(t_tail).with_pos(y[-n_tail:]), SIGMA)
+    assert torch.allclose(x[-n_tail:], ref, rtol=1e-4, atol=1e-5), (x[-n_tail:] - ref).abs().max()
+    # (3) equivariance
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(1)))
+    if torch.det(Q) < 0:
+        Q[:, 0] *= -1
+    xr = run(y @ Q.T + torch.tensor([0.5, -0.1, 0.2]))
+    assert torch.allclose(xr, x @ Q.T, atol=3e-5), (xr - x @ Q.T).abs().max()
+
+
+def test_dense_graph_tc_equals_exact_pipeline(models, monkeypatch):
+    """1000-atom chains: every in-degree sits at the neighbour cap (33-35 > 32, so each node takes two operand chunks in the
+    tensor-core builder); the tensor-core pipeline must still equal the exact-fp32 CUDA-core pipeline."""
+    from jamun_b200 import data, engine, synthetic
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors([1000] * 5 + [333], n_res=100)
+    gen = torch.Generator().manual_seed(23)
+    y = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=gen)
+    yb = data.Batch.from_tensors(t).to("cuda")
+    yb.pos = y.cuda().contiguous()
+
+    def run():
+        return prod.xhat(yb, SIGMA).pos.cpu()
+
+    x = run()
+    topo = prod.topology_for(yb)
+    deg = (topo.rowptr[1:] - topo.rowptr[:-1])
+    assert int(deg.max()) > 32 and float(deg.float().mean()) > 30
+    monkeypatch.setattr(engine, "CONV_IMPL", "simt")
+    monkeypatch.setenv("JAMUN_B200_TAIL", "simt")
+    x_simt = run()
+    assert torch.isfinite(x).all()
+    assert torch.allclose(x, x_simt, rtol=1e-4, atol=1e-5), (x - x_simt).abs().max()
