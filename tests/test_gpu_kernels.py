@@ -484,3 +484,28 @@ def test_dense_graph_tc_equals_exact_pipeline(models, monkeypatch):
     x_simt = run()
     assert torch.isfinite(x).all()
     assert torch.allclose(x, x_simt, rtol=1e-4, atol=1e-5), (x - x_simt).abs().max()
+
+
+def test_full_size_graph_replay_equals_eager(models):
+    """The same check at the headline size (1024 chains): with two streams and persistent kernels in the captured step, graph
+    replay must reproduce the eager launches bit for bit, and a second run of the same seed must reproduce the first."""
+    import itertools
+
+    from jamun_b200 import data, synthetic
+    from jamun_b200.sampling.mcmc.functional import _splitting, fused_baoab
+
+    o32, o64, prod = models
+    t = synthetic.make_tensors(synthetic.workload_sizes("2AA", 1024))
+    y = (t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=torch.Generator().manual_seed(4))).cuda()
+    topo = prod.topology_for(data.Batch.from_tensors(t).to("cuda"))
+    kw = dict(steps=6, v_init="gaussian", save_trajectory=False, delta=0.04, friction=1.0, M=1.0, inverse_temperature=1.0,
+              score_fn_clip=100.0)
+    outs = []
+    for use_graph in (False, True, True):
+        torch.manual_seed(7)
+        _splitting._call_counter = itertools.count(1)
+        outs.append(fused_baoab(prod, topo, y, SIGMA, use_cuda_graph=use_graph, **kw))
+    for key in ("y", "v", "xhat"):
+        assert torch.isfinite(outs[0][key]).all()
+        assert torch.equal(outs[0][key], outs[1][key]), key
+        assert torch.equal(outs[1][key], outs[2][key]), key
