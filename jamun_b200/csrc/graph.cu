@@ -153,7 +153,9 @@ __global__ void exclusive_scan_kernel(const int* __restrict__ in, int* __restric
     if (tid == 0) out[n] = carry_s;
 }
 
-// ---- K2a: edge geometry.  One warp per 1 edge-slot group: lane = radial basis index. ----------------
+// ---- K2a: edge geometry.  A warp takes 32 consecutive edges: lane = edge for the geometry (all gathers of the 32 edges in
+// flight together, one 16-byte rhat store per lane), then lane = radial basis index for the 32 x 32 Gaussians (one 128-byte
+// row per edge). ----------------
 __global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restrict__ rowptr,
                                  const int* __restrict__ col, const int* __restrict__ edst, int N,
                                  const float* __restrict__ mu, float step, float* __restrict__ rhat,
@@ -162,17 +164,22 @@ __global__ void edge_geom_kernel(const float* __restrict__ p, const int* __restr
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const float mu_k = mu[lane];
-    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < E; e += warps) {
-        int j = col[e], i = edst[e];
-        float dx = p[3 * j] - p[3 * i], dy = p[3 * j + 1] - p[3 * i + 1], dz = p[3 * j + 2] - p[3 * i + 2];
-        float d = sqrtf(dx * dx + dy * dy + dz * dz);
-        float inv = 1.0f / fmaxf(d, 1e-12f);
-        if (lane < 4) {
-            float v = lane == 0 ? dx * inv : lane == 1 ? dy * inv : lane == 2 ? dz * inv : d;
-            rhat[4 * (size_t)e + lane] = v;
+    const float inv_step = 1.0f / step;
+    for (int e0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; e0 < E; e0 += warps * 32) {
+        const int e = e0 + lane;
+        float d = 0.f;
+        if (e < E) {
+            const int j = col[e], i = edst[e];
+            const float dx = p[3 * j] - p[3 * i], dy = p[3 * j + 1] - p[3 * i + 1], dz = p[3 * j + 2] - p[3 * i + 2];
+            d = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float inv = 1.0f / fmaxf(d, 1e-12f);
+            *reinterpret_cast<float4*>(rhat + 4 * (size_t)e) = make_float4(dx * inv, dy * inv, dz * inv, d);
         }
-        float t = (d - mu_k) / step;
-        rb[(size_t)e * JAMUN_NBASIS + lane] = expf(-(t * t)) / 1.12f;
+        const int cnt = min(32, E - e0);
+        for (int q = 0; q < cnt; ++q) {
+            const float t = (__shfl_sync(0xffffffffu, d, q) - mu_k) * inv_step;
+            rb[(size_t)(e0 + q) * JAMUN_NBASIS + lane] = __expf(-(t * t)) * (1.0f / 1.12f);
+        }
     }
 }
 
@@ -370,7 +377,7 @@ extern "C" int jamun_edge_geom(const float* p, const int* rowptr, const int* col
                                const float* mu, float step, float* rhat, float* rb, jamun_stream_t stream) {
     JB_CHECK_ARG(p && rowptr && col && edst && mu && rhat && rb, "null argument");
     if (N == 0 || cap == 0) return JAMUN_OK;
-    long long warps = cap;
+    long long warps = (cap + 31) / 32;
     int blocks = (int)((warps * 32 + 255) / 256);
     int max_blocks = jb::kNumSMs * 16;
     if (blocks > max_blocks) blocks = max_blocks;
