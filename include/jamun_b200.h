@@ -146,6 +146,14 @@ int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, co
                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                       const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                       const float* row_scale, float* out, int out_ld, jamun_stream_t stream);
+/* Split-K form of jamun_gemm_tf32x3 for small row counts (few 128-row tiles would leave most SMs idle): k_splits CTAs per tile
+ * each accumulate a contiguous share of every segment's stages and write a scaled partial result to
+ * partial[k_splits, rows, out_ld] (scratch); a second kernel sums the partials in ascending order (deterministic).
+ * No addend, no column blocks. */
+int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                             const int* n_valid, const int* out_col, const float* alpha, int rows, int rows_pad,
+                             const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
+                             jamun_stream_t stream);
 
 /* Gate + self-interaction + skip Linear + noise-conditional skip/scale
  * (e3tools/nn/_gate.py:63-64, _interaction.py:26-30, model/noise_conditioning.py:50-73,

@@ -40,6 +40,8 @@ _PROTOS = {
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
+    "jamun_gemm_tf32x3_splitk": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
+                                  C.POINTER(F), I, I, c_f, c_f, I, I, c_f, c_f], I),
     "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f, c_f, c_f, F, I, c_f], I),
     "jamun_tail_mix": ([c_f, c_f, c_f, c_f, I, c_f, c_f, c_f, I, c_f], I),

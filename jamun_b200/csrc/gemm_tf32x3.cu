@@ -52,6 +52,12 @@ struct Params {
     int col_blocks;
     const float* row_scale;  // [rows] or null
     int coalesce;            // stationary mode: transpose output blocks through shared memory (full-line stores)
+    // split-K (small row counts: few tiles): CTA (tile, y) accumulates stages [n*y/k_splits, n*(y+1)/k_splits) of every segment
+    // and writes its scaled partial result to partial + y * partial_stride; gemm_splitk_reduce_kernel sums them in order
+    int cb_groups;  // column-block passes spread over gridDim.y CTAs per tile (few tiles: the passes of one tile run in parallel)
+    int k_splits;
+    float* partial;
+    long long partial_stride;
 };
 
 struct __align__(1024) Smem {
@@ -94,8 +100,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     umma::fence_after_sync();
     const uint32_t tmem = S.tmem_base;
 
+    const int ksp = P.k_splits, ky = P.k_splits > 1 ? blockIdx.y : 0;
+    // this CTA's column blocks: [cb_base, cb_base + ncb) -- `cb` below is relative to cb_base
+    const int cb_base = P.cb_groups > 1 ? (int)((long long)P.col_blocks * blockIdx.y / P.cb_groups) : 0;
+    const int ncb = P.cb_groups > 1 ? (int)((long long)P.col_blocks * (blockIdx.y + 1) / P.cb_groups) - cb_base : P.col_blocks;
+    auto st_lo = [&](const Seg& sg) { return (int)((long long)sg.n_stages * ky / ksp); };
+    auto st_hi = [&](const Seg& sg) { return (int)((long long)sg.n_stages * (ky + 1) / ksp); };
     int total_stages = 0;
-    for (int s = 0; s < P.nseg; ++s) total_stages += P.seg[s].n_stages;
+    for (int s = 0; s < P.nseg; ++s) total_stages += st_hi(P.seg[s]) - st_lo(P.seg[s]);
     // A-stationary mode (wide per-node transforms: few K stages, many column-block passes): the converted operand stays in its
     // TMEM slots after pass 0; later passes only stream weight images and issue MMAs.
     const bool stationary = P.col_blocks > 1 && total_stages <= kTSlots;
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int sw = r & 7;
         const float rs_own = (P.row_scale && tile_row0 + r < P.rows) ? P.row_scale[tile_row0 + r] : 1.0f;
-        for (int cb = 0; cb < P.col_blocks; ++cb) {
+        for (int cb = 0; cb < ncb; ++cb) {
         for (int g = cb * total_stages + grp; g < (cb + 1) * total_stages && !(stationary && cb > 0); g += kConvWarps / 4) {
             const int sa = g % kASlots, st = g % kTSlots;
             umma::mbar_wait(&S.a_full[sa], (g / kASlots) & 1);
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                                         __uint_as_float(v[4 * q + 2]) * sc, __uint_as_float(v[4 * q + 3]) * sc);
                     __syncwarp();
                     const int ch = lane & 7;
-                    float* obase = sg.out + sg.out_col + cb * sg.n_valid + c0 + 4 * ch;
+                    float* obase = sg.out + sg.out_col + (cb_base + cb) * sg.n_valid + c0 + 4 * ch;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rl = it * 4 + (lane >> 3);
@@ -179,7 +191,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                 const int row = tile_row0 + r;
                 if (row < P.rows) {
                     const float sc = sg.alpha * rs_own;
-                    float* o = sg.out + (size_t)row * P.out_ld + sg.out_col + cb * sg.n_valid + c0;
+                    float* o = (ksp > 1 ? P.partial + (size_t)ky * P.partial_stride : sg.out) + (size_t)row * P.out_ld + sg.out_col +
+                               (cb_base + cb) * sg.n_valid + c0;
+                    if (st_hi(sg) == st_lo(sg)) {  // this split holds no stage of the segment: its accumulator was never written
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = 0u;
+                    }
                     const float* ad = sg.addend ? sg.addend + (size_t)row * sg.addend_ld + c0 : nullptr;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -209,10 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     } else if (warp == kConvWarps) {
         // ------------------------------------------------ A loader: one 16 KB bulk copy per stage
         int g = 0;
-        for (int cb = 0; cb < (stationary ? 1 : P.col_blocks); ++cb) {
+        for (int cb = 0; cb < (stationary ? 1 : ncb); ++cb) {
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
-                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int st_first = st_lo(sg);
+                for (int st = st_first, st_end = st_hi(sg); st < st_end; ++st, ++g) {
                     const int sa = g % kASlots;
                     umma::mbar_wait(&S.a_empty[sa], ((g / kASlots) & 1) ^ 1);
                     if (umma::elect_one()) {
@@ -226,16 +244,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     } else if (warp == kConvWarps + 1) {
         // ------------------------------------------------ B loader
         int g = 0;
-        for (int cb = 0; cb < P.col_blocks; ++cb) {
+        for (int cb = 0; cb < ncb; ++cb) {
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
                 const uint32_t bytes = 2u * sg.n_pad * 128u;
-                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int st_first = st_lo(sg);
+                for (int st = st_first, st_end = st_hi(sg); st < st_end; ++st, ++g) {
                     const int sb = g % kBSlots;
                     umma::mbar_wait(&S.b_empty[sb], ((g / kBSlots) & 1) ^ 1);
                     if (umma::elect_one()) {
                         umma::mbar_arrive_expect_tx(&S.b_full[sb], bytes);
-                        umma::bulk_g2s(S.b[sb], sg.b + (size_t)cb * P.b_block_floats + (size_t)st * (bytes / 4), bytes, &S.b_full[sb]);
+                        umma::bulk_g2s(S.b[sb], sg.b + (size_t)(cb_base + cb) * P.b_block_floats + (size_t)st * (bytes / 4), bytes, &S.b_full[sb]);
                     }
                     __syncwarp();
                 }
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
     } else {
         // ------------------------------------------------ MMA issuer (whole warp converged; one elected lane issues)
         int g = 0;
-        for (int cb = 0; cb < P.col_blocks; ++cb) {
+        for (int cb = 0; cb < ncb; ++cb) {
             const int db = dbuf ? (cb & 1) : 0;
             if (dbuf ? cb >= 2 : cb > 0) {  // the epilogue that last used this accumulator buffer must have drained it
                 umma::mbar_wait(&S.d_empty[db], dbuf ? ((cb - 2) >> 1) & 1 : (cb - 1) & 1);
@@ -255,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                 const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
                 const uint32_t d_addr = tmem + (uint32_t)(sg.d_col + db * 128);
                 const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
-                for (int st = 0; st < sg.n_stages; ++st, ++g) {
+                const int st_first = st_lo(sg);
+                for (int st = st_first, st_end = st_hi(sg); st < st_end; ++st, ++g) {
                     const int gl = g - cb * total_stages;  // stage index within the pass
                     const int ts = stationary ? gl : g % kTSlots, sb = g % kBSlots;
                     if (!stationary || cb == 0) umma::mbar_wait(&S.t_full[ts], stationary ? 0 : (g / kTSlots) & 1);
@@ -268,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                         for (int k = 0; k < kBK / 8; ++k) {
                             const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
                             const uint64_t dbl = umma::make_desc(bl + 2 * k, umma::kDescHiKmajorSw128);
-                            umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st | k) != 0);
+                            umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st != st_first) || k != 0);
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
                         }
@@ -292,15 +312,62 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
 }  // namespace
 
 // Generic entry: out[rows, n_valid] (+ column offsets) from up to 4 segments.  Exposed for tests and for the conv path.
+namespace {
+// out[row, c] = sum_y partial[y][row, c] over the segments' column ranges, y ascending (deterministic)
+__global__ void gemm_splitk_reduce_kernel(const float* __restrict__ partial, long long stride, int k_splits, int rows, int out_ld,
+                                          int4 c0, int4 nc, int nseg, float* __restrict__ out) {
+    const int col0[4] = {c0.x, c0.y, c0.z, c0.w}, ncol[4] = {nc.x, nc.y, nc.z, nc.w};
+    int width = 0;
+    for (int s = 0; s < nseg; ++s) width += ncol[s];
+    const long long total = (long long)rows * width;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(t / width);
+        int c = (int)(t % width), s = 0;
+        while (c >= ncol[s]) c -= ncol[s++];
+        const size_t off = (size_t)row * out_ld + col0[s] + c;
+        float acc = 0.f;
+        for (int y = 0; y < k_splits; ++y) acc += partial[(size_t)y * stride + off];
+        out[off] = acc;
+    }
+}
+}  // namespace
+
+static int gemm_launch(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                       const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
+                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, jamun_stream_t stream);
+
 extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                                  const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                                  const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                                  const float* row_scale, float* out, int out_ld, jamun_stream_t stream) {
+    return gemm_launch(nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats, rows,
+                       rows_pad, row_scale, out, out_ld, 1, nullptr, stream);
+}
+
+// Split-K form for small row counts (few 128-row tiles): k_splits CTAs per tile, partial: [k_splits, rows, out_ld] scratch.
+extern "C" int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const float* const* b, const int* n_stages,
+                                        const int* n_pad, const int* n_valid, const int* out_col, const float* alpha, int rows,
+                                        int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
+                                        jamun_stream_t stream) {
+    JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || partial), "bad k_splits / partial");
+    return gemm_launch(nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, nullptr, nullptr, 1, 0, rows, rows_pad, row_scale, out,
+                       out_ld, k_splits, partial, stream);
+}
+
+static int gemm_launch(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                       const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
+                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, jamun_stream_t stream) {
     JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
     if (rows == 0) return JAMUN_OK;
     Params P{};
     P.nseg = nseg;
+    P.k_splits = k_splits;
+    P.cb_groups = 1;
+    P.partial = partial;
+    P.partial_stride = (long long)rows * out_ld;
     {
         const char* e = getenv("JAMUN_GEMM_COALESCE");
         P.coalesce = e ? atoi(e) : 1;
@@ -329,8 +396,27 @@ extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* c
         jb::set_error("jamun_gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return JAMUN_ECUDA;
     }
-    if (wide) gemm_tf32x3_kernel<true><<<rows_pad / 128, kThreads, smem, jb::as_stream(stream)>>>(P);
-    else gemm_tf32x3_kernel<false><<<rows_pad / 128, kThreads, smem, jb::as_stream(stream)>>>(P);
+    if (wide) {
+        const int tiles = rows_pad / 128;
+        int groups = jb::kNumSMs / tiles;  // few tiles: run the column-block passes of a tile on several CTAs
+        if (groups > col_blocks) groups = col_blocks;
+        if (groups < 1) groups = 1;
+        P.cb_groups = groups;
+        gemm_tf32x3_kernel<true><<<dim3(tiles, groups), kThreads, smem, jb::as_stream(stream)>>>(P);
+    }
+    else gemm_tf32x3_kernel<false><<<dim3(rows_pad / 128, k_splits), kThreads, smem, jb::as_stream(stream)>>>(P);
+    if (k_splits > 1) {
+        int4 c0 = {0, 0, 0, 0}, nc = {0, 0, 0, 0};
+        int* pc0 = &c0.x;
+        int* pnc = &nc.x;
+        long long width = 0;
+        for (int s = 0; s < nseg; ++s) pc0[s] = out_col[s], pnc[s] = n_valid[s], width += n_valid[s];
+        long long total = (long long)rows * width;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > jb::kNumSMs * 8) blocks = jb::kNumSMs * 8;
+        gemm_splitk_reduce_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(partial, P.partial_stride, k_splits, rows, out_ld, c0, nc,
+                                                                            nseg, out);
+    }
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -206,6 +206,24 @@ class E3ConvPlan:
         return values[1:-1].to(self.device).contiguous(), step
 
 
+def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows: int, rp: int, rs_ptr, out_ptr,
+              addend=None) -> None:
+    """The contraction GEMM; with few row tiles (small batches) the K stages are split over several CTAs per tile."""
+    tiles = (nrows + 127) // 128
+    ks = min(16, 148 // tiles, min(n_stages)) if addend is None else 1
+    if os.environ.get("JAMUN_B200_SPLITK", "1") != "1":
+        ks = 1
+    if ks > 1:
+        need = ks * nrows * ops.GATE_IN
+        if getattr(topo, "gemm_partial", None) is None or topo.gemm_partial.numel() < need:
+            topo.gemm_partial = torch.empty(need, dtype=torch.float32, device=topo.device)
+        ops.gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, ks,
+                               topo.gemm_partial)
+    else:
+        ops.gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN,
+                        addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96])
+
+
 def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False) -> None:
     """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
     17 column blocks) -> aggregate A of the other paths (jamun_conv_build_tc: per-node tcgen05 products; or the FP32-pipe
@@ -277,16 +295,15 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
             b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
             p2 = topo.p2.data_ptr() + 4 * row0 * 96
             addend = None if build_impl == "tc" else [None, p2, p2 + 4 * 32, p2 + 4 * 64]
-            ops.gemm_tf32x3(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
-                            [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
-                            out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN,
-                            addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96])
+            _contract(topo, a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
+                      [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
+                      out.data_ptr() + 4 * row0 * ops.GATE_IN, addend=addend)
         else:  # initial block: the 1e output is the path-2 gather alone, written in place
             if build_impl != "tc":
                 ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base, None, 0,
                                  out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
-            ops.gemm_tf32x3([base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
-                            topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, ops.GATE_IN)
+            _contract(topo, [base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
+                      topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN)
 
 
 def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:

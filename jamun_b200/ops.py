@@ -179,6 +179,19 @@ def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: 
     _count()
 
 
+def gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr, out_ptr,
+                       out_ld: int, k_splits: int, partial):
+    """Split-K front end: partial is a [k_splits, rows, out_ld] fp32 scratch tensor."""
+    n = len(a_ptrs)
+    VP, IA, FA = C.c_void_p * n, C.c_int * n, C.c_float * n
+    assert partial.numel() >= k_splits * rows * out_ld
+    rc = _lib.lib().jamun_gemm_tf32x3_splitk(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col),
+                                             FA(*alpha), rows, rows_pad, row_scale_ptr, out_ptr, out_ld, int(k_splits),
+                                             _ptr(partial), _stream())
+    _lib.check(rc, "jamun_gemm_tf32x3_splitk")
+    _count(2 if k_splits > 1 else 1)
+
+
 def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
                c_act: float, c_gate: float, x_new, x_scaled, vadd=None):
     N = conv.shape[0]

@@ -255,3 +255,37 @@ def test_conv_tc_row_chunks(models, monkeypatch, build):
         outs.append(got)
     assert not torch.isnan(outs[1]).any()
     assert (outs[0] - outs[1]).abs().max().item() <= 2e-6 * max(1.0, outs[0].abs().max().item())
+
+
+@pytest.mark.parametrize("k_splits", [2, 5, 16])
+def test_gemm_splitk_matches_single_pass(k_splits):
+    """Split-K (few row tiles) == the single-pass GEMM up to the accumulation order, and is itself deterministic."""
+    from jamun_b200 import ops, packing
+
+    gen = torch.Generator().manual_seed(4)
+    rows, rows_pad = 200, 256
+    Ks, Ns, pads = [32 * 20, 32 * 7, 32 * 7], [152, 32, 32], [160, 32, 32]
+    A = [torch.randn(rows, k, generator=gen) for k in Ks]
+    B = [torch.randn(Ks[0], 152, generator=gen), torch.randn(Ks[1], 32, generator=gen)]
+    B = [B[0], B[1], B[1]]
+    a_ops = []
+    for a in A:
+        op = torch.empty(a.shape[1] // 32 * rows_pad * 32, device="cuda")
+        ops.pack_rows(a.cuda(), 0, a.shape[1], rows_pad, op)
+        a_ops.append(op)
+    imgs = [packing.pack_b_images(w.cuda(), p) for w, p in zip(B, pads)]
+    rs = (torch.rand(rows, generator=gen) + 0.5).cuda()
+    args = ([o.data_ptr() for o in a_ops], [i.data_ptr() for i in imgs], [k // 32 for k in Ks], pads, Ns, [0, 152, 184], [0.5, 2.0, 2.0],
+            rows, rows_pad, rs.data_ptr())
+    ref = torch.full((rows, 216), float("nan"), device="cuda")
+    ops.gemm_tf32x3(*args, ref.data_ptr(), 216)
+    outs = []
+    for _ in range(2):
+        out = torch.full((rows, 216), float("nan"), device="cuda")
+        partial = torch.full((k_splits * rows * 216,), float("nan"), device="cuda")
+        ops.gemm_tf32x3_splitk(*args, out.data_ptr(), 216, k_splits, partial)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert not torch.isnan(outs[0]).any()
+    assert (outs[0] - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
