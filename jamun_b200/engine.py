@@ -210,7 +210,12 @@ def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col,
               addend=None) -> None:
     """The contraction GEMM; with few row tiles (small batches) the K stages are split over several CTAs per tile."""
     tiles = (nrows + 127) // 128
-    ks = min(16, 148 // tiles, min(n_stages)) if addend is None else 1
+    if addend is not None:
+        ks = 1
+    elif tiles <= 74:  # few tiles: fill the SMs
+        ks = min(16, 148 // tiles, min(n_stages))
+    else:              # (balancing the last wave of multi-wave launches with a 2-4x split was measured: no gain)
+        ks = 1
     if os.environ.get("JAMUN_B200_SPLITK", "1") != "1":
         ks = 1
     if ks > 1:
