@@ -149,6 +149,7 @@ class _WalkWorkspace:
         self.score_traj = torch.empty(score_rows, N, 3, **f32)
         self.state = torch.zeros(2, dtype=torch.int64, device=device)  # [philox step, trajectory slot]
         self.graphs = {}
+        self.graph_launches = {}  # kernels per replay of each captured graph
 
 
 def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, steps: int,
@@ -220,6 +221,7 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
             if g is None:
                 prm.first, prm.last = 0, 0
                 g = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES
                 with torch.cuda.graph(g):
                     denoise()
                     ops.walk_step(ws.y, ws.v, ws.ybar, ws.p, ws.g, topo.chain_ptr, prm, None, ws.xhat, ws.score,
@@ -227,6 +229,8 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
                                   dev_state=ws.state)
                     ops.walk_advance(ws.state, 1 if save else 0)
                 ws.graphs[(gkey, save)] = g
+                ws.graph_launches[(gkey, save)] = ops.LAUNCHES - n0  # kernels recorded in the graph = launched per replay
+                ops.LAUNCHES = n0                                     # capture itself launches nothing
             return g
 
         first_slot = 1 if 0 in slot else 0
@@ -237,7 +241,7 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
             graphs = {s: graph_for(s) for s in needed}
             for i in range(1, steps - 1):
                 graphs[i in slot].replay()
-                ops._count(ws_launches(plan))
+                ops._count(ws.graph_launches[(gkey, i in slot)])
         if steps > 1:
             eager_step(steps - 1)
     out_y, out_v, out_x = ws.y.clone(), ws.v.clone(), ws.xhat.clone()
@@ -249,8 +253,3 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
         xhat_traj = xhat_traj.cpu() if xhat_traj is not None else None
         score_traj = score_traj.cpu()
     return {"y": out_y, "v": out_v, "xhat": out_x, "y_traj": y_traj, "xhat_traj": xhat_traj, "score_traj": score_traj}
-
-
-def ws_launches(plan) -> int:
-    """Kernel launches inside one replayed walk-jump step (for bench.py's gpu_launches claim)."""
-    return 3 + 1 + len(plan.blocks) * 6 - 2 + 1 + 2  # the initial block's transform is cached
