@@ -141,6 +141,15 @@ int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, 
                   const float* y, int N, float* t_edge, float* p2, int p2_ld, float p2_scale, float* inv_deg,
                   jamun_stream_t stream);
 
+/* Weight re-layout on the device (replaces the host-side packing of jamun_b200/packing.py; same bytes): row-major fp32
+ * weights -> the (hi | lo) stage images jamun_gemm_tf32x3 streams as its B operand, out[col_blocks][n_stages][2][n_pad*32]
+ * (UMMA K-major SWIZZLE_128B; hi = w & 0xFFFFE000, lo = w - hi).  Element (k, col) comes from
+ * src[(row + (col / n_inner) * outer_rows) * ld + col % n_inner] with row = row_map ? row_map[k] : k; rows outside
+ * [0, K_src) and columns >= N_valid are zero.  The operands replaced are the re-laid-out radial_nn.3 weights of
+ * e3tools/nn/_conv.py:84-94 and the o3.Linear weights of _interaction.py:23-24. */
+int jamun_pack_b(const float* src, int ld, const int* row_map, int K_src, int n_stages, int N_valid, int n_inner,
+                 int outer_rows, int n_pad, int col_blocks, float* out, jamun_stream_t stream);
+
 int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                       const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
@@ -229,6 +238,14 @@ int jamun_gaussian_axpy(const float* x, float a, float b, const float* noise, un
  * edge_attr): out[r, o] = act(sum_k w[o, k] in[r, k] + b[o]); act 0 = identity, 1 = SiLU. */
 int jamun_linear_act(const float* in, const float* w, const float* b, int rows, int K, int O, int act, float* out,
                      jamun_stream_t stream);
+
+/* e3nn.o3.FullyConnectedTensorProduct(in1, in2, out, shared_weights=False, internal_weights=False) for l <= 1 with per-row
+ * weights: the reference's plug-in seam `tp(x_src, sh, weight)` (e3tools/nn/_conv.py:76-94).  x1:[Z,d1] x2:[Z,d2] w:[Z,w_ld]
+ * in e3nn layouts; instr: [n_instr][12] int32 records (off1, mul1, l1, off2, mul2, l2, off_out, mul_out, l_out, weight offset,
+ * path coefficient sqrt(dim_out/fan_in) as float bits, 0) in e3nn's instruction order; out:[Z,d_out].  Not on the sampling
+ * path (which never materialises per-edge weights). */
+int jamun_tensor_product(const float* x1, int d1, const float* x2, int d2, const float* w, long long w_ld, const int* instr,
+                         int n_instr, int d_out, int Z, float* out, jamun_stream_t stream);
 
 /* e3nn layout <-> SoA layout for `s x0e + v x1e` rows. */
 int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);

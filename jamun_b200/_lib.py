@@ -37,6 +37,8 @@ _PROTOS = {
     "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
     "jamun_conv_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, c_f, I, F, c_f, c_f], I),
     "jamun_csr_by_source": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
+    "jamun_pack_b": ([c_f, I, c_f, I, I, I, I, I, I, I, c_f, c_f], I),
+    "jamun_tensor_product": ([c_f, I, c_f, I, c_f, C.c_longlong, c_f, I, I, I, c_f, c_f], I),
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),

@@ -197,6 +197,23 @@ __global__ void fill_sources_kernel(const int* __restrict__ rowptr, const int* _
     }
 }
 
+// The atomic cursor above leaves each source's out-edge list in arrival order; an insertion sort of every (short) list makes
+// src_eid ascending per source, i.e. bit-reproducible, so source-major reductions (backward dx) are deterministic.
+__global__ void sort_sources_kernel(const int* __restrict__ src_rowptr, int N, int* __restrict__ src_eid) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
+    for (int a = s0 + 1; a < s1; ++a) {
+        const int v = src_eid[a];
+        int b = a - 1;
+        while (b >= s0 && src_eid[b] > v) {
+            src_eid[b + 1] = src_eid[b];
+            --b;
+        }
+        src_eid[b + 1] = v;
+    }
+}
+
 // ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0rt[k][o] rb[e][k] + b0eff[flag][o]) --------
 // A [E x 32] . [32 x 64] product on the FP32 pipe.  One CTA of 128 threads owns a tile of 128 edges: the tile's radial
 // basis (16 KB, contiguous) and the transposed weight (8 KB) arrive by two bulk async copies; each thread keeps an
@@ -369,6 +386,7 @@ extern "C" int jamun_csr_by_source(const int* rowptr, const int* col, int N, int
     exclusive_scan_kernel<<<1, 1024, 0, s>>>(scratch, src_rowptr, N);
     cudaMemsetAsync(scratch, 0, (size_t)(N + 1) * sizeof(int), s);
     fill_sources_kernel<<<blocks, 256, 0, s>>>(rowptr, col, N, src_rowptr, scratch, src_eid);
+    sort_sources_kernel<<<(N + 127) / 128, 128, 0, s>>>(src_rowptr, N, src_eid);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -107,6 +107,7 @@ class Topology:
         self.xs_op_of = None  # the tensor whose scalars currently sit packed in xs_op (written by tail_mix)
         self.y0 = None
         self.y0_key = None
+        self.csr_generation = 0  # bumped by every writer of the CSR buffers (Denoiser.add_edges tags batches with it)
 
     def build_csr(self, pos: torch.Tensor, r_cut: float):
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
@@ -115,6 +116,7 @@ class Topology:
         ops.radius_csr(pos, self.chain_of, self.chain_ptr, r2, mnn, self.bond_rowptr, self.bond_src, self.scratch,
                        self.rowptr, self.col, self.edst, self.ebond)
         ops.csr_by_source(self.rowptr, self.col, self.scratch, self.src_rowptr, self.src_eid)
+        self.csr_generation += 1
 
     def set_csr_from_edge_index(self, edge_index: torch.Tensor, bond_mask: torch.Tensor):
         """Compatibility path for callers that hand E3Conv.forward an explicit edge list."""
@@ -130,6 +132,7 @@ class Topology:
         rp[1:] = torch.cumsum(torch.bincount(ei[1], minlength=self.N), 0)
         self.rowptr.copy_(rp.to(torch.int32))
         ops.csr_by_source(self.rowptr, self.col, self.scratch, self.src_rowptr, self.src_eid)
+        self.csr_generation += 1
 
     def edge_index(self):
         """Materialise (edge_index [2,E] int64, bond_mask [E] int64) from the CSR -- host sync; tests/API only."""
@@ -160,50 +163,68 @@ class E3ConvPlan:
         self.c_noise = float(c_noise)
         self.device = dev
         self.serial = next(E3ConvPlan._serials)  # cache key for plan-dependent constants held by topologies
+        # Parameter re-layout happens on a host copy of the module (pure indexing, once per plan) and the results are uploaded;
+        # the (hi | lo) operand images are produced on the device by jamun_pack_b -- one launch per operand, so building a
+        # plan issues a few dozen launches of this library's kernels and no framework indexing kernels.
+        import copy
+
+        saved, g._plan = g._plan, None
+        try:
+            with torch.no_grad():  # parameters / buffers are copied device -> host directly (memo), the module tree is cloned
+                memo = {id(t): torch.nn.Parameter(t.detach().cpu(), requires_grad=False) for t in g.parameters()}
+                memo.update({id(t): t.detach().cpu() for t in g.buffers()})
+                gc = copy.deepcopy(g, memo)
+        finally:
+            g._plan = saved
+        up = lambda t: t.detach().to(torch.float32).contiguous().to(dev)  # noqa: E731  (host -> device copy, no kernel)
         with torch.no_grad():
-            emb = g.embed_bondedness.weight.detach().to(dev, torch.float32)
-            self.tables = [t.detach().to(dev, torch.float32).contiguous() for t in g.atom_embedder.tables()]
+            emb = gc.embed_bondedness.weight.detach().to(torch.float32)
+            self.tables = [up(t) for t in gc.atom_embedder.tables()]
             if sum(t.shape[1] for t in self.tables) != ops.S0:
                 raise NotImplementedError("atom embedding width must be 56")
             self.use_residue_sequence_index = g.atom_embedder.use_residue_sequence_index
             self.blocks: List[Dict] = []
-            for b in blocks:
+            for b in [gc.initial_projector, *gc.layers]:
                 pk = b.pack(emb)
-                blk = {k: (v.detach().to(dev, torch.float32).contiguous() if isinstance(v, torch.Tensor) else v)
-                       for k, v in pk.items()}
-                w0, w1, wy = packing.conv_k_layout(blk["m0"], blk["m1"], blk["s_in"], blk["v_in"])
-                blk["b0_img"] = packing.pack_b_images(w0, 160)
-                blk["b1_img"] = packing.pack_b_images(w1, 32) if w1 is not None else None
-                wy_pad = torch.zeros(wy.shape[0], Y_LD, dtype=wy.dtype, device=wy.device)
-                wy_pad[:, :wy.shape[1]] = wy
-                blk["wy_img"] = packing.pack_b_column_blocks(wy_pad, 128)
+                host = {k: (v.detach().to(torch.float32).contiguous() if isinstance(v, torch.Tensor) else v) for k, v in pk.items()}
+                ns_in = (host["s_in"] + 31) // 32
                 # block tail as one GEMM: [activated scalars (128) | input scalars (32 NS)] . [W_self ; W_skip], same for vectors
-                ns_in = (blk["s_in"] + 31) // 32
-                ws = torch.zeros(128 + 32 * ns_in, 120, dtype=torch.float32, device=dev)
-                ws[:120] = blk["wself_s"]
-                ws[128:128 + blk["s_in"]] = blk["wskip_s"]
-                blk["tail_bs_img"] = packing.pack_b_images(ws, 128)
-                wv = blk["wself_v"] if blk["wskip_v"] is None else torch.cat([blk["wself_v"], blk["wskip_v"]], dim=0)
-                blk["tail_bv_img"] = packing.pack_b_images(wv.contiguous(), 32)
+                ws = torch.zeros(128 + 32 * ns_in, 120, dtype=torch.float32)
+                ws[:120] = host["wself_s"]
+                ws[128:128 + host["s_in"]] = host["wskip_s"]
+                wv = host["wself_v"] if host["wskip_v"] is None else torch.cat([host["wself_v"], host["wskip_v"]], dim=0)
+                blk = {k: (up(v) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+                blk["b0_img"], blk["b1_img"], blk["wy_img"] = packing.pack_conv_operands_device(blk["m0"], blk["m1"], blk["s_in"],
+                                                                                                blk["v_in"])
+                blk["tail_bs_img"] = ops.pack_b(up(ws), n_stages=ws.shape[0] // 32, n_pad=128)
+                blk["tail_bv_img"] = ops.pack_b(up(wv), n_stages=wv.shape[0] // 32, n_pad=32)
                 self.blocks.append(blk)
-            self.w0r_all = torch.stack([b["w0r"] for b in self.blocks]).contiguous()      # [L, 32, 64]
-            self.b0eff_all = torch.stack([b["b0eff"] for b in self.blocks]).contiguous()  # [L, 2, 64]
+            self.w0r_all = up(torch.stack([b.pack(emb)["w0r"] for b in [gc.initial_projector, *gc.layers]]))      # [L, 32, 64]
+            self.b0eff_all = up(torch.stack([b.pack(emb)["b0eff"] for b in [gc.initial_projector, *gc.layers]]))  # [L, 2, 64]
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
             self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
             self.skips = [ops.noise_mlp(*map(f32, m.weights.mlp_operands()), self.c_noise, True) for m in g.skip_connections]
-            blk, lin2 = g.output_head[0], g.output_head[1]
-            self.head_w1s = f32(blk.lin.packed(0))
-            self.head_w1v = f32(blk.lin.packed(1))
+            blk, lin2 = gc.output_head[0], gc.output_head[1]
+            self.head_w1s = up(blk.lin.packed(0))
+            self.head_w1v = up(blk.lin.packed(1))
             self.head_cgate = blk.gate.c_gate
-            self.head_w2 = f32(lin2.packed(1).reshape(-1) * g.output_gain.detach())
+            self.head_w2 = up(lin2.packed(1).reshape(-1) * gc.output_gain.detach())
         self.n_basis = ops.NBASIS
+        self._grids: Dict[float, tuple] = {}  # r_cut -> (centres on the device, spacing); never evicted (see radial_grid)
 
     def radial_grid(self, r_cut: float):
-        """soft_one_hot_linspace(..., cutoff=True) grid: centres linspace(0, r, n+2)[1:-1] and their spacing."""
-        values = torch.linspace(0.0, float(r_cut), self.n_basis + 2, dtype=torch.float32)
-        step = float(values[1] - values[0])
-        return values[1:-1].to(self.device).contiguous(), step
+        """soft_one_hot_linspace(..., cutoff=True) grid: centres linspace(0, r, n+2)[1:-1] and their spacing.
+
+        The device tensor is cached on the plan (keyed by r_cut): CUDA graphs captured by fused_baoab bake its raw pointer
+        into edge_geom through the C ABI, so it must outlive every graph that replays it."""
+        key = float(r_cut)
+        hit = self._grids.get(key)
+        if hit is None:
+            values = torch.linspace(0.0, key, self.n_basis + 2, dtype=torch.float32)
+            step = float(values[1] - values[0])
+            hit = self._grids[key] = (values[1:-1].to(self.device).contiguous(), step)
+        return hit
 
 
 def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows: int, rp: int, rs_ptr, out_ptr,

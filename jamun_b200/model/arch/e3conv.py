@@ -65,7 +65,12 @@ class E3Conv(torch.nn.Module):
         if topo is None:
             topo = engine.Topology(data, pos.device, max_num_neighbors=None)
             data["_topology"] = topo
-        if "_csr_ready" not in data or not data["_csr_ready"]:
+        tag = data["_csr_ready"] if "_csr_ready" in data else None
+        if tag != (topo.csr_generation, pos.data_ptr(), pos._version) and tag != (topo.csr_generation, "scaled"):
+            # no CSR, or one built for other positions / overwritten since: use the edge list the caller supplied
+            if "bond_mask" not in data:
+                raise RuntimeError("E3Conv.forward: the graph carries neither a current CSR (Denoiser.add_edges on these "
+                                   "positions) nor an explicit edge_index + bond_mask")
             topo.set_csr_from_edge_index(data["edge_index"], data["bond_mask"])
         plan = self.plan(float(torch.as_tensor(c_noise).reshape(-1)[0]), pos.device)
         g = torch.empty_like(pos)

@@ -130,6 +130,8 @@ class Denoiser(_Base):
         key = float(torch.as_tensor(sigma, dtype=torch.float32))
         ctx = self._sigma_ctx.get(key)
         if ctx is None:
+            if len(self._sigma_ctx) >= 16:  # training draws sigma from a continuous distribution: keep the cache bounded
+                self._sigma_ctx.pop(next(iter(self._sigma_ctx)))
             ctx = self._sigma_ctx[key] = SigmaContext(key, self.average_squared_distance, self.max_radius)
         return ctx
 
@@ -212,7 +214,9 @@ class Denoiser(_Base):
         ``materialize=True`` additionally writes ``edge_index``/``bond_mask`` tensors (host sync)."""
         topo = self.topology_for(y)
         topo.build_csr(y.pos.contiguous(), float(radial_cutoff))
-        y["_csr_ready"] = True
+        # tag: the CSR held by `topo` was built from exactly this position tensor (E3Conv.forward checks it, so a clone whose
+        # positions changed, or a topology rebuilt by another call, falls back to the explicit edge_index)
+        y["_csr_ready"] = (topo.csr_generation, y.pos.data_ptr(), y.pos._version)
         if materialize:
             y.edge_index, y.bond_mask = topo.edge_index()
         return y
@@ -222,6 +226,7 @@ class Denoiser(_Base):
         y = self.add_edges(y, ctx.r_cut)
         y_scaled = y.clone("pos")
         y_scaled.pos = y.pos * ctx.c_in
+        y_scaled["_csr_ready"] = (y["_csr_ready"][0], "scaled")  # same graph, positions scaled by c_in (denoiser.py:192)
         xhat = y.clone("pos")
         c_noise = torch.tensor([ctx.c_noise], dtype=torch.float32)
         g_pred = self.g(y_scaled, c_noise, ctx.r_cut)
@@ -322,9 +327,18 @@ class Denoiser(_Base):
                 k2 = "g." + k[len("g._orig_mod."):]
             elif k.startswith("g.") and not k.startswith("g._orig_mod.") and want_shim:
                 k2 = "g._orig_mod." + k[2:]
-            if k2 not in own and (v.numel() == 0 or k2.endswith("output_mask") or "_w3j" in k2 or "_compiled_main" in k2
-                                  or ".tp." in k2 or k2.endswith(".sh._lmax")):
-                continue
+            if k2 not in own:
+                # e3nn's constant buffers: empty weight/bias of tensor products with external weights,
+                # output masks, Wigner-3j tables of the compiled tensor products
+                if v.numel() == 0 or k2.endswith("output_mask") or "_w3j" in k2 or "_compiled_main" in k2 \
+                        or k2.endswith(".sh._lmax"):
+                    continue
+                if ".tp." in k2:  # anything else under a tensor product would be a learnable tensor we do not model
+                    import warnings
+
+                    warnings.warn(f"load_state_dict: ignoring unknown tensor-product entry {k2!r} with {v.numel()} elements "
+                                  f"(only e3nn's constant buffers are expected there)", stacklevel=2)
+                    continue
             fixed[k2] = v
         return super().load_state_dict(fixed, strict=strict, **kw)
 

@@ -156,13 +156,29 @@ def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
     rc = _lib.lib().jamun_csr_by_source(_ptr(rowptr, i32), _ptr(col, i32), rowptr.numel() - 1, col.numel(), _ptr(scratch, i32),
                                         _ptr(src_rowptr, i32), _ptr(src_eid, i32), _stream())
     _lib.check(rc, "jamun_csr_by_source")
-    _count(3)
+    _count(4)
 
 
 def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
     rc = _lib.lib().jamun_pack_rows(_ptr(x), x.shape[1], col0, ncols, x.shape[0], rows_pad, _ptr(a), _stream())
     _lib.check(rc, "jamun_pack_rows")
     _count()
+
+
+def pack_b(src, n_stages: int, n_pad: int, row_map=None, k_src: Optional[int] = None, n_valid: Optional[int] = None,
+           n_inner: Optional[int] = None, outer_rows: int = 0, col_blocks: int = 1, out=None):
+    """Row-major weights -> (hi | lo) stage images of the GEMM's B operand ([col_blocks, n_stages, 2, n_pad*32])."""
+    assert src.dim() == 2
+    k_src = src.shape[0] if k_src is None else k_src
+    n_valid = src.shape[1] if n_valid is None else n_valid
+    n_inner = max(n_valid, 1) if n_inner is None else n_inner
+    shape = (col_blocks, n_stages, 2, n_pad * 32) if col_blocks > 1 else (n_stages, 2, n_pad * 32)
+    out = torch.empty(shape, dtype=torch.float32, device=src.device) if out is None else out
+    rc = _lib.lib().jamun_pack_b(_ptr(src), src.stride(0), _ptr(row_map, torch.int32), k_src, n_stages, n_valid, n_inner,
+                                 outer_rows, n_pad, col_blocks, _ptr(out), _stream())
+    _lib.check(rc, "jamun_pack_b")
+    _count()
+    return out
 
 
 def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr,
@@ -283,5 +299,15 @@ def linear_act(x, w, b, act: int = 0):
     out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
     rc = _lib.lib().jamun_linear_act(_ptr(x), _ptr(w), _ptr(b), x.shape[0], x.shape[1], w.shape[0], int(act), _ptr(out), _stream())
     _lib.check(rc, "jamun_linear_act")
+    _count()
+    return out
+
+
+def tensor_product(x1, x2, weight, table, d_out: int):
+    Z = x1.shape[0]
+    out = torch.empty(Z, d_out, device=x1.device, dtype=torch.float32)
+    rc = _lib.lib().jamun_tensor_product(_ptr(x1), x1.shape[1], _ptr(x2), x2.shape[1], _ptr(weight), weight.stride(0),
+                                         _ptr(table, torch.int32), table.shape[0], d_out, Z, _ptr(out), _stream())
+    _lib.check(rc, "jamun_tensor_product")
     _count()
     return out

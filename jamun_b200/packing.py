@@ -65,3 +65,46 @@ def pack_b_column_blocks(w: torch.Tensor, block: int = 160) -> torch.Tensor:
     K, N = w.shape
     assert N % block == 0
     return torch.stack([pack_b_images(w[:, c:c + block].contiguous(), block) for c in range(0, N, block)]).contiguous()
+
+
+# ---- device-side packing (jamun_pack_b): the same images, produced by one kernel launch per operand ---------------------
+_ROW_MAPS = {}
+
+
+def conv_row_maps(s_in: int, v_in: int, device):
+    """int32 row maps for jamun_pack_b reproducing conv_k_layout without materialising w0 / w1:
+    map0[k] -> row of m0.view(65*(s_in+v_in), 152) (or -1 for the zero padding of the scalar slots),
+    map1[k] -> row of m1.view(65*(s_in+2 v_in), 32) (None if v_in == 0)."""
+    key = (s_in, v_in, str(device))
+    hit = _ROW_MAPS.get(key)
+    if hit is None:
+        ns = (s_in + 31) // 32
+        u0, u1 = s_in + v_in, s_in + 2 * v_in
+        per = ns * 32 + v_in
+        kp = torch.arange(65)[:, None]
+        r = torch.arange(per)[None, :]
+        m = torch.where(r < s_in, kp * u0 + r, torch.where(r < ns * 32, torch.full_like(r, -1), kp * u0 + s_in + (r - ns * 32)))
+        map0 = m.reshape(-1).to(torch.int32)
+        map1 = None
+        if v_in:
+            r1 = torch.arange(2 * v_in)[None, :]
+            map1 = (kp * u1 + s_in + r1).reshape(-1).to(torch.int32).to(device)
+        hit = _ROW_MAPS[key] = (map0.to(device), map1)
+    return hit
+
+
+def pack_conv_operands_device(m0: torch.Tensor, m1: torch.Tensor, s_in: int, v_in: int):
+    """(b0_img, b1_img | None, wy_img) for CUDA tensors m0 [65, s_in+v_in, 152], m1 [65, s_in+2 v_in, 32] -- three launches
+    of jamun_pack_b.  Equal, bit for bit, to pack_b_images / pack_b_column_blocks of conv_k_layout(m0, m1, s_in, v_in)."""
+    from . import ops
+
+    ns = (s_in + 31) // 32
+    map0, map1 = conv_row_maps(s_in, v_in, m0.device)
+    K = m0.shape[0]
+    u0, u1 = s_in + v_in, s_in + 2 * v_in
+    b0 = ops.pack_b(m0.reshape(K * u0, m0.shape[2]), n_stages=K * (ns * 32 + v_in) // 32, n_pad=160, row_map=map0)
+    b1 = ops.pack_b(m1.reshape(K * u1, m1.shape[2]), n_stages=K * 2 * v_in // 32, n_pad=32, row_map=map1) if v_in else None
+    # W_y[u, k'*32 + w] = m1[k', u, w] for the scalar rows u < s_in; 65*32 = 2080 columns in 17 blocks of 128
+    wy = ops.pack_b(m1.reshape(K * u1, m1.shape[2]), n_stages=ns, n_pad=128, k_src=s_in, n_valid=K * m1.shape[2],
+                    n_inner=m1.shape[2], outer_rows=u1, col_blocks=17)
+    return b0, b1, wy

@@ -72,7 +72,11 @@ class Sampler:
                 return iterable
         return iterable
 
-    def sample(self, model, batch_sampler, num_batches: int, init_graphs, continue_chain: bool = False):
+    def sample(self, model, batch_sampler, num_batches: int, init_graphs, continue_chain: bool = False,
+               return_outputs: bool = False):
+        """Mirror of _sampler.py:53-98.  Like the reference it returns nothing: every batch's samples go to the callbacks
+        (``on_after_sample_batch``).  ``return_outputs=True`` (tests, notebooks) keeps each batch's output dict, moved to
+        the host so that long runs do not accumulate trajectories in device memory."""
         self.fabric.launch()
         model = self.fabric.setup(model)
         model.eval()
@@ -81,7 +85,7 @@ class Sampler:
         y_init = model_wrapped.sample_initial_noisy_positions()
         v_init = "gaussian"
         self.fabric.call("on_sample_start", sampler=self)
-        outputs = []
+        outputs = [] if return_outputs else None
         with torch.inference_mode():
             for batch_idx in self.progbar_wrapper(range(num_batches), total=num_batches, desc="Sampling", leave=False):
                 self.global_step = batch_idx
@@ -96,7 +100,8 @@ class Sampler:
                     v_init = "gaussian"
                 self.fabric.call("on_after_sample_batch", sample=samples, sampler=self)
                 self.fabric.log("sampler/global_step", batch_idx)
-                outputs.append(out)
+                if outputs is not None:
+                    outputs.append({k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in out.items()})
         self.fabric.call("on_sample_end", sampler=self)
         return outputs
 

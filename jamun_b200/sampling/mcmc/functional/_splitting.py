@@ -150,6 +150,7 @@ class _WalkWorkspace:
         self.state = torch.zeros(2, dtype=torch.int64, device=device)  # [philox step, trajectory slot]
         self.graphs = {}
         self.graph_launches = {}  # kernels per replay of each captured graph
+        self.graph_refs = {}      # tensors whose raw pointers a captured graph holds through the C ABI (kept alive with it)
 
 
 def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, steps: int,
@@ -229,6 +230,7 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
                                   dev_state=ws.state)
                     ops.walk_advance(ws.state, 1 if save else 0)
                 ws.graphs[(gkey, save)] = g
+                ws.graph_refs[(gkey, save)] = (plan, mu)
                 ws.graph_launches[(gkey, save)] = ops.LAUNCHES - n0  # kernels recorded in the graph = launched per replay
                 ops.LAUNCHES = n0                                     # capture itself launches nothing
             return g

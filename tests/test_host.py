@@ -282,3 +282,21 @@ def test_training_conv_formulation_matches_kernel_model():
         got = train._conv(x, s_in, v_in, src, eid_pad, deg, h, rhat, pk)
         want = KM.conv(x, s_in, v_in, src, dst, h, rhat, pk["m0"], pk["m1"], 0.7, 1.3, N)
         assert torch.allclose(got, want, rtol=1e-10, atol=1e-10)
+
+
+import warnings
+
+
+def test_load_state_dict_warns_on_unknown_tensor_product_entries(models):
+    import jamun_b200 as J
+
+    o32, _, _ = models
+    sd = dict(o32.state_dict())
+    key = next(k for k in sd if "radial_nn.3.weight" in k).replace("radial_nn.3.weight", "tp.mystery")
+    sd[key] = torch.ones(5)
+    sd[key.replace("mystery", "weight")] = torch.zeros(0)  # e3nn's empty external-weight buffer: silently ignored
+    m = J.default_denoiser()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        m.load_state_dict(sd)
+    assert any("tp.mystery" in str(w.message) for w in rec) and not any("tp.weight" in str(w.message) for w in rec)

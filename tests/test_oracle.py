@@ -181,3 +181,99 @@ def test_jump_is_free_for_baoab(models):
     g = np.load(GOLD)
     y, s, x = g["wj_y_traj"], g["wj_score_traj"], g["wj_xhat_traj"]
     assert np.allclose(y + 0.04 ** 2 * s, x, atol=2e-6)
+
+
+# ---- pinning the [DEP-recalled] constants as far as this image allows -------------------------------------------------------
+def _e3nn_so3_clebsch_gordan(l1, l2, l3):
+    """Replay of e3nn 0.5.x `o3._wigner._so3_clebsch_gordan` (the generator of its wigner_3j constants) with exact SU(2)
+    Clebsch-Gordan coefficients from sympy: C = real(Q1 (x) Q2 (x) conj(Q3^T) . CG_su2) / ||.||,
+    Q_l = (-i)^l * (real -> complex change of basis), index order m = -l..l = e3nn's component order."""
+    import numpy as np
+    from sympy.physics.quantum.cg import CG
+
+    def q(l):
+        m_ = np.zeros((2 * l + 1, 2 * l + 1), dtype=np.complex128)
+        for m in range(-l, 0):
+            m_[l + m, l + abs(m)] = 1 / 2 ** 0.5
+            m_[l + m, l - abs(m)] = -1j / 2 ** 0.5
+        m_[l, l] = 1
+        for m in range(1, l + 1):
+            m_[l + m, l + abs(m)] = (-1) ** m / 2 ** 0.5
+            m_[l + m, l - abs(m)] = 1j * (-1) ** m / 2 ** 0.5
+        return (-1j) ** l * m_
+
+    su2 = np.zeros((2 * l1 + 1, 2 * l2 + 1, 2 * l3 + 1))
+    for m1 in range(-l1, l1 + 1):
+        for m2 in range(-l2, l2 + 1):
+            if abs(m1 + m2) <= l3:
+                su2[l1 + m1, l2 + m2, l3 + m1 + m2] = float(CG(l1, m1, l2, m2, l3, m1 + m2).doit())
+    c = np.einsum("ij,kl,mn,ikn->jlm", q(l1), q(l2), np.conj(q(l3).T), su2.astype(np.complex128))
+    assert np.abs(c.imag).max() < 1e-12
+    return c.real / np.linalg.norm(c.real)
+
+
+def test_wigner_3j_matches_sympy_replay_of_e3nn_recipe():
+    """The single convention risk for released checkpoints: sign / index order of wigner_3j(1,1,1)."""
+    pytest.importorskip("sympy")
+    for key in ((0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 1)):
+        ref = torch.from_numpy(_e3nn_so3_clebsch_gordan(*key))
+        assert torch.allclose(O.wigner_3j(*key), ref, atol=1e-14), key
+
+
+def test_normalize2mom_recipe_is_recomputed_not_hard_coded():
+    """c = E[f(z)^2]^(-1/2) over z = randn(1e6, seed-0 CPU generator, fp64) (e3nn.math.normalize2mom), recomputed here."""
+    z = torch.randn(1_000_000, generator=torch.Generator("cpu").manual_seed(0), dtype=torch.float64)
+    for name, f in (("leaky_relu", lambda t: torch.nn.functional.leaky_relu(t, 0.01)), ("sigmoid", torch.sigmoid)):
+        c = f(z).pow(2).mean().pow(-0.5).item()
+        assert O.normalize2mom_const(name) == pytest.approx(c, rel=1e-12)
+
+
+# ---- dormant until e3nn is importable (e.g. a driver-provided baseline/_ref): the oracle's layers against the real ones -----
+def _e3nn():
+    import sys
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    return pytest.importorskip("e3nn")
+
+
+def test_oracle_tensor_product_vs_e3nn():
+    e3nn = _e3nn()
+    from e3nn import o3
+
+    for in1 in ("120x0e+32x1e", "8x0e+8x0e+32x0e+8x0e"):
+        tp_ref = o3.FullyConnectedTensorProduct(in1, "1x0e+1x1e", "152x0e+32x1e", shared_weights=False, internal_weights=False)
+        tp = O.FullyConnectedTP(in1, "1x0e+1x1e", "152x0e+32x1e")
+        assert tp.weight_numel == tp_ref.weight_numel
+        gen = torch.Generator().manual_seed(0)
+        x = torch.randn(5, o3.Irreps(in1).dim, generator=gen)
+        sh = torch.randn(5, 4, generator=gen)
+        w = torch.randn(5, tp.weight_numel, generator=gen)
+        assert torch.allclose(tp(x, sh, w), tp_ref(x, sh, w), rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_linear_gate_radial_sh_vs_e3nn():
+    e3nn = _e3nn()
+    from e3nn import nn as enn
+    from e3nn import o3
+    from e3nn.math import soft_one_hot_linspace
+
+    gen = torch.Generator().manual_seed(1)
+    lin_ref = o3.Linear("120x0e+32x1e", "152x0e+32x1e")
+    lin = O.O3Linear("120x0e+32x1e", "152x0e+32x1e")
+    with torch.no_grad():
+        lin.weight.copy_(lin_ref.weight)
+    x = torch.randn(7, 216, generator=gen)
+    assert torch.allclose(lin(x), lin_ref(x), rtol=1e-5, atol=1e-5)
+    gate_ref = enn.Gate("120x0e", [torch.nn.LeakyReLU(0.01)], "32x0e", [torch.sigmoid], "32x1e")
+    gate = O.Gate("120x0e+32x1e")
+    xg = torch.randn(7, 248, generator=gen)
+    assert torch.allclose(gate(xg), gate_ref(xg), rtol=1e-5, atol=1e-6)
+    d = torch.rand(9, generator=gen) * 0.8
+    rb_ref = soft_one_hot_linspace(d, 0.0, 0.5872643, 32, basis="gaussian", cutoff=True)
+    assert torch.allclose(O.soft_one_hot_linspace_gaussian_cutoff(d, 0.0, 0.5872643, 32), rb_ref, rtol=1e-5, atol=1e-6)
+    v = torch.randn(9, 3, generator=gen)
+    sh_ref = o3.spherical_harmonics(o3.Irreps("1x0e+1x1e"), v, normalize=True, normalization="component")
+    assert torch.allclose(O.spherical_harmonics_l01(v), sh_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(O.wigner_3j(1, 1, 1), o3.wigner_3j(1, 1, 1).double(), atol=1e-7)
