@@ -145,10 +145,11 @@ int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, 
  * weights -> the (hi | lo) stage images jamun_gemm_tf32x3 streams as its B operand, out[col_blocks][n_stages][2][n_pad*32]
  * (UMMA K-major SWIZZLE_128B; hi = w & 0xFFFFE000, lo = w - hi).  Element (k, col) comes from
  * src[(row + (col / n_inner) * outer_rows) * ld + col % n_inner] with row = row_map ? row_map[k] : k; rows outside
- * [0, K_src) and columns >= N_valid are zero.  The operands replaced are the re-laid-out radial_nn.3 weights of
+ * [0, K_src) and columns >= N_valid are zero.  transpose != 0 packs the transposed matrix instead (element (k, col) =
+ * src[row_map ? row_map[col] : col][k], k < N_valid, col < K_src) -- the weight operand of the backward GEMMs.  The operands replaced are the re-laid-out radial_nn.3 weights of
  * e3tools/nn/_conv.py:84-94 and the o3.Linear weights of _interaction.py:23-24. */
 int jamun_pack_b(const float* src, int ld, const int* row_map, int K_src, int n_stages, int N_valid, int n_inner,
-                 int outer_rows, int n_pad, int col_blocks, float* out, jamun_stream_t stream);
+                 int outer_rows, int n_pad, int col_blocks, int transpose, float* out, jamun_stream_t stream);
 
 int jamun_pack_rows(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, float* a, jamun_stream_t stream);
 int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
@@ -250,6 +251,91 @@ int jamun_tensor_product(const float* x1, int d1, const float* x2, int d2, const
 /* e3nn layout <-> SoA layout for `s x0e + v x1e` rows. */
 int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);
 int jamun_layout_from_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training path: backward of the network, loss and alignment.  Reference: model/denoiser.py:87-109,
+ * 219-319 (noise, align, loss, training_step), utils/align.py:9-56 (Kabsch); the backward of e3nn / torch_scatter ops the
+ * reference obtains from autograd is written out here per forward kernel.  All reductions have a fixed order (no atomics).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Y[n, :b] (+)= X[n, :a] . W, W row-major [a, b] (transW: [b, a], i.e. Y = X . W^T).  b <= 160.  rows_dev (optional): device
+ * row count (clamped to rows).  Forward / recompute of the o3.Linear stand-ins (_interaction.py:23-24) and their dX. */
+int jamun_rowmat_mul(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int rows,
+                     const int* rows_dev, int a, int b, int accumulate, jamun_stream_t stream);
+/* dW (+)= X^T . dY (a reduction over nodes or edges in row chunks, partial sums added in ascending order).
+ * scratch: jamun_rowmat_dw_scratch(rows, a, b) floats. */
+long long jamun_rowmat_dw_scratch(int rows, int a, int b);
+int jamun_rowmat_dw(const float* X, int ldx, const float* dY, int ldy, float* dW, int lddw, int transW, int rows,
+                    const int* rows_dev, int a, int b, int accumulate, float* scratch, jamun_stream_t stream);
+/* out[c] (+)= sum_n M[n, c] (rows with flag[n] == flag_value when flag != NULL); fold_v > 0 folds SoA columns
+ * [fold_s | fold_v x3] to per-irrep [fold_s + fold_v].  scratch: jamun_colsum_scratch(rows, cols) floats. */
+long long jamun_colsum_scratch(int rows, int cols);
+int jamun_colsum(const float* M, int ld, int rows, const int* rows_dev, int cols, const unsigned char* flag, int flag_value,
+                 int fold_s, int fold_v, float* out, int accumulate, float* scratch, jamun_stream_t stream);
+
+/* Conv backward (e3tools/nn/_conv.py:93-119): see jamun_b200/csrc/train_conv_bwd.cu for the scheme.
+ * jamun_conv_bwd_scale   g = dOut * inv_deg * (alpha0 | alpha1)                                   [N, 248]
+ * jamun_stage_atb        acc[u, w] = sum_c sum_r A_c[stage][r][u] * B[r][b_col0 + c*b_comp_stride + w] for every stage of a
+ *                        stage-major GEMM operand (dM = A^T . G, dM2 = dY^T . x_s, tail/weight gradients); mode 0 scatters
+ *                        operand slots to output rows (slot_row0/slot_rows: HOST arrays of nslots entries), mode 1 writes
+ *                        the transpose out[(k*out_rows + w)*32 + u].
+ * jamun_conv_bwd_edge    per receiver: dh[e, :64] and dxe[e, :D_in] from dA0 [N, ld0] / dA1 [3][N, ld1] (rows of G . M^T).
+ * jamun_conv_bwd_p2      path 0e(x)1e->1e, source-major: dh[e] += Y_j . dT_e, dY operand [65][rows_pad][32].
+ * jamun_conv_bwd_gather  dx[j] = sum_{e in out(j)} dxe[e] (+ extra[j, :n_extra]), ascending edge id. */
+int jamun_conv_bwd_scale(const float* dout, const float* inv_deg, float alpha0, float alpha1, int N, float* g,
+                         jamun_stream_t stream);
+int jamun_stage_atb(const float* a, long long a_comp_stride, int ncomp, int n_stages, int nslots, int rows, int rows_pad,
+                    const float* b, int ldb, int b_col0, int b_comp_stride, int W, float* out, int mode, int out_rows,
+                    const int* slot_row0, const int* slot_rows, jamun_stream_t stream);
+int jamun_conv_bwd_edge(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                        const float* rhat, const float* dA0, int ld0, const float* dA1, int ld1, long long dA1_comp_stride,
+                        int N, float* dh, float* dxe, jamun_stream_t stream);
+int jamun_conv_bwd_p2(const int* src_rowptr, const int* src_eid, const int* edst, const float* h, const float* rhat,
+                      const float* y, int y_ld, const float* g, int N, int rows_pad, float* dh, float* dy_op,
+                      jamun_stream_t stream);
+int jamun_conv_bwd_gather(const int* src_rowptr, const int* src_eid, const float* dxe, int D, const float* extra,
+                          int extra_ld, int n_extra, int N, float* dx, jamun_stream_t stream);
+
+/* Gate (e3tools/nn/_gate.py:63-64), SoA layout: gated [N, 216] from conv [N, 248] and its backward. */
+int jamun_gate_fwd(const float* conv, float c_act, float c_gate, int N, float* gated, jamun_stream_t stream);
+int jamun_gate_bwd(const float* conv, const float* dgated, float c_act, float c_gate, int N, float* dconv,
+                   jamun_stream_t stream);
+/* Backward of x_new = skip_w ? x_res*w + y*(1-w) : y; x_scaled = x_new*s (arch/e3conv.py:132-133):
+ * dy, dx_res and the per-element products whose column sums are ds (prod_s) and dw (prod_w). */
+int jamun_mix_bwd(const float* dx_new, const float* dx_scaled, const float* y, const float* x_res, const float* skip_w,
+                  const float* s_next, int N, float* dy, float* dx_res, float* prod_s, float* prod_w, jamun_stream_t stream);
+/* Output head backward, elementwise part (e3tools/nn/_mlp.py:37-114): pre [N,32] gate pre-activations, hv [N,3,32]. */
+int jamun_head_bwd(const float* pre, const float* hv, const float* w2, const float* dg, float c_gate, int N, float* dpre,
+                   float* dhv, float* prod_w2, jamun_stream_t stream);
+/* Radial MLP hidden layer backward: dz = dh * SiLU'(rb . w0r + b0eff[ebond])  [cap, 64] (rows < rowptr[N]). */
+int jamun_radial_bwd(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap, const float* w0r,
+                     const float* b0eff, const float* dh, float* dz, jamun_stream_t stream);
+/* Atom embedding backward (model/atom_embedding.py:58-76): dtab_k[r] = scale * sum_{i: idx_k[i] = r} dx0[i, cols_k];
+ * prod [N, D] = dx0 * embedding (column sums = dscale). */
+int jamun_embed_bwd(const int* idx0, const int* idx1, const int* idx2, const int* idx3, const float* tab0, const float* tab1,
+                    const float* tab2, const float* tab3, int dim0, int dim1, int dim2, int dim3, int rows0, int rows1,
+                    int rows2, int rows3, const float* scale, const float* dx0, int N, float* dtab0, float* dtab1,
+                    float* dtab2, float* dtab3, float* prod, jamun_stream_t stream);
+/* NoiseConditionalScaling MLP backward (model/noise_conditioning.py:33-38). */
+int jamun_noise_mlp_bwd(const float* w1, const float* b1, const float* w2, const float* b2, float c_noise, int n,
+                        int apply_sigmoid, const float* dout, float* dw1, float* db1, float* dw2, float* db2,
+                        jamun_stream_t stream);
+/* xhat = center_chain(c_skip*ybar + c_mix*g) (model/denoiser.py:200,213-215; ybar may be NULL).  Its backward with respect
+ * to g is the same map applied to dxhat with ybar = NULL. */
+int jamun_combine_xhat(const float* g, const float* ybar, const int* chain_ptr, int G, float c_skip, float c_mix, int center,
+                       float* xhat, jamun_stream_t stream);
+/* Coordinate loss (model/denoiser.py:251-287) per chain: raw = mean |xhat - x|^2, loss = raw * loss_weight * scale
+ * (scale = 1/c_out^2), rmsd = mean |xhat - x| / (sigma sqrt3); backward: dxhat = dloss * 2 (xhat - x) loss_weight scale / n. */
+int jamun_loss_fwd(const float* xhat, const float* x, const int* chain_ptr, int G, float scale, float sigma,
+                   const float* loss_weight, float* loss, float* raw, float* rmsd, jamun_stream_t stream);
+int jamun_loss_bwd(const float* xhat, const float* x, const int* chain_of, const int* chain_ptr, int N, float scale,
+                   const float* loss_weight, const float* dloss, float* dxhat, jamun_stream_t stream);
+/* Batched Kabsch alignment (utils/align.py:9-56): out = R y + t per chain, R = V diag(1,1,det) U^T from the SVD of
+ * H = sum y_c x_c^T (one-sided Jacobi in fp64).  rot (optional): [G, 9] rotation matrices. */
+int jamun_kabsch_align(const float* y, const float* x, const int* chain_ptr, int G, float* out, float* rot,
+                       jamun_stream_t stream);
+/* out[:, col0 : col0+n] += add[:, :n]. */
+int jamun_add_cols(float* out, int ld, int col0, const float* add, int add_ld, int n, int N, jamun_stream_t stream);
 
 #ifdef __cplusplus
 }

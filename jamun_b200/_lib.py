@@ -37,8 +37,30 @@ _PROTOS = {
     "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
     "jamun_conv_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, c_f, I, F, c_f, c_f], I),
     "jamun_csr_by_source": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
-    "jamun_pack_b": ([c_f, I, c_f, I, I, I, I, I, I, I, c_f, c_f], I),
+    "jamun_pack_b": ([c_f, I, c_f, I, I, I, I, I, I, I, I, c_f, c_f], I),
     "jamun_tensor_product": ([c_f, I, c_f, I, c_f, C.c_longlong, c_f, I, I, I, c_f, c_f], I),
+    "jamun_rowmat_mul": ([c_f, I, c_f, I, I, c_f, I, I, c_f, I, I, I, c_f], I),
+    "jamun_rowmat_dw_scratch": ([I, I, I], C.c_longlong),
+    "jamun_rowmat_dw": ([c_f, I, c_f, I, c_f, I, I, I, c_f, I, I, I, c_f, c_f], I),
+    "jamun_colsum_scratch": ([I, I], C.c_longlong),
+    "jamun_colsum": ([c_f, I, I, c_f, I, c_f, I, I, I, c_f, I, c_f, c_f], I),
+    "jamun_conv_bwd_scale": ([c_f, c_f, F, F, I, c_f, c_f], I),
+    "jamun_stage_atb": ([c_f, C.c_longlong, I, I, I, I, I, c_f, I, I, I, I, c_f, I, I, C.POINTER(I), C.POINTER(I), c_f], I),
+    "jamun_conv_bwd_edge": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, c_f, I, C.c_longlong, I, c_f, c_f, c_f], I),
+    "jamun_conv_bwd_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, I, I, c_f, c_f, c_f], I),
+    "jamun_conv_bwd_gather": ([c_f, c_f, c_f, I, c_f, I, I, I, c_f, c_f], I),
+    "jamun_gate_fwd": ([c_f, F, F, I, c_f, c_f], I),
+    "jamun_gate_bwd": ([c_f, c_f, F, F, I, c_f, c_f], I),
+    "jamun_mix_bwd": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_head_bwd": ([c_f, c_f, c_f, c_f, F, I, c_f, c_f, c_f, c_f], I),
+    "jamun_radial_bwd": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_embed_bwd": ([c_f] * 8 + [I] * 8 + [c_f, c_f, I, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_noise_mlp_bwd": ([c_f, c_f, c_f, c_f, F, I, I, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_combine_xhat": ([c_f, c_f, c_f, I, F, F, I, c_f, c_f], I),
+    "jamun_loss_fwd": ([c_f, c_f, c_f, I, F, F, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_loss_bwd": ([c_f, c_f, c_f, c_f, I, F, c_f, c_f, c_f, c_f], I),
+    "jamun_kabsch_align": ([c_f, c_f, c_f, I, c_f, c_f, c_f], I),
+    "jamun_add_cols": ([c_f, I, I, c_f, I, I, I, c_f], I),
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),

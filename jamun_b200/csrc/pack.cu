@@ -9,11 +9,13 @@ namespace {
 // out[cb][stage][2][n_pad*32]; element (stage, n, kk) of column block cb is W[k = stage*32 + kk][col = cb*n_pad + n] with
 //   source row  = row_map ? row_map[k] : k      (negative or >= K_src: zero)
 //   source elem = src[(row + (col / n_inner) * outer_rows) * ld + (col % n_inner)]      (col >= N_valid: zero)
+// transpose != 0: element (k, col) = src[row_map ? row_map[col] : col][k] for k < N_valid, col < K_src (K_src then counts the
+// entries of row_map, or the source rows), i.e. the image of the transposed (and row-gathered) matrix.
 // n_inner >= N_valid gives a plain [K, N] matrix; n_inner < N_valid addresses a [outer][K][n_inner] tensor whose leading index
 // is spread along the columns (the per-node transform W_y[u, k'*32 + w] = m1[k', u, w]).
 __global__ void __launch_bounds__(256)
 pack_b_kernel(const float* __restrict__ src, int ld, const int* __restrict__ row_map, int K_src, int n_stages, int N_valid,
-              int n_inner, int outer_rows, int n_pad, int col_blocks, float* __restrict__ out) {
+              int n_inner, int outer_rows, int n_pad, int col_blocks, int transpose, float* __restrict__ out) {
     const long long per_stage = (long long)n_pad * 32;
     const long long total = (long long)col_blocks * n_stages * per_stage;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -26,11 +28,19 @@ pack_b_kernel(const float* __restrict__ src, int ld, const int* __restrict__ row
         const int cb = (int)(q / n_stages);
         const int k = stage * 32 + kk;
         const int col = cb * n_pad + n;
-        int row = row_map ? row_map[k] : k;
         float v = 0.f;
-        if (row >= 0 && row < K_src && col < N_valid) {
-            const int o = col / n_inner, ci = col - o * n_inner;
-            v = src[((size_t)row + (size_t)o * outer_rows) * ld + ci];
+        if (transpose) {
+            // the image of the transposed matrix: element (k, col) = src[row(col)][k]   (backward GEMMs: dA = G . M^T)
+            if (k < N_valid) {
+                const int row = row_map ? (col < K_src ? row_map[col] : -1) : col;
+                if (row >= 0 && (row_map || row < K_src)) v = src[(size_t)row * ld + k];
+            }
+        } else {
+            const int row = row_map ? row_map[k] : k;
+            if (row >= 0 && row < K_src && col < N_valid) {
+                const int o = col / n_inner, ci = col - o * n_inner;
+                v = src[((size_t)row + (size_t)o * outer_rows) * ld + ci];
+            }
         }
         const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         const int fidx = (n >> 3) * 256 + (n & 7) * 32 + (((kk >> 2) ^ (n & 7)) << 2) + (kk & 3);  // float index in the image
@@ -43,15 +53,15 @@ pack_b_kernel(const float* __restrict__ src, int ld, const int* __restrict__ row
 }  // namespace
 
 extern "C" int jamun_pack_b(const float* src, int ld, const int* row_map, int K_src, int n_stages, int N_valid, int n_inner,
-                            int outer_rows, int n_pad, int col_blocks, float* out, jamun_stream_t stream) {
+                            int outer_rows, int n_pad, int col_blocks, int transpose, float* out, jamun_stream_t stream) {
     JB_CHECK_ARG(src && out, "null argument");
     JB_CHECK_ARG(n_stages >= 1 && n_pad >= 16 && n_pad % 8 == 0 && col_blocks >= 1 && n_inner >= 1 && ld >= 1, "bad shape");
-    JB_CHECK_ARG(row_map || K_src <= n_stages * 32, "K_src exceeds the padded K extent");
+    JB_CHECK_ARG(transpose || row_map || K_src <= n_stages * 32, "K_src exceeds the padded K extent");
     const long long total = (long long)col_blocks * n_stages * n_pad * 32;
     long long blocks = (total + 255) / 256;
     if (blocks > jb::kNumSMs * 16) blocks = jb::kNumSMs * 16;
     pack_b_kernel<<<(int)blocks, 256, 0, jb::as_stream(stream)>>>(src, ld, row_map, K_src, n_stages, N_valid, n_inner, outer_rows,
-                                                                   n_pad, col_blocks, out);
+                                                                   n_pad, col_blocks, transpose, out);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

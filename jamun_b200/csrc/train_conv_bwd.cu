@@ -1,0 +1,362 @@
+// Backward of the equivariant convolution (Conv.forward, /root/reference/src/jamun/e3tools/nn/_conv.py:93-119) in the
+// aggregate-then-transform formulation of the forward kernels:
+//
+//   forward   A_i = sum_{e->i} h'_e (x) f_e,  out_i = G-scale_i * A_i . M        (+ path 0e(x)1e->1e via Y = x_s . M2)
+//   backward  G_i    = alpha / deg_i * dOut_i                                      jamun_conv_bwd_scale
+//             dM     = sum_i A_i^T (x) G_i          (A recomputed by the builder)  jamun_stage_atb  ("A^T . B" over the nodes)
+//             dA_i   = M . G_i                                                     jamun_gemm_tf32x3 (column blocks, tcgen05)
+//             dh'_e  = <dA_i, f_e>,  df_e = h'_e . dA_i   (per edge, receiver CTA) jamun_conv_bwd_edge
+//             path 2: dT_e = rhat_e . G1_i,  dY_j = sum_{e from j} h'_e (x) dT_e,  dh'_e += Y_j . dT_e     jamun_conv_bwd_p2
+//                     dM2 = x_s^T . dY (jamun_stage_atb),  dx_s += dY . M2^T (jamun_gemm_tf32x3)
+//             dx_j   = sum_{e from j} J_e^T df_e  (+ dx_s)  -- source-major, out-edge lists sorted: deterministic
+//                                                                                  jamun_conv_bwd_gather
+// Every reduction has a fixed order; no atomics.
+#include "common.cuh"
+
+namespace {
+using namespace jb;
+
+constexpr float kInvSqrt3 = 0.57735026918962576451f;
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+
+// ---- G = alpha * dOut / deg ---------------------------------------------------------------------------------------------------
+__global__ void conv_bwd_scale_kernel(const float* __restrict__ dout, const float* __restrict__ inv_deg, float a0, float a1, int N,
+                                      float* __restrict__ g) {
+    const size_t total = (size_t)N * JAMUN_GATE_IN;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / JAMUN_GATE_IN), c = (int)(t % JAMUN_GATE_IN);
+        g[t] = dout[t] * inv_deg[i] * (c < JAMUN_S + JAMUN_V ? a0 : a1);
+    }
+}
+
+// ---- stage-major operand, transposed, times a row-major matrix ----------------------------------------------------------------
+// acc[u, w] = sum_c sum_{r < rows} A_c[stage][r][u] * B[r][b_col0 + c*b_comp_stride + w]     (u < 32, w < W <= 160)
+// A: jamun_gemm_tf32x3's A layout ([stage][rows_pad][32], 16-byte chunks XOR-swizzled with row & 7), component c at
+// a + c*a_comp_stride.  Output element (stage = k*nslots + slot, u, w):
+//   mode 0:  row = slot_row0[slot] + u (skipped if >= slot_row0[slot] + slot_rows[slot]);  out[(k*out_rows + row)*W + w]
+//   mode 1:  transposed (the operand's 32 columns are the output's minor index):           out[(k*out_rows + w)*32 + u]
+struct AtbParams {
+    const float* a;
+    long long a_comp_stride;
+    int ncomp, rows, rows_pad, nslots;
+    const float* b;
+    int ldb, b_col0, b_comp_stride, W;
+    float* out;
+    int mode, out_rows;
+    int slot_row0[8], slot_rows[8];
+};
+
+__global__ void __launch_bounds__(256) stage_atb_kernel(const AtbParams P) {
+    __shared__ __align__(16) float As[32][32];
+    __shared__ float Bs[32][161];
+    const int stage = blockIdx.x;
+    const int u4 = threadIdx.x & 7, wg = threadIdx.x >> 3;  // 4 operand columns x (up to 5) matrix columns wg + 32 q
+    float acc[4][5];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) acc[i][q] = 0.f;
+    for (int c = 0; c < P.ncomp; ++c) {
+        const float* a = P.a + (size_t)c * P.a_comp_stride + (size_t)stage * P.rows_pad * 32;
+        const int bc = P.b_col0 + c * P.b_comp_stride;
+        for (int r0 = 0; r0 < P.rows; r0 += 32) {
+            // operand tile: 32 rows x 128 B, contiguous; rows beyond `rows` hold stale data -> masked
+            {
+                const int rr = threadIdx.x >> 3, ch = threadIdx.x & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + rr < P.rows) v = *reinterpret_cast<const float4*>(a + (size_t)(r0 + rr) * 32 + 4 * ch);
+                *reinterpret_cast<float4*>(&As[rr][4 * ch]) = v;  // kept swizzled: un-swizzled on read
+            }
+            for (int t = threadIdx.x; t < 32 * P.W; t += 256) {
+                const int rr = t / P.W, w = t - rr * P.W;
+                Bs[rr][w] = (r0 + rr < P.rows) ? P.b[(size_t)(r0 + rr) * P.ldb + bc + w] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                const float4 av = *reinterpret_cast<const float4*>(&As[rr][4 * (u4 ^ ((r0 + rr) & 7))]);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float bv = Bs[rr][wg + 32 * q];
+                    acc[0][q] = fmaf(av.x, bv, acc[0][q]);
+                    acc[1][q] = fmaf(av.y, bv, acc[1][q]);
+                    acc[2][q] = fmaf(av.z, bv, acc[2][q]);
+                    acc[3][q] = fmaf(av.w, bv, acc[3][q]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int k = stage / P.nslots, slot = stage - k * P.nslots;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int u = 4 * u4 + i;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int w = wg + 32 * q;
+            if (w >= P.W) continue;
+            if (P.mode == 0) {
+                if (u < P.slot_rows[slot]) P.out[((size_t)k * P.out_rows + P.slot_row0[slot] + u) * P.W + w] = acc[i][q];
+            } else {
+                P.out[((size_t)k * P.out_rows + w) * 32 + u] = acc[i][q];
+            }
+        }
+    }
+}
+
+// ---- per-edge backward of the aggregated paths ---------------------------------------------------------------------------------
+// One CTA per receiver i.  dA0_i [65][NSL0*32] and dA1_i[c] [65][64] (rows of the column-block GEMM outputs) are staged in shared
+// memory once and reused by all in-edges of i:
+//   df0[u'] = sum_k' h'[k'] dA0[k'][u']      df1[c][u'] = sum_k' h'[k'] dA1[c][k'][u']        (threads over u')
+//   dh[k']  = sum_u' f0[u'] dA0[k'][u'] + sum_c sum_u' f1[c][u'] dA1[c][k'][u']   (k' < 64)   (warps over k', lanes over u')
+//   dxe[e]  = J_e^T df  (row of the per-edge input gradient, SoA layout; summed per source by jamun_conv_bwd_gather)
+template <int S_IN, int V_IN>
+__global__ void __launch_bounds__(384)
+conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
+                     const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ dA0, int ld0,
+                     const float* __restrict__ dA1, int ld1, long long dA1_comp_stride, int N, float* __restrict__ dh,
+                     float* __restrict__ dxe) {
+    constexpr int D_IN = S_IN + 3 * V_IN;
+    constexpr int NS = (S_IN + 31) / 32;
+    constexpr int W0 = (NS + (V_IN > 0 ? 1 : 0)) * 32;  // padded 0e feature columns
+    constexpr int W1 = V_IN > 0 ? 64 : 0;
+    constexpr int NF = W0 + 3 * W1;
+    extern __shared__ __align__(16) float sm[];
+    float* sA0 = sm;                       // [65][W0]
+    float* sA1 = sA0 + 65 * W0;            // [3][65][W1]
+    float* sf = sA1 + 3 * 65 * W1;         // [NF] features of the current edge
+    float* sdf = sf + NF;                  // [NF] their gradients
+    float* sh = sdf + NF;                  // [65] h'
+    const int i = blockIdx.x;
+    if (i >= N) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e0 = rowptr[i], e1 = rowptr[i + 1];
+    if (e0 == e1) return;
+    for (int t = tid; t < 65 * W0; t += 384) sA0[t] = dA0[(size_t)i * ld0 + t];
+    if (V_IN > 0)
+        for (int c = 0; c < 3; ++c)
+            for (int t = tid; t < 65 * W1; t += 384) sA1[c * 65 * W1 + t] = dA1[(size_t)c * dA1_comp_stride + (size_t)i * ld1 + t];
+    for (int e = e0; e < e1; ++e) {
+        __syncthreads();  // previous edge done with sf / sdf / sh (and the dA tiles are loaded)
+        const int j = col[e];
+        const float* xr = x + (size_t)j * D_IN;
+        const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+        for (int t = tid; t < NS * 32; t += 384) sf[t] = t < S_IN ? xr[t] : 0.f;
+        if (V_IN > 0 && tid < V_IN) {
+            const float vx = xr[S_IN + tid], vy = xr[S_IN + V_IN + tid], vz = xr[S_IN + 2 * V_IN + tid];
+            sf[NS * 32 + tid] = vx * rh.x + vy * rh.y + vz * rh.z;
+            sf[W0 + 0 * 64 + tid] = vx * kInvSqrt3;
+            sf[W0 + 1 * 64 + tid] = vy * kInvSqrt3;
+            sf[W0 + 2 * 64 + tid] = vz * kInvSqrt3;
+            sf[W0 + 0 * 64 + 32 + tid] = (vy * rh.z - vz * rh.y) * kInvSqrt2;
+            sf[W0 + 1 * 64 + 32 + tid] = (vz * rh.x - vx * rh.z) * kInvSqrt2;
+            sf[W0 + 2 * 64 + 32 + tid] = (vx * rh.y - vy * rh.x) * kInvSqrt2;
+        }
+        if (tid >= 320 && tid < 384) sh[tid - 320] = h[(size_t)e * JAMUN_EDGE_HID + tid - 320];
+        if (tid == 319) sh[64] = 1.f;
+        __syncthreads();
+        // df: one feature column per thread
+        if (tid < NF) {
+            float acc = 0.f;
+            if (tid < W0) {
+#pragma unroll 5
+                for (int k = 0; k < 65; ++k) acc = fmaf(sh[k], sA0[k * W0 + tid], acc);
+            } else {
+                const int c = (tid - W0) / 64, u = (tid - W0) % 64;
+                const float* A = sA1 + c * 65 * W1;
+#pragma unroll 5
+                for (int k = 0; k < 65; ++k) acc = fmaf(sh[k], A[k * W1 + u], acc);
+            }
+            sdf[tid] = acc;
+        }
+        // dh: warp per channel
+        for (int k = warp; k < 64; k += 12) {
+            float acc = 0.f;
+            for (int u = lane; u < W0; u += 32) acc = fmaf(sf[u], sA0[k * W0 + u], acc);
+            if (V_IN > 0)
+                for (int c = 0; c < 3; ++c) {
+                    const float* A = sA1 + (c * 65 + k) * W1;
+                    acc = fmaf(sf[W0 + c * 64 + lane], A[lane], acc);
+                    acc = fmaf(sf[W0 + c * 64 + 32 + lane], A[32 + lane], acc);
+                }
+            acc = warp_sum(acc);
+            if (lane == 0) dh[(size_t)e * JAMUN_EDGE_HID + k] = acc;
+        }
+        __syncthreads();
+        // dxe = J^T df
+        float* o = dxe + (size_t)e * D_IN;
+        for (int t = tid; t < S_IN; t += 384) o[t] = sdf[t];
+        if (V_IN > 0 && tid < V_IN) {
+            const float dd = sdf[NS * 32 + tid];
+            const float cx = sdf[W0 + 0 * 64 + 32 + tid], cy = sdf[W0 + 1 * 64 + 32 + tid], cz = sdf[W0 + 2 * 64 + 32 + tid];
+            // cross = x_v x rhat  =>  d x_v = rhat x d cross
+            o[S_IN + tid] = dd * rh.x + sdf[W0 + 0 * 64 + tid] * kInvSqrt3 + (rh.y * cz - rh.z * cy) * kInvSqrt2;
+            o[S_IN + V_IN + tid] = dd * rh.y + sdf[W0 + 1 * 64 + tid] * kInvSqrt3 + (rh.z * cx - rh.x * cz) * kInvSqrt2;
+            o[S_IN + 2 * V_IN + tid] = dd * rh.z + sdf[W0 + 2 * 64 + tid] * kInvSqrt3 + (rh.x * cy - rh.y * cx) * kInvSqrt2;
+        }
+    }
+}
+
+// ---- path 0e(x)1e->1e, source-major ---------------------------------------------------------------------------------------------
+// One warp per source j (lane = output channel w): Y_j [65][32] in registers; for every out-edge e (receiver i):
+//   dT[w] = sum_c rhat_e[c] G1_i[c][w];  dY[k'][w] += h'_e[k'] dT[w];  dh_e[k'] += sum_w Y[k'][w] dT[w]   (k' < 64)
+// dY_j is written as a stage-major, chunk-swizzled GEMM operand ([65][rows_pad][32]).
+constexpr int kP2Warps = 4;
+__global__ void __launch_bounds__(32 * kP2Warps)
+conv_bwd_p2_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ src_eid, const int* __restrict__ edst,
+                   const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int y_ld,
+                   const float* __restrict__ g, int N, int rows_pad, float* __restrict__ dh, float* __restrict__ dy_op) {
+    __shared__ float prod[kP2Warps][64][33];
+    __shared__ float hs[kP2Warps][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int j = blockIdx.x * kP2Warps + wib;
+    if (j >= N) return;
+    const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
+    float yr[65], dy[65];
+#pragma unroll
+    for (int k = 0; k < 65; ++k) {
+        yr[k] = y[(size_t)j * y_ld + k * JAMUN_V + lane];
+        dy[k] = 0.f;
+    }
+    for (int q = s0; q < s1; ++q) {
+        const int e = src_eid[q];
+        const int i = edst[e];
+        const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+        const float* gi = g + (size_t)i * JAMUN_GATE_IN + JAMUN_S + JAMUN_V;
+        const float dT = rh.x * gi[lane] + rh.y * gi[JAMUN_V + lane] + rh.z * gi[2 * JAMUN_V + lane];
+        hs[wib][lane] = h[(size_t)e * JAMUN_EDGE_HID + lane];
+        hs[wib][32 + lane] = h[(size_t)e * JAMUN_EDGE_HID + 32 + lane];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            dy[k] = fmaf(hs[wib][k], dT, dy[k]);
+            prod[wib][k][lane] = yr[k] * dT;
+        }
+        dy[64] += dT;
+        __syncwarp();
+        // lane sums rows lane and lane + 32 of the product tile (ascending w: fixed order)
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int w = 0; w < 32; ++w) {
+            a0 += prod[wib][lane][w];
+            a1 += prod[wib][32 + lane][w];
+        }
+        float* dhe = dh + (size_t)e * JAMUN_EDGE_HID;
+        dhe[lane] += a0;
+        dhe[32 + lane] += a1;
+        __syncwarp();
+    }
+    const int pos = (((lane >> 2) ^ (j & 7)) << 2) | (lane & 3);
+#pragma unroll
+    for (int k = 0; k < 65; ++k) dy_op[((size_t)k * rows_pad + j) * 32 + pos] = dy[k];
+}
+
+// ---- dx_j = sum over the out-edges of j (ascending edge id) of dxe[e]  (+ extra[j, :n_extra]) ----------------------------------
+__global__ void __launch_bounds__(256)
+conv_bwd_gather_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ src_eid, const float* __restrict__ dxe, int D,
+                       const float* __restrict__ extra, int extra_ld, int n_extra, int N, float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= N) return;
+    const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
+    for (int c0 = 0; c0 < D; c0 += 32) {
+        const int c = c0 + lane;
+        if (c >= D) break;
+        float acc = (extra && c < n_extra) ? extra[(size_t)j * extra_ld + c] : 0.f;
+        for (int q = s0; q < s1; ++q) acc += dxe[(size_t)src_eid[q] * D + c];
+        dx[(size_t)j * D + c] = acc;
+    }
+}
+
+template <int S_IN, int V_IN>
+int launch_edge(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, const float* dA0, int ld0,
+                const float* dA1, int ld1, long long comp, int N, float* dh, float* dxe, cudaStream_t s) {
+    constexpr int NS = (S_IN + 31) / 32;
+    constexpr int W0 = (NS + (V_IN > 0 ? 1 : 0)) * 32, W1 = V_IN > 0 ? 64 : 0, NF = W0 + 3 * W1;
+    constexpr size_t smem = (size_t)(65 * W0 + 3 * 65 * W1 + 2 * NF + 65 + 3) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_bwd_edge_kernel<S_IN, V_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            jb::set_error("jamun_conv_bwd_edge: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return JAMUN_ECUDA;
+        }
+        attr_set = true;
+    }
+    conv_bwd_edge_kernel<S_IN, V_IN><<<N, 384, smem, s>>>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, comp, N, dh, dxe);
+    return JAMUN_OK;
+}
+
+}  // namespace
+
+extern "C" int jamun_conv_bwd_scale(const float* dout, const float* inv_deg, float alpha0, float alpha1, int N, float* g,
+                                    jamun_stream_t stream) {
+    JB_CHECK_ARG(dout && inv_deg && g, "null argument");
+    if (N == 0) return JAMUN_OK;
+    size_t total = (size_t)N * JAMUN_GATE_IN;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > jb::kNumSMs * 16) blocks = jb::kNumSMs * 16;
+    conv_bwd_scale_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(dout, inv_deg, alpha0, alpha1, N, g);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_stage_atb(const float* a, long long a_comp_stride, int ncomp, int n_stages, int nslots, int rows, int rows_pad,
+                               const float* b, int ldb, int b_col0, int b_comp_stride, int W, float* out, int mode, int out_rows,
+                               const int* slot_row0, const int* slot_rows, jamun_stream_t stream) {
+    JB_CHECK_ARG(a && b && out, "null argument");
+    JB_CHECK_ARG(W >= 1 && W <= 160 && nslots >= 1 && nslots <= 8 && n_stages % nslots == 0 && ncomp >= 1, "bad shape");
+    JB_CHECK_ARG(mode == 1 || (slot_row0 && slot_rows), "mode 0 needs the slot tables (host pointers)");
+    if (n_stages == 0) return JAMUN_OK;
+    AtbParams P{};
+    P.a = a, P.a_comp_stride = a_comp_stride, P.ncomp = ncomp, P.rows = rows, P.rows_pad = rows_pad, P.nslots = nslots;
+    P.b = b, P.ldb = ldb, P.b_col0 = b_col0, P.b_comp_stride = b_comp_stride, P.W = W;
+    P.out = out, P.mode = mode, P.out_rows = out_rows;
+    for (int s = 0; s < nslots && mode == 0; ++s) P.slot_row0[s] = slot_row0[s], P.slot_rows[s] = slot_rows[s];
+    stage_atb_kernel<<<n_stages, 256, 0, jb::as_stream(stream)>>>(P);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_conv_bwd_edge(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                                   const float* rhat, const float* dA0, int ld0, const float* dA1, int ld1,
+                                   long long dA1_comp_stride, int N, float* dh, float* dxe, jamun_stream_t stream) {
+    JB_CHECK_ARG(x && rowptr && col && h && rhat && dA0 && dh && dxe, "null argument");
+    if (N == 0) return JAMUN_OK;
+    cudaStream_t s = jb::as_stream(stream);
+    int rc;
+    if (s_in == JAMUN_S && v_in == JAMUN_V) {
+        JB_CHECK_ARG(dA1, "dA1 required for vector inputs");
+        rc = launch_edge<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, dA1_comp_stride, N, dh, dxe, s);
+    } else if (s_in == JAMUN_S0 && v_in == 0) {
+        rc = launch_edge<JAMUN_S0, 0>(x, rowptr, col, h, rhat, dA0, ld0, nullptr, 0, 0, N, dh, dxe, s);
+    } else {
+        jb::set_error("jamun_conv_bwd_edge: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
+        return JAMUN_EINVAL;
+    }
+    if (rc != JAMUN_OK) return rc;
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_conv_bwd_p2(const int* src_rowptr, const int* src_eid, const int* edst, const float* h, const float* rhat,
+                                 const float* y, int y_ld, const float* g, int N, int rows_pad, float* dh, float* dy_op,
+                                 jamun_stream_t stream) {
+    JB_CHECK_ARG(src_rowptr && src_eid && edst && h && rhat && y && g && dh && dy_op, "null argument");
+    JB_CHECK_ARG(N <= rows_pad, "N exceeds rows_pad");
+    if (N == 0) return JAMUN_OK;
+    conv_bwd_p2_kernel<<<(N + kP2Warps - 1) / kP2Warps, 32 * kP2Warps, 0, jb::as_stream(stream)>>>(src_rowptr, src_eid, edst, h, rhat, y,
+                                                                                                   y_ld, g, N, rows_pad, dh, dy_op);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_conv_bwd_gather(const int* src_rowptr, const int* src_eid, const float* dxe, int D, const float* extra,
+                                     int extra_ld, int n_extra, int N, float* dx, jamun_stream_t stream) {
+    JB_CHECK_ARG(src_rowptr && src_eid && dxe && dx, "null argument");
+    if (N == 0) return JAMUN_OK;
+    const int blocks = (int)(((size_t)N * 32 + 255) / 256);
+    conv_bwd_gather_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(src_rowptr, src_eid, dxe, D, extra, extra_ld, n_extra, N, dx);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}

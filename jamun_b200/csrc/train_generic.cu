@@ -1,0 +1,193 @@
+// Building blocks of the training (backward) path that are not conv-shaped: small dense products over the node / edge
+// dimension and deterministic column reductions.  All FP32 on the CUDA cores: together they are < 2 % of a training step's
+// FLOPs (35 kFLOP per node for the self-interaction / skip Linears against 3.8 MFLOP for one conv contraction).
+//
+//   jamun_rowmat_mul  Y[n, :b] (+)= X[n, :a] . W          (forward / recompute of the o3.Linear stand-ins; dX = dY . W^T)
+//   jamun_rowmat_dw   dW (+)= X^T . dY                    (weight gradients: a reduction over nodes or edges)
+//   jamun_colsum      out[c] (+)= sum_n M[n, c]           (bias-like gradients, per-irrep scale gradients)
+// Reductions over rows run in a fixed order (row chunks -> partial sums -> ascending final sum): results are bit-reproducible.
+// `rows_dev` (optional) is a device-side row count (e.g. rowptr + N for the live edge count) clamped to `rows`.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxB = 160;
+
+// ---- Y = X . W (transW: W stored [b, a]) ------------------------------------------------------------------------------------
+// One CTA = 32 rows.  thread t: row t >> 3, columns (t & 7) + 8 q.  K is staged through shared memory in slabs of 32.
+__global__ void __launch_bounds__(256)
+rowmat_mul_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, int transW, float* __restrict__ Y,
+                  int ldy, int rows, const int* __restrict__ rows_dev, int a, int b, int accumulate) {
+    __shared__ float Xs[32][33];
+    __shared__ float Ws[32][kMaxB + 1];
+    if (rows_dev) rows = min(rows, *rows_dev);
+    const int row0 = blockIdx.x * 32;
+    if (row0 >= rows) return;
+    const int r = threadIdx.x >> 3, cg = threadIdx.x & 7;
+    float acc[kMaxB / 8];
+#pragma unroll
+    for (int q = 0; q < kMaxB / 8; ++q) acc[q] = 0.f;
+    for (int k0 = 0; k0 < a; k0 += 32) {
+        for (int t = threadIdx.x; t < 32 * 32; t += 256) {
+            const int rr = t >> 5, kk = t & 31;
+            Xs[rr][kk] = (row0 + rr < rows && k0 + kk < a) ? X[(size_t)(row0 + rr) * ldx + k0 + kk] : 0.f;
+        }
+        if (!transW) {
+            for (int t = threadIdx.x; t < 32 * b; t += 256) {
+                const int kk = t / b, j = t - kk * b;
+                Ws[kk][j] = (k0 + kk < a) ? W[(size_t)(k0 + kk) * ldw + j] : 0.f;
+            }
+        } else {
+            for (int t = threadIdx.x; t < 32 * b; t += 256) {
+                const int j = t >> 5, kk = t & 31;
+                Ws[kk][j] = (k0 + kk < a) ? W[(size_t)j * ldw + k0 + kk] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < 32; ++kk) {
+            const float x = Xs[r][kk];
+#pragma unroll
+            for (int q = 0; q < kMaxB / 8; ++q)
+                if (cg + 8 * q < b) acc[q] = fmaf(x, Ws[kk][cg + 8 * q], acc[q]);
+        }
+        __syncthreads();
+    }
+    if (row0 + r < rows) {
+        float* y = Y + (size_t)(row0 + r) * ldy;
+#pragma unroll
+        for (int q = 0; q < kMaxB / 8; ++q)
+            if (cg + 8 * q < b) y[cg + 8 * q] = accumulate ? y[cg + 8 * q] + acc[q] : acc[q];
+    }
+}
+
+// ---- dW = X^T . dY over a chunk of rows -------------------------------------------------------------------------------------
+// grid (ceil(a/16), ceil(b/16), splits): thread (ty, tx) owns dW[k0+ty][j0+tx] for rows [chunk z); partial[z][a][b].
+__global__ void __launch_bounds__(256)
+rowmat_dw_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, float* __restrict__ partial, int rows,
+                 const int* __restrict__ rows_dev, int a, int b, int rows_per_split) {
+    __shared__ float Xs[64][17], Ys[64][17];
+    if (rows_dev) rows = min(rows, *rows_dev);
+    const int k0 = blockIdx.x * 16, j0 = blockIdx.y * 16;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int n_begin = blockIdx.z * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
+    float acc = 0.f;
+    for (int n0 = n_begin; n0 < n_end; n0 += 64) {
+        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+            const int rr = t >> 4, cc = t & 15;
+            const bool ok = n0 + rr < n_end;
+            Xs[rr][cc] = (ok && k0 + cc < a) ? X[(size_t)(n0 + rr) * ldx + k0 + cc] : 0.f;
+            Ys[rr][cc] = (ok && j0 + cc < b) ? dY[(size_t)(n0 + rr) * ldy + j0 + cc] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int rr = 0; rr < 64; ++rr) acc = fmaf(Xs[rr][ty], Ys[rr][tx], acc);
+        __syncthreads();
+    }
+    if (k0 + ty < a && j0 + tx < b) partial[((size_t)blockIdx.z * a + k0 + ty) * b + j0 + tx] = acc;
+}
+
+__global__ void rowmat_dw_reduce_kernel(const float* __restrict__ partial, int splits, int a, int b, float* __restrict__ dW, int lddw,
+                                        int transW, int accumulate) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a * b) return;
+    const int k = t / b, j = t - k * b;
+    float acc = 0.f;
+    for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * a * b + t];
+    float* o = dW + (transW ? (size_t)j * lddw + k : (size_t)k * lddw + j);
+    *o = accumulate ? *o + acc : acc;
+}
+
+// ---- column sums ---------------------------------------------------------------------------------------------------------------
+// grid (ceil(cols/32), splits); block (32 columns x 8 row lanes).  flag != null: only rows with flag[n] == flag_value.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ M, int ld, int rows, const int* __restrict__ rows_dev, int cols,
+              const unsigned char* __restrict__ flag, int flag_value, float* __restrict__ partial, int rows_per_split) {
+    __shared__ float red[8][33];
+    if (rows_dev) rows = min(rows, *rows_dev);
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    const int n_begin = blockIdx.y * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
+    float acc = 0.f;
+    if (c < cols)
+        for (int n = n_begin + ry; n < n_end; n += 8)
+            if (!flag || flag[n] == flag_value) acc += M[(size_t)n * ld + c];
+    red[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x];
+        partial[(size_t)blockIdx.y * cols + c] = s;
+    }
+}
+
+// out[fold(c)] (+)= sum_z partial[z][c]; fold: SoA rows [S scalars | V x | V y | V z] -> per-irrep [S + V] (fold_v > 0)
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int splits, int cols, int fold_s, int fold_v,
+                                     float* __restrict__ out, int accumulate) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_out = fold_v > 0 ? fold_s + fold_v : cols;
+    if (o >= n_out) return;
+    float acc = 0.f;
+    const int reps = (fold_v > 0 && o >= fold_s) ? (cols - fold_s) / fold_v : 1;
+    for (int q = 0; q < reps; ++q) {
+        const int c = o + q * fold_v;
+        for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * cols + c];
+    }
+    out[o] = accumulate ? out[o] + acc : acc;
+}
+
+inline int pick_splits(int rows, int per_min, int max_splits) {
+    int s = (rows + per_min - 1) / per_min;
+    if (s < 1) s = 1;
+    if (s > max_splits) s = max_splits;
+    return s;
+}
+
+}  // namespace
+
+extern "C" int jamun_rowmat_mul(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int rows,
+                                const int* rows_dev, int a, int b, int accumulate, jamun_stream_t stream) {
+    JB_CHECK_ARG(X && W && Y, "null argument");
+    JB_CHECK_ARG(a >= 1 && b >= 1 && b <= kMaxB, "b must be in [1, 160]");
+    if (rows == 0) return JAMUN_OK;
+    rowmat_mul_kernel<<<(rows + 31) / 32, 256, 0, jb::as_stream(stream)>>>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b,
+                                                                           accumulate);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+// scratch: >= jamun_rowmat_dw_scratch(rows, a, b) floats
+extern "C" long long jamun_rowmat_dw_scratch(int rows, int a, int b) { return (long long)pick_splits(rows, 2048, 128) * a * b; }
+
+extern "C" int jamun_rowmat_dw(const float* X, int ldx, const float* dY, int ldy, float* dW, int lddw, int transW, int rows,
+                               const int* rows_dev, int a, int b, int accumulate, float* scratch, jamun_stream_t stream) {
+    JB_CHECK_ARG(X && dY && dW && scratch, "null argument");
+    JB_CHECK_ARG(a >= 1 && b >= 1, "bad shape");
+    cudaStream_t s = jb::as_stream(stream);
+    const int splits = pick_splits(rows, 2048, 128);
+    const int per = rows > 0 ? (rows + splits - 1) / splits : 1;
+    if (rows > 0)
+        rowmat_dw_kernel<<<dim3((a + 15) / 16, (b + 15) / 16, splits), 256, 0, s>>>(X, ldx, dY, ldy, scratch, rows, rows_dev, a, b,
+                                                                                    per);
+    rowmat_dw_reduce_kernel<<<(a * b + 255) / 256, 256, 0, s>>>(scratch, rows > 0 ? splits : 0, a, b, dW, lddw, transW, accumulate);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" long long jamun_colsum_scratch(int rows, int cols) { return (long long)pick_splits(rows, 1024, 256) * cols; }
+
+extern "C" int jamun_colsum(const float* M, int ld, int rows, const int* rows_dev, int cols, const unsigned char* flag,
+                            int flag_value, int fold_s, int fold_v, float* out, int accumulate, float* scratch,
+                            jamun_stream_t stream) {
+    JB_CHECK_ARG(M && out && scratch && cols >= 1, "bad argument");
+    JB_CHECK_ARG(fold_v == 0 || (cols > fold_s && (cols - fold_s) % fold_v == 0), "fold does not divide the columns");
+    cudaStream_t s = jb::as_stream(stream);
+    const int splits = pick_splits(rows, 1024, 256);
+    const int per = rows > 0 ? (rows + splits - 1) / splits : 1;
+    if (rows > 0)
+        colsum_kernel<<<dim3((cols + 31) / 32, splits), 256, 0, s>>>(M, ld, rows, rows_dev, cols, flag, flag_value, scratch, per);
+    const int n_out = fold_v > 0 ? fold_s + fold_v : cols;
+    colsum_reduce_kernel<<<(n_out + 127) / 128, 128, 0, s>>>(scratch, rows > 0 ? splits : 0, cols, fold_s, fold_v, out, accumulate);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}

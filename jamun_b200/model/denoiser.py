@@ -257,30 +257,28 @@ class Denoiser(_Base):
         return xhat, y
 
     def xhat_with_grad(self, y, sigma: Union[float, torch.Tensor]):
-        """xhat with an autograd graph to the parameters (training; library path -- see jamun_b200/train.py)."""
-        from .. import train
+        """xhat with an autograd graph to the parameters: forward and backward on this library's kernels through the
+        torch.library operators of jamun_b200/autograd_ops.py (composition in jamun_b200/training.py)."""
+        from .. import training
 
         topo = self.topology_for(y)
         out = y.clone("pos")
-        out.pos = train.xhat_positions(self, y.pos, topo, sigma)
+        out.pos = training.xhat_positions(self, y.pos, topo, sigma)
         return out
 
     def compute_loss(self, x, xhat, sigma):
-        """Per-graph loss (differentiable w.r.t. xhat.pos; denoiser.py:251-287)."""
+        """Per-graph loss (differentiable w.r.t. xhat.pos; denoiser.py:251-287) -- one kernel forward, one backward."""
+        from .. import autograd_ops  # noqa: F401
         from ..utils import mean_center
 
         if self.mean_center:
             x = mean_center(x)
         D = xhat.pos.shape[-1]
         topo = self.topology_for(x)
-        raw = ((xhat.pos - x.pos) ** 2).sum(dim=-1)
-        scaled_rmsd = torch.sqrt(raw) / (float(torch.as_tensor(sigma)) * np.sqrt(D))
-        G = topo.G
-        cnt = (topo.chain_ptr_long[1:] - topo.chain_ptr_long[:-1]).clamp_min(1).to(raw.dtype)
-        seg = lambda t: torch.zeros(G, dtype=t.dtype, device=t.device).index_add_(0, topo.batch_long, t) / cnt  # noqa: E731
-        raw_g, rmsd_g = seg(raw), seg(scaled_rmsd)
-        lw = x.loss_weight.to(raw_g) if "loss_weight" in x else torch.ones_like(raw_g)
-        loss = raw_g * lw * float(self.loss_weight(torch.as_tensor(float(sigma)), self.average_squared_distance, D))
+        lw = x.loss_weight.to(xhat.pos.device, torch.float32).contiguous() if "loss_weight" in x else None
+        scale = float(self.loss_weight(torch.as_tensor(float(sigma)), self.average_squared_distance, D))
+        loss, raw_g, rmsd_g = torch.ops.jamun_b200.coordinate_loss(xhat.pos, x.pos.contiguous(), topo.chain_of, topo.chain_ptr, lw,
+                                                                   scale, float(torch.as_tensor(sigma)))
         return loss, {"coordinate_loss": loss, "raw_coordinate_loss": raw_g, "scaled_rmsd": rmsd_g}
 
     def noise_and_compute_loss(self, x, sigma, align_noisy_input: bool):
@@ -288,8 +286,7 @@ class Denoiser(_Base):
         return self.compute_loss(x, xhat, sigma)
 
     def training_step(self, batch, batch_idx: int):
-        """denoiser.py:299-319.  Gradients come from torch autograd over jamun_b200/train.py (the backward kernels of the conv
-        stack are not written yet); the forward of validation/sampling stays on the CUDA kernels."""
+        """denoiser.py:299-319.  Forward and backward run on this library's kernels (jamun_b200/training.py)."""
         sigma = self.sigma_distribution.sample().to(self.device)
         loss, aux = self.noise_and_compute_loss(batch, sigma, align_noisy_input=self.align_noisy_input_during_training)
         aux["loss"] = loss

@@ -166,7 +166,7 @@ def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
 
 
 def pack_b(src, n_stages: int, n_pad: int, row_map=None, k_src: Optional[int] = None, n_valid: Optional[int] = None,
-           n_inner: Optional[int] = None, outer_rows: int = 0, col_blocks: int = 1, out=None):
+           n_inner: Optional[int] = None, outer_rows: int = 0, col_blocks: int = 1, transpose: bool = False, out=None):
     """Row-major weights -> (hi | lo) stage images of the GEMM's B operand ([col_blocks, n_stages, 2, n_pad*32])."""
     assert src.dim() == 2
     k_src = src.shape[0] if k_src is None else k_src
@@ -175,7 +175,7 @@ def pack_b(src, n_stages: int, n_pad: int, row_map=None, k_src: Optional[int] = 
     shape = (col_blocks, n_stages, 2, n_pad * 32) if col_blocks > 1 else (n_stages, 2, n_pad * 32)
     out = torch.empty(shape, dtype=torch.float32, device=src.device) if out is None else out
     rc = _lib.lib().jamun_pack_b(_ptr(src), src.stride(0), _ptr(row_map, torch.int32), k_src, n_stages, n_valid, n_inner,
-                                 outer_rows, n_pad, col_blocks, _ptr(out), _stream())
+                                 outer_rows, n_pad, col_blocks, int(transpose), _ptr(out), _stream())
     _lib.check(rc, "jamun_pack_b")
     _count()
     return out
@@ -311,3 +311,183 @@ def tensor_product(x1, x2, weight, table, d_out: int):
     _lib.check(rc, "jamun_tensor_product")
     _count()
     return out
+
+
+# ---- training path (backward kernels); the torch.library operators built on these are in jamun_b200/autograd_ops.py --------
+def _pc(t: torch.Tensor, col: int = 0) -> int:
+    """Device pointer of column `col` of a row-major fp32 matrix (rows keep their leading dimension)."""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("jamun_b200 ops need CUDA fp32 tensors (no CPU fallback)")
+    return t.data_ptr() + 4 * col
+
+
+_scratch = {}
+
+
+def _scratch_for(n: int, device) -> torch.Tensor:
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < n:
+        buf = _scratch[device] = torch.empty(max(n, 1 << 16), dtype=torch.float32, device=device)
+    return buf
+
+
+def rowmat_mul(X, xcol: int, W, wcol: int, Y, ycol: int, a: int, b: int, trans_w: bool = False, accumulate: bool = False,
+               rows: Optional[int] = None, rows_dev=None):
+    rows = X.shape[0] if rows is None else rows
+    rc = _lib.lib().jamun_rowmat_mul(_pc(X, xcol), X.stride(0), _pc(W, wcol), W.stride(0), int(trans_w), _pc(Y, ycol), Y.stride(0),
+                                     rows, _ptr(rows_dev, torch.int32), a, b, int(accumulate), _stream())
+    _lib.check(rc, "jamun_rowmat_mul")
+    _count()
+
+
+def rowmat_dw(X, xcol: int, dY, ycol: int, dW, wcol: int, a: int, b: int, trans_w: bool = False, accumulate: bool = False,
+              rows: Optional[int] = None, rows_dev=None):
+    rows = X.shape[0] if rows is None else rows
+    scratch = _scratch_for(int(_lib.lib().jamun_rowmat_dw_scratch(rows, a, b)), X.device)
+    rc = _lib.lib().jamun_rowmat_dw(_pc(X, xcol), X.stride(0), _pc(dY, ycol), dY.stride(0), _pc(dW, wcol), dW.stride(0), int(trans_w),
+                                    rows, _ptr(rows_dev, torch.int32), a, b, int(accumulate), _ptr(scratch), _stream())
+    _lib.check(rc, "jamun_rowmat_dw")
+    _count(2)
+
+
+def colsum(M, cols: int, out, flag=None, flag_value: int = 0, fold_s: int = 0, fold_v: int = 0, accumulate: bool = False,
+           rows: Optional[int] = None, rows_dev=None, mcol: int = 0, ocol: int = 0):
+    rows = M.shape[0] if rows is None else rows
+    scratch = _scratch_for(int(_lib.lib().jamun_colsum_scratch(rows, cols)), M.device)
+    rc = _lib.lib().jamun_colsum(_pc(M, mcol), M.stride(0), rows, _ptr(rows_dev, torch.int32), cols, _ptr(flag, torch.uint8),
+                                 int(flag_value), fold_s, fold_v, out.data_ptr() + 4 * ocol, int(accumulate), _ptr(scratch), _stream())
+    _lib.check(rc, "jamun_colsum")
+    _count(2)
+
+
+def conv_bwd_scale(dout, inv_deg, alpha0: float, alpha1: float, g):
+    rc = _lib.lib().jamun_conv_bwd_scale(_ptr(dout), _ptr(inv_deg), float(alpha0), float(alpha1), dout.shape[0], _ptr(g), _stream())
+    _lib.check(rc, "jamun_conv_bwd_scale")
+    _count()
+
+
+def stage_atb(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, nslots: int, rows: int, rows_pad: int, b, b_col0: int,
+              b_comp_stride: int, W: int, out, mode: int, out_rows: int, slot_row0=None, slot_rows=None):
+    IA = C.c_int * nslots
+    r0 = IA(*slot_row0) if slot_row0 is not None else None
+    rn = IA(*slot_rows) if slot_rows is not None else None
+    rc = _lib.lib().jamun_stage_atb(a_ptr, int(a_comp_stride), ncomp, n_stages, nslots, rows, rows_pad, _ptr(b), b.stride(0), b_col0,
+                                    b_comp_stride, W, _ptr(out), mode, out_rows, r0, rn, _stream())
+    _lib.check(rc, "jamun_stage_atb")
+    _count()
+
+
+def conv_bwd_edge(x, s_in: int, v_in: int, rowptr, col, h, rhat, dA0, dA1, dh, dxe):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_bwd_edge(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), _ptr(dA0),
+                                        dA0.stride(0), _ptr(dA1), dA1.stride(1) if dA1 is not None else 0,
+                                        dA1.stride(0) if dA1 is not None else 0, x.shape[0], _ptr(dh), _ptr(dxe), _stream())
+    _lib.check(rc, "jamun_conv_bwd_edge")
+    _count()
+
+
+def conv_bwd_p2(src_rowptr, src_eid, edst, h, rhat, y, g, rows_pad: int, dh, dy_op):
+    i32 = torch.int32
+    N = g.shape[0]
+    rc = _lib.lib().jamun_conv_bwd_p2(_ptr(src_rowptr, i32), _ptr(src_eid, i32), _ptr(edst, i32), _ptr(h), _ptr(rhat), _ptr(y),
+                                      y.stride(0), _ptr(g), N, rows_pad, _ptr(dh), _ptr(dy_op), _stream())
+    _lib.check(rc, "jamun_conv_bwd_p2")
+    _count()
+
+
+def conv_bwd_gather(src_rowptr, src_eid, dxe, extra, n_extra: int, dx):
+    i32 = torch.int32
+    rc = _lib.lib().jamun_conv_bwd_gather(_ptr(src_rowptr, i32), _ptr(src_eid, i32), _ptr(dxe), dx.shape[1], _ptr(extra),
+                                          extra.stride(0) if extra is not None else 0, n_extra, dx.shape[0], _ptr(dx), _stream())
+    _lib.check(rc, "jamun_conv_bwd_gather")
+    _count()
+
+
+def gate_fwd(conv, c_act: float, c_gate: float, gated):
+    rc = _lib.lib().jamun_gate_fwd(_ptr(conv), float(c_act), float(c_gate), conv.shape[0], _ptr(gated), _stream())
+    _lib.check(rc, "jamun_gate_fwd")
+    _count()
+
+
+def gate_bwd(conv, dgated, c_act: float, c_gate: float, dconv):
+    rc = _lib.lib().jamun_gate_bwd(_ptr(conv), _ptr(dgated), float(c_act), float(c_gate), conv.shape[0], _ptr(dconv), _stream())
+    _lib.check(rc, "jamun_gate_bwd")
+    _count()
+
+
+def mix_bwd(dx_new, dx_scaled, y, x_res, skip_w, s_next, dy, dx_res, prod_s, prod_w):
+    rc = _lib.lib().jamun_mix_bwd(_ptr(dx_new), _ptr(dx_scaled), _ptr(y), _ptr(x_res), _ptr(skip_w), _ptr(s_next), y.shape[0],
+                                  _ptr(dy), _ptr(dx_res), _ptr(prod_s), _ptr(prod_w), _stream())
+    _lib.check(rc, "jamun_mix_bwd")
+    _count()
+
+
+def head_bwd(pre, hv, w2, dg, c_gate: float, dpre, dhv, prod_w2):
+    rc = _lib.lib().jamun_head_bwd(_ptr(pre), _ptr(hv), _ptr(w2), _ptr(dg), float(c_gate), pre.shape[0], _ptr(dpre), _ptr(dhv),
+                                   _ptr(prod_w2), _stream())
+    _lib.check(rc, "jamun_head_bwd")
+    _count()
+
+
+def radial_bwd(rb, ebond, rowptr, w0r, b0eff, dh, dz):
+    N, cap = rowptr.numel() - 1, ebond.numel()
+    rc = _lib.lib().jamun_radial_bwd(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap, _ptr(w0r), _ptr(b0eff),
+                                     _ptr(dh), _ptr(dz), _stream())
+    _lib.check(rc, "jamun_radial_bwd")
+    _count()
+
+
+def embed_bwd(idx, tabs, scale, dx0, dtabs, prod):
+    i32 = torch.int32
+    N = dx0.shape[0]
+    rc = _lib.lib().jamun_embed_bwd(_ptr(idx[0], i32), _ptr(idx[1], i32), _ptr(idx[2], i32),
+                                    _ptr(idx[3], i32) if idx[3] is not None else None, *[_ptr(t) for t in tabs],
+                                    *[t.shape[1] for t in tabs], *[t.shape[0] for t in tabs], _ptr(scale), _ptr(dx0), N,
+                                    *[_ptr(t) for t in dtabs], _ptr(prod), _stream())
+    _lib.check(rc, "jamun_embed_bwd")
+    _count(5)
+
+
+def noise_mlp_bwd(w1, b1, w2, b2, c_noise: float, apply_sigmoid: bool, dout, dw1, db1, dw2, db2):
+    rc = _lib.lib().jamun_noise_mlp_bwd(_ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), float(c_noise), b1.numel(), int(apply_sigmoid),
+                                        _ptr(dout), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _stream())
+    _lib.check(rc, "jamun_noise_mlp_bwd")
+    _count()
+
+
+def combine_xhat(g, ybar, chain_ptr, c_skip: float, c_mix: float, center: bool, xhat):
+    G = chain_ptr.numel() - 1
+    rc = _lib.lib().jamun_combine_xhat(_ptr(g), _ptr(ybar), _ptr(chain_ptr, torch.int32), G, float(c_skip), float(c_mix), int(center),
+                                       _ptr(xhat), _stream())
+    _lib.check(rc, "jamun_combine_xhat")
+    _count()
+    return xhat
+
+
+def loss_fwd(xhat, x, chain_ptr, scale: float, sigma: float, lw, loss, raw, rmsd):
+    G = chain_ptr.numel() - 1
+    rc = _lib.lib().jamun_loss_fwd(_ptr(xhat), _ptr(x), _ptr(chain_ptr, torch.int32), G, float(scale), float(sigma), _ptr(lw),
+                                   _ptr(loss), _ptr(raw), _ptr(rmsd), _stream())
+    _lib.check(rc, "jamun_loss_fwd")
+    _count()
+
+
+def loss_bwd(xhat, x, chain_of, chain_ptr, scale: float, lw, dloss, dxhat):
+    rc = _lib.lib().jamun_loss_bwd(_ptr(xhat), _ptr(x), _ptr(chain_of, torch.int32), _ptr(chain_ptr, torch.int32), xhat.shape[0],
+                                   float(scale), _ptr(lw), _ptr(dloss), _ptr(dxhat), _stream())
+    _lib.check(rc, "jamun_loss_bwd")
+    _count()
+
+
+def kabsch_align(y, x, chain_ptr, out, rot=None):
+    G = chain_ptr.numel() - 1
+    rc = _lib.lib().jamun_kabsch_align(_ptr(y), _ptr(x), _ptr(chain_ptr, torch.int32), G, _ptr(out), _ptr(rot), _stream())
+    _lib.check(rc, "jamun_kabsch_align")
+    _count()
+    return out
+
+
+def add_cols(out, col0: int, add, n: int):
+    rc = _lib.lib().jamun_add_cols(_ptr(out), out.stride(0), col0, _ptr(add), add.stride(0), n, out.shape[0], _stream())
+    _lib.check(rc, "jamun_add_cols")
+    _count()

@@ -260,10 +260,10 @@ def test_jamun_alias_resolves_reference_targets():
 
 
 def test_training_conv_formulation_matches_kernel_model():
-    """jamun_b200/train.py evaluates the conv as a degree-padded batched GEMM; its helpers are device-agnostic torch code, so the
-    algebra is checked here against the per-edge reference emulation (the full training path itself is CUDA-only)."""
+    """tests/torch_reference.py (the autograd reference the GPU tests hold the backward kernels to) evaluates the conv as a
+    degree-padded batched GEMM; its algebra is checked here against the per-edge reference emulation."""
     import kernel_model as KM
-    from jamun_b200 import train
+    import torch_reference as train
 
     gen = torch.Generator().manual_seed(11)
     N, E = 13, 70

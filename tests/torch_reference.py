@@ -1,4 +1,7 @@
-"""Differentiable evaluation of the denoiser for training.
+"""TEST INFRASTRUCTURE (round 1's library-path training forward, kept as the torch/autograd reference of the custom ops in
+jamun_b200/autograd_ops.py -- nothing under jamun_b200/ imports it).
+
+Differentiable evaluation of the denoiser for training.
 
 Status: LIBRARY PATH.  The sampling path runs on this repo's CUDA kernels; their backward counterparts (dM = A^T dOut and
 dA = dOut M^T on tcgen05, the transposed aggregate builder) are not written yet.  Until they are, ``Denoiser.training_step``
@@ -18,7 +21,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from . import engine, ops
+from jamun_b200 import engine, ops
 
 S, V, HID, SO = ops.S, ops.V, ops.HID, 152
 
