@@ -241,7 +241,7 @@ def block_tail_bwd(dx_new: Optional[Tensor], dx_scaled: Optional[Tensor], conv_o
     conv_out, x_in = conv_out.contiguous(), x_in.contiguous()
     N, D_in = conv_out.shape[0], x_in.shape[1]
     like = conv_out
-    none = _empty(0, like=like)
+    none = lambda: _empty(0, like=like)  # noqa: E731  (outputs of a custom op may not alias each other)
     gated, y = _empty(N, HID, like=like), _empty(N, HID, like=like)
     ops.gate_fwd(conv_out, c_act, c_gate, gated)
     # recompute y = Lin_self(gated) + Lin_skip(x_in)
@@ -253,14 +253,14 @@ def block_tail_bwd(dx_new: Optional[Tensor], dx_scaled: Optional[Tensor], conv_o
             ops.rowmat_mul(x_in, s_in + v_in * c, wskip_v, 0, y, S + V * c, v_in, V, accumulate=True)
     dy = _empty(N, HID, like=like)
     has_skip, has_scale = skip_w is not None, (s_next is not None and dx_scaled is not None)
-    dx_res = _empty(N, HID, like=like) if has_skip else none
+    dx_res = _empty(N, HID, like=like) if has_skip else none()
     prod_s = _empty(N, HID, like=like) if has_scale else None
     prod_w = _empty(N, HID, like=like) if has_skip else None
     ops.mix_bwd(None if dx_new is None else dx_new.contiguous(), dx_scaled.contiguous() if has_scale else None, y,
                 None if x_res is None else x_res.contiguous(), skip_w, s_next if has_scale else None, dy,
                 dx_res if has_skip else None, prod_s, prod_w)
-    ds_next = torch.zeros(SO, dtype=torch.float32, device=like.device) if s_next is not None else none
-    dskip_w = _empty(SO, like=like) if has_skip else none
+    ds_next = torch.zeros(SO, dtype=torch.float32, device=like.device) if s_next is not None else none()
+    dskip_w = _empty(SO, like=like) if has_skip else none()
     if has_scale:
         ops.colsum(prod_s, HID, ds_next, fold_s=S, fold_v=V)
     if has_skip:
@@ -270,7 +270,7 @@ def block_tail_bwd(dx_new: Optional[Tensor], dx_scaled: Optional[Tensor], conv_o
     ops.rowmat_mul(dy, 0, wself_s, 0, dgated, 0, S, S, trans_w=True)
     ops.rowmat_mul(dy, 0, wskip_s, 0, dx_in, 0, S, s_in, trans_w=True)
     dwself_s, dwself_v, dwskip_s = torch.empty_like(wself_s), torch.empty_like(wself_v), torch.empty_like(wskip_s)
-    dwskip_v = torch.empty_like(wskip_v) if v_in else none
+    dwskip_v = torch.empty_like(wskip_v) if v_in else none()
     ops.rowmat_dw(gated, 0, dy, 0, dwself_s, 0, S, S)
     ops.rowmat_dw(x_in, 0, dy, 0, dwskip_s, 0, s_in, S)
     for c in range(3):
