@@ -3,11 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
     python bench.py --impl reference ...                      (the reference algorithm on the host CPU: oracle port)
+    python bench.py --workload 4AA|ala2_capped|protein1000|train4AA ...   (one of the other BASELINE configs as the headline)
 
-A bench "step" is one pass of the hot path over one batch: `--inner` consecutive BAOAB walk-jump steps (radius graph,
-edge features, 6 conv blocks, head, fused integrator + jump) over all chains of the workload.  The workload at N=1 is
-BASELINE.json configs[1]: uncapped 2AA peptides, 1024 chains (per GPU; weak scaling at N>1), random-init default
-denoiser with output_gain=1, synthetic coordinates.  One JSON line is printed by rank 0.
+A bench "step" is one pass of the hot path over one batch: `--inner` consecutive BAOAB walk-jump steps (radius graph, edge
+features, 6 conv blocks, head, fused integrator + jump) over all chains of the workload.  The default workload is
+BASELINE.json configs[1] (C2): uncapped 2AA peptides, 1024 chains per GPU (weak scaling at N>1), random-init default denoiser
+with output_gain=1, synthetic coordinates.  One JSON line is printed by rank 0.  Besides the contract keys it carries
+
+  roofline      the dominant kernels timed alone with CUDA events (the contraction GEMM against the dense-TF32 peak, the
+                aggregate builder against the measured HBM bandwidth)
+  cpu_baseline  the oracle port on the host cores, with and without the reference's redundant jump pass
+  parity        max |xhat - oracle| and max relative score error of the GPU path on the CPU sample, measured in this run
+  configs       the other BASELINE configs under the same clock: C1 (capped ALA-ALA, 64 chains x 100 steps), C3 (4AA, 1024
+                chains/GPU, gathered; with its own CPU baseline), C4 (1000-atom chains, 512 chains/GPU, row-chunked) and C5
+                (training step fwd+bwd on 4AA batches, DDP all-reduce at N>1); `--no-configs` skips them.
 """
 from __future__ import annotations
 
@@ -28,6 +37,8 @@ SIGMA = 0.04
 MCMC = dict(delta=0.04, friction=1.0, M=1.0, inverse_temperature=1.0, score_fn_clip=100.0)
 METRIC = "walkjump_atom_steps_per_s"
 UNIT = "atoms*steps/s"
+N_RES = {"2AA": 2, "4AA": 4, "ala2_capped": 2, "protein1000": 100, "train4AA": 4}
+DEFAULT_CHAINS = {"2AA": 1024, "4AA": 1024, "ala2_capped": 64, "protein1000": 512, "train4AA": 1024}
 
 
 def parse():
@@ -36,11 +47,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="2AA", choices=["2AA", "4AA", "ala2_capped", "protein1000"])
-    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: 1024; protein1000: 64)")
+    ap.add_argument("--workload", default="2AA", choices=list(N_RES))
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the BASELINE config's)")
     ap.add_argument("--inner", type=int, default=32, help="walk-jump steps per bench step")
     ap.add_argument("--cpu-sample-chains", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configs (C1, C3, C4, C5)")
     return ap.parse_args()
 
 
@@ -48,21 +60,20 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            d = json.load(f)
-        return d, "measured"
+            return json.load(f), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def measured_traffic(args, atoms):
+def measured_traffic(workload, chains):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload only)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        if args.workload == "2AA" and (args.chains or 1024) == 1024:
-            return d["dram_bytes_per_launch"]
-    except Exception:  # noqa: BLE001
-        pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            if workload == "2AA" and chains == 1024:
+                return d["dram_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            continue
     return None
 
 
@@ -102,192 +113,280 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_workload(args, rank: int):
+def workload_tensors(workload: str, chains: int, rank: int, world: int):
     from jamun_b200 import synthetic
 
-    chains = args.chains or (64 if args.workload == "protein1000" else 1024)
-    sizes_all = synthetic.workload_sizes(args.workload, chains * max(1, args.gpus))
+    name = "4AA" if workload == "train4AA" else workload
+    sizes_all = synthetic.workload_sizes(name, chains * max(1, world))
     sizes = sizes_all[rank * chains:(rank + 1) * chains]
-    n_res = {"2AA": 2, "4AA": 4, "ala2_capped": 2, "protein1000": 100}[args.workload]
-    t = synthetic.make_tensors(sizes, n_res=n_res, first_chain_id=rank * chains)
-    return t, sizes
+    return synthetic.make_tensors(sizes, n_res=N_RES[workload], first_chain_id=rank * chains), sizes
 
 
-def oracle_model():
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def oracle_from(model_state=None):
     from oracle import jamun_oracle as O
 
     torch.manual_seed(0)
     o = O.Denoiser()
-    O.randomize_for_parity(o)
+    if model_state is None:
+        O.randomize_for_parity(o)
+    else:
+        o.load_state_dict({k.replace("g._orig_mod.", "g."): v.detach().cpu() for k, v in model_state.items()})
     return o
 
 
-def cpu_reference_rate(args, sizes_sample, steps: int):
+def oracle_batch(t):
+    from oracle import jamun_oracle as O
+
+    return O.OracleBatch(pos=t["pos"], batch=t["batch"], num_graphs=t["num_graphs"], edge_index=t["edge_index"],
+                         atom_type_index=t["atom_type_index"], atom_code_index=t["atom_code_index"],
+                         residue_code_index=t["residue_code_index"], residue_sequence_index=t["residue_sequence_index"])
+
+
+def cpu_reference_rate(workload: str, sizes_sample, steps: int, redundant_jump: bool, o=None):
     """The reference's formulation (oracle port) on the host cores: atoms x steps / s on a bounded sample."""
     from jamun_b200 import synthetic
     from oracle import jamun_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
-    o = oracle_model()
-    n_res = {"2AA": 2, "4AA": 4, "ala2_capped": 2, "protein1000": 100}[args.workload]
-    t = synthetic.make_tensors(sizes_sample, n_res=n_res)
-    ob = O.OracleBatch(pos=t["pos"], batch=t["batch"], num_graphs=t["num_graphs"], edge_index=t["edge_index"],
-                       atom_type_index=t["atom_type_index"], atom_code_index=t["atom_code_index"],
-                       residue_code_index=t["residue_code_index"], residue_sequence_index=t["residue_sequence_index"])
-    y0 = t["pos"] + SIGMA * torch.randn(t["pos"].shape)
+    o = o or oracle_from()
+    t = synthetic.make_tensors(sizes_sample, n_res=N_RES[workload])
+    ob = oracle_batch(t)
+    y0 = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=torch.Generator().manual_seed(5))
     with torch.no_grad():
-        O.walk_jump(o, ob, y0, SIGMA, mcmc=O.baoab, v_init="gaussian", steps=2, save_trajectory=True, redundant_jump=False, **MCMC)
         t0 = time.perf_counter()
         # steps+1 score evaluations advance `steps` Langevin updates; the reference's redundant jump pass doubles that
         O.walk_jump(o, ob, y0, SIGMA, mcmc=O.baoab, v_init="gaussian", steps=steps + 1, save_trajectory=True,
-                    redundant_jump=True, **MCMC)
+                    redundant_jump=redundant_jump, **MCMC)
         dt = time.perf_counter() - t0
     atoms = int(t["pos"].shape[0])
     return atoms * steps / dt, atoms, dt
 
 
+def cpu_baseline_block(workload: str, chains: int, n_sample: int, o=None):
+    from jamun_b200 import synthetic
+
+    name = "4AA" if workload == "train4AA" else workload
+    sizes = synthetic.workload_sizes(name, chains)[:n_sample]
+    cpu_reference_rate(workload, sizes[:2], 1, False, o)  # warm the thread pool / allocator
+    r_jump, atoms, dt_j = cpu_reference_rate(workload, sizes, 1, True, o)
+    r_nojump, _, dt_n = cpu_reference_rate(workload, sizes, 1, False, o)
+    return {"value": r_jump, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "value_without_redundant_jump": r_nojump,
+            "sample": f"first {len(sizes)} chains ({atoms} atoms) of the {name} workload x 1 walk-jump step; `value` = the reference "
+                      f"formulation incl. its redundant jump pass (2 denoiser evaluations per step, {dt_j:.1f} s), "
+                      f"`value_without_redundant_jump` = 1 evaluation per step like the GPU path ({dt_n:.1f} s)"}
+
+
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from jamun_b200 import synthetic
 
-    chains = args.chains or (64 if args.workload == "protein1000" else 1024)
-    sizes = synthetic.workload_sizes(args.workload, chains)[: args.cpu_sample_chains]
-    inner = 1
-    rates, times = [], []
+    chains = args.chains or DEFAULT_CHAINS[args.workload]
+    name = "4AA" if args.workload == "train4AA" else args.workload
+    sizes = synthetic.workload_sizes(name, chains)[: args.cpu_sample_chains]
+    o = oracle_from()
+    rates, rates_nj, times = [], [], []
     for k in range(args.warmup + args.steps):
-        rate, atoms, dt = cpu_reference_rate(args, sizes, inner)
+        rate, atoms, dt = cpu_reference_rate(args.workload, sizes, 1, True, o)
+        rate_nj, _, _ = cpu_reference_rate(args.workload, sizes, 1, False, o)
         if k >= args.warmup:
             rates.append(rate)
+            rates_nj.append(rate_nj)
             times.append(dt)
     value = sum(rates) / len(rates)
-    sample = f"first {len(sizes)} chains ({atoms} atoms) of the {args.workload} workload x {inner} walk-jump step(s) per bench step, " \
-             f"reference formulation incl. its redundant jump pass"
+    sample = f"first {len(sizes)} chains ({atoms} atoms) of the {name} workload x 1 walk-jump step per bench step, reference " \
+             f"formulation incl. its redundant jump pass (value_without_redundant_jump: 1 denoiser evaluation per step)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} uncapped peptides, {chains} chains/GPU, sigma=0.04, BAOAB", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "config": {"workload": f"{name} peptides, {chains} chains/GPU, sigma=0.04, BAOAB", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "value_without_redundant_jump": sum(rates_nj) / len(rates_nj)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def run_native(args):
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Ctx:
+    def __init__(self):
+        import torch.distributed as dist
 
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms_sum_atoms(self, ms: float, atoms: int):
+        tt = torch.tensor([ms, float(atoms)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            tmax, tsum = tt.clone(), tt.clone()
+            self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(tsum, op=self.dist.ReduceOp.SUM)
+            return float(tmax[0]), float(tsum[1])
+        return ms, float(atoms)
+
+
+def make_model(dev):
+    """Seed-0 default init + parity re-draws (output_gain=1), identical on every rank -- product-side init."""
     import jamun_b200 as J
-    from jamun_b200 import data, ops, utils
-    from jamun_b200.sampling.mcmc import BAOAB
-    from jamun_b200.sampling.mcmc.functional import fused_baoab
-    from jamun_b200.sampling.walkjump import SingleMeasurementSampler
+    from jamun_b200.model.noise_conditioning import NoiseConditionalScaling
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    t, sizes = build_workload(args, rank)
-    atoms = int(t["pos"].shape[0])
-    # weights: seed-0 default init + parity re-draws (output_gain=1), identical on every rank -- product-side init
     torch.manual_seed(0)
     model = J.default_denoiser()
     gen = torch.Generator().manual_seed(0)
     with torch.no_grad():
         model.arch_module.output_gain.fill_(1.0)
-        from jamun_b200.model.noise_conditioning import NoiseConditionalScaling
-
         for m in model.modules():
             if isinstance(m, NoiseConditionalScaling):
                 last = m.scale_predictor[-1]
                 last.weight.copy_(torch.randn(last.weight.shape, generator=gen) * 0.1)
                 last.bias.copy_(1.0 + torch.randn(last.bias.shape, generator=gen) * 0.1)
-    model = model.to(dev).eval()
-    torch.manual_seed(1234 + rank)  # per-rank Philox stream (cmdline/sample.py:86-88)
-    batch = data.Batch.from_tensors(t).to(dev)
+    return model.to(dev).eval()
+
+
+def measure_sampling(cx: Ctx, model, workload: str, chains: int, inner: int, steps: int, warmup: int, e2e: bool = True,
+                     clocks: bool = False):
+    """Device-resident and end-to-end throughput of `inner` walk-jump steps over the workload's chains on every rank."""
+    from jamun_b200 import data, ops, utils
+    from jamun_b200.sampling import Sampler
+    from jamun_b200.sampling.mcmc import BAOAB
+    from jamun_b200.sampling.mcmc.functional import fused_baoab
+    from jamun_b200.sampling.walkjump import SingleMeasurementSampler
+
+    t, sizes = workload_tensors(workload, chains, cx.rank, cx.world)
+    atoms = int(t["pos"].shape[0])
+    torch.manual_seed(1234 + cx.rank)  # per-rank Philox stream (cmdline/sample.py:86-88)
+    batch = data.Batch.from_tensors(t).to(cx.dev)
     wrapped = utils.ModelSamplingWrapper(model, batch, SIGMA)
     topo = wrapped.topology
-    sampler = SingleMeasurementSampler(BAOAB(steps=args.inner + 1, save_trajectory=False, **MCMC), SIGMA)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (`value`)
     y = wrapped.sample_initial_noisy_positions()
 
     def device_step():
         # every bench step walks `inner` steps from the same noisy start (same workload per step, as in the e2e leg below;
         # with random-init weights a continued chain drifts apart and its graphs get sparser, i.e. cheaper)
-        return fused_baoab(model, topo, y, SIGMA, steps=args.inner + 1, v_init="gaussian", **MCMC)
+        return fused_baoab(model, topo, y, SIGMA, steps=inner + 1, v_init="gaussian", **MCMC)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
-    barrier()
-    clocks = ClockSampler(local_rank)
+    cx.barrier()
+    clk = ClockSampler(cx.local_rank) if clocks else None
     launches0 = ops.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = device_step()
-    if world > 1:  # the run's only collective: final NCCL gather of the denoised samples
-        from jamun_b200.sampling import Sampler
-
-        gathered = Sampler.gather_samples_ragged(out["xhat"])
+    if cx.world > 1:  # the run's only collective: final NCCL gather of the denoised samples
+        Sampler.gather_samples_ragged(out["xhat"])
     ev1.record()
-    barrier()
+    cx.barrier()
     launches = ops.LAUNCHES - launches0
-    ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop()
-    tt = torch.tensor([ms, float(atoms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        tmax = tt.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = tt.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, total_atoms = float(tmax[0]), float(tsum[1])
-    else:
-        total_atoms = float(atoms)
-    value = total_atoms * args.inner * args.steps / (ms * 1e-3)
+    ms, total_atoms = cx.max_ms_sum_atoms(ev0.elapsed_time(ev1), atoms)
+    res = {"value": total_atoms * inner * steps / (ms * 1e-3), "ms_per_step": ms / steps, "atoms_per_gpu": atoms,
+           "chains_per_gpu": len(sizes), "gpu_launches": launches, "mean_in_degree": int(topo.rowptr[-1].item()) / max(1, atoms)}
+    if clk is not None:
+        res["clocks"] = clk.stop()
+    if e2e:  # through the public sampler API with HOST buffers: H2D of y_init and D2H of the samples inside the timed region
+        sampler = SingleMeasurementSampler(BAOAB(steps=inner + 1, save_trajectory=False, **MCMC), SIGMA)
+        y_host = y.detach().cpu().pin_memory()
+        x_host = torch.empty_like(y_host).pin_memory()
 
-    # ---------------- end-to-end through the public sampler API with HOST buffers (`e2e`)
-    y_host = y.detach().cpu().pin_memory()
-    x_host = torch.empty_like(y_host).pin_memory()
+        def e2e_step():
+            y_dev = y_host.to(cx.dev, non_blocking=True)
+            o = sampler.sample(wrapped, y_init=y_dev, v_init="gaussian")
+            x_host.copy_(o["sample"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    def e2e_step():
-        y_dev = y_host.to(dev, non_blocking=True)
-        o = sampler.sample(wrapped, y_init=y_dev, v_init="gaussian")
-        x_host.copy_(o["sample"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        for _ in range(max(1, warmup)):
+            e2e_step()
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            e2e_step()
+        e1.record()
+        cx.barrier()
+        ems, _ = cx.max_ms_sum_atoms(e0.elapsed_time(e1), atoms)
+        res["e2e"] = {"value": total_atoms * inner * steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(y_host.numel() * 4),
+                      "d2h_bytes_per_step": int(y_host.numel() * 4), "ms_per_step": ems / steps}
+    res["_state"] = (wrapped, topo, y, t, sizes)
+    return res
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    ems = e0.elapsed_time(e1)
-    if world > 1:
-        te = torch.tensor([ems], device=dev, dtype=torch.float64)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ems = float(te[0])
-    e2e_value = total_atoms * args.inner * args.steps / (ems * 1e-3)
-    bytes_io = int(y_host.numel() * 4)
 
-    # ---------------- roofline of the dominant kernels, each timed alone with CUDA events on the launch stream
+def measure_training(cx: Ctx, chains: int, steps: int, warmup: int):
+    """C5: Denoiser.training_step forward + backward (+ DDP gradient all-reduce at N>1, + Adam) on synthetic 4AA batches."""
+    import jamun_b200 as J
+    from jamun_b200 import data, ops
+    from jamun_b200.ddp import GradientReducer, broadcast_parameters
+
+    t, sizes = workload_tensors("train4AA", chains, cx.rank, cx.world)
+    atoms = int(t["pos"].shape[0])
+    torch.manual_seed(0)
+    model = make_model(cx.dev).train()
+    broadcast_parameters(model)
+    reducer = GradientReducer(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    batch = data.Batch.from_tensors(t).to(cx.dev)
+    torch.manual_seed(77 + cx.rank)
+    fwd_ms = bwd_ms = 0.0
+
+    def step(timed: bool):
+        nonlocal fwd_ms, bwd_ms
+        reducer.reset()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = model.training_step(batch, 0)
+        e[1].record()
+        out["loss"].backward()
+        reducer.finish()
+        e[2].record()
+        opt.step()
+        if timed:
+            torch.cuda.synchronize()
+            fwd_ms += e[0].elapsed_time(e[1])
+            bwd_ms += e[1].elapsed_time(e[2])
+        return out["loss"]
+
+    for _ in range(warmup):
+        step(False)
+    cx.barrier()
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        loss = step(True)
+    ev1.record()
+    cx.barrier()
+    ms, total_atoms = cx.max_ms_sum_atoms(ev0.elapsed_time(ev1), atoms)
+    return {"metric": "train_atoms_per_s", "value": total_atoms * steps / (ms * 1e-3), "unit": "atoms/s (fwd+bwd+allreduce+Adam)",
+            "ms_per_step": ms / steps, "fwd_ms": fwd_ms / steps, "bwd_allreduce_ms": bwd_ms / steps, "atoms_per_gpu": atoms,
+            "graphs_per_gpu": len(sizes), "allreduce_bytes_per_step": reducer.gradient_bytes if cx.world > 1 else 0,
+            "gradient_buckets": len(reducer.buckets), "gpu_launches": ops.LAUNCHES - launches0, "loss": float(loss.detach()),
+            "parallelism": f"DDP x{cx.world}: bucketed NCCL all-reduce (AVG) overlapped with backward" if cx.world > 1 else "1 GPU"}
+
+
+def roofline_block(model, state, workload, chains, dev):
+    """The dominant kernels, each timed alone with CUDA events on the launch stream (hidden block 1 of the headline workload)."""
+    from jamun_b200 import engine as _engine
+    from jamun_b200 import ops
+
+    wrapped, topo, y, t, sizes = state
+    atoms = topo.N
     pk, pk_src = peaks()
     plan = model.arch_module.plan(model.sigma_context(SIGMA).c_noise, dev)
     blk = plan.blocks[1]
     x_in = topo.xs[0]
-    E = int(topo.rowptr[-1].item())
-    deg = E / max(1, atoms)
+    deg = int(topo.rowptr[-1].item()) / max(1, atoms)
 
     def time_kernel(fn, reps=5):
         fn()
@@ -299,8 +398,6 @@ def run_native(args):
         t1.record()
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) / reps
-
-    from jamun_b200 import engine as _engine
 
     rp = topo.chunk_rows
     st0, st1 = 65 * 5, 65 * 2
@@ -326,48 +423,121 @@ def run_native(args):
     gemm_flop = nrows * 2.0 * 65 * (152 * 152 + 3 * 64 * 32)
     a_bytes = nrows * 65.0 * (160 + 3 * 64) * 4
     tf32_peak = pk["bf16_tflops"] / 2.0
-    roofline = {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
-                "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": measured_traffic(args, atoms),
-                "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
-                "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
-                "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
-                "second_kernel": {"kernel": "conv_build_tc_kernel<120,32> (per-node aggregate F^T.H on tcgen05, 3xTF32; writes the A operand)",
-                                  "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
-                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                  "tensor_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 64) / (build_ms * 1e-3) / 1e12},
-                "fourth_kernel": {"kernel": "conv_p2_edge_kernel + conv_p2_reduce_kernel (0e(x)1e->1e, source-major)",
-                                  "ms_per_launch": p2_ms, "fma_TFLOPs": nrows * deg * 2 * 65 * 32 / (p2_ms * 1e-3) / 1e12},
-                "third_kernel": {"kernel": "gemm_tf32x3_kernel, 17 column-block passes, A-stationary (per-node transform Y = x_s.W, N=2080)",
-                                 "ms_per_launch": ygemm_ms, "achieved": atoms * 2.0 * 120 * 2080 / (ygemm_ms * 1e-3) / 1e12,
-                                 "unit": "TFLOP/s"}}
+    return {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
+            "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": measured_traffic(workload, chains),
+            "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
+            "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
+            "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
+            "second_kernel": {"kernel": "conv_build_tc_kernel<120,32> (per-node aggregate F^T.H on tcgen05, 3xTF32; writes the A operand)",
+                              "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
+                              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                              "tensor_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 64) / (build_ms * 1e-3) / 1e12},
+            "fourth_kernel": {"kernel": "conv_p2_edge_kernel + conv_p2_reduce_kernel (0e(x)1e->1e, source-major)",
+                              "ms_per_launch": p2_ms, "fma_TFLOPs": nrows * deg * 2 * 65 * 32 / (p2_ms * 1e-3) / 1e12},
+            "third_kernel": {"kernel": "gemm_tf32x3_kernel, 17 column-block passes, A-stationary (per-node transform Y = x_s.W, N=2080)",
+                             "ms_per_launch": ygemm_ms, "achieved": atoms * 2.0 * 120 * 2080 / (ygemm_ms * 1e-3) / 1e12,
+                             "unit": "TFLOP/s"}}
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"{args.workload} uncapped peptides, {len(sizes)} chains/GPU ({atoms} atoms/GPU), "
-                                       f"{args.inner} BAOAB walk-jump steps per bench step, sigma=0.04, default e3conv denoiser "
-                                       f"(random init, output_gain=1)",
-                           "l2": "inputs larger than L2: every denoiser evaluation streams a 1.7 GB conv operand per layer "
-                                 "(>> 126 MB L2) and every step advances y, so nothing is served from a warm cache",
-                           "parallelism": f"chains sharded x{world}, final NCCL all_gather of samples"},
-                "clocks": clk, "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
-                        "ms_per_step": ems / args.steps},
-                "roofline": roofline}
-        if not args.no_cpu_baseline and world == 1:
-            from jamun_b200 import synthetic
 
-            chains = args.chains or (64 if args.workload == "protein1000" else 1024)
-            sample_sizes = synthetic.workload_sizes(args.workload, chains)[: args.cpu_sample_chains]
-            rate, a, dt = cpu_reference_rate(args, sample_sizes, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"first {len(sample_sizes)} chains ({a} atoms) x 1 walk-jump step, reference "
-                                              f"formulation incl. redundant jump pass, {dt:.1f} s"}
+def parity_block(model, workload: str, chains: int, n_sample: int, dev, o):
+    """GPU path vs the oracle (same weights) on the CPU sample: one denoiser evaluation, xhat and score (SIGMA = 0.04)."""
+    from jamun_b200 import data, synthetic
+
+    sizes = synthetic.workload_sizes(workload, chains)[:n_sample]
+    t = synthetic.make_tensors(sizes, n_res=N_RES[workload])
+    y0 = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=torch.Generator().manual_seed(5))
+    ob = oracle_batch(t)
+    with torch.no_grad():
+        xh_ref = o.xhat(ob.with_pos(y0), SIGMA)
+        sc_ref = o.score(ob.with_pos(y0), SIGMA)
+        batch = data.Batch.from_tensors(t).to(dev)
+        topo = model.topology_for(batch)
+        xh, sc = model.denoise_positions(y0.to(dev), topo, SIGMA)
+    dx = (xh.cpu() - xh_ref).abs()
+    ds = (sc.cpu() - sc_ref).abs()
+    return {"max_abs_xhat_err": float(dx.max()), "max_rel_xhat_err": float((dx / xh_ref.abs().clamp_min(1e-3)).max()),
+            "max_abs_score_err": float(ds.max()), "max_rel_score_err": float(ds.max() / sc_ref.abs().max()),
+            "within_rtol1e-4_atol1e-5_xhat": bool(torch.allclose(xh.cpu(), xh_ref, rtol=1e-4, atol=1e-5)),
+            "sample": f"first {len(sizes)} chains of {workload} ({t['pos'].shape[0]} atoms), one teacher-forced evaluation vs the fp32 oracle"}
+
+
+def run_native(args):
+    cx = Ctx()
+    model = make_model(cx.dev)
+    chains = args.chains or DEFAULT_CHAINS[args.workload]
+    line = None
+    if args.workload == "train4AA":
+        tr = measure_training(cx, chains, args.steps, args.warmup)
+        if cx.rank == 0:
+            line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": cx.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"C5: training step on synthetic 4AA batches, {tr['graphs_per_gpu']} graphs/GPU "
+                                           f"({tr['atoms_per_gpu']} atoms/GPU), sigma=0.04, Kabsch alignment on, Adam",
+                               "parallelism": tr["parallelism"], "l2": "per-layer operands (3.2 GB) exceed L2"},
+                    "gpu_launches": tr["gpu_launches"], "train": tr}
+    else:
+        head = measure_sampling(cx, model, args.workload, chains, args.inner, args.steps, args.warmup, e2e=True, clocks=True)
+        state = head.pop("_state")
+        if cx.rank == 0:
+            line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": cx.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"{args.workload} peptides, {head['chains_per_gpu']} chains/GPU ({head['atoms_per_gpu']} "
+                                           f"atoms/GPU), {args.inner} BAOAB walk-jump steps per bench step, sigma=0.04, default e3conv "
+                                           f"denoiser (random init, output_gain=1)",
+                               "l2": "inputs larger than L2: every denoiser evaluation streams a 1.7 GB conv operand per layer "
+                                     "(>> 126 MB L2) and every step advances y, so nothing is served from a warm cache",
+                               "parallelism": f"chains sharded x{cx.world}, final NCCL all_gather of samples"},
+                    "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head["e2e"],
+                    "roofline": roofline_block(model, state, args.workload, chains, cx.dev)}
+        del state
+        torch.cuda.empty_cache()
+        # ---- the other BASELINE configs, same process, same clocks
+        configs = {}
+        if not args.no_configs and args.workload == "2AA":
+            c3 = measure_sampling(cx, model, "4AA", 1024, 16, 3, 3, e2e=True)
+            c3.pop("_state")
+            c3["config"] = f"C3: uncapped 4AA, 1024 chains/GPU x {cx.world} GPU(s) = {1024 * cx.world} chains, 16 steps per bench " \
+                           f"step, samples gathered over NCCL"
+            configs["C3_4AA"] = c3
+            torch.cuda.empty_cache()
+            c5 = measure_training(cx, 1024, 3, 3)
+            c5["config"] = "C5: training step fwd+bwd on synthetic 4AA batches, 1024 graphs/GPU, DDP all-reduce at N>1"
+            configs["C5_train4AA"] = c5
+            torch.cuda.empty_cache()
+            if cx.world == 1:
+                c1 = measure_sampling(cx, model, "ala2_capped", 64, 100, 3, 3, e2e=True)
+                c1.pop("_state")
+                c1["config"] = "C1: capped ALA-ALA (22 atoms), 64 chains x 100 walk-jump steps per bench step"
+                configs["C1_ala2_capped"] = c1
+                torch.cuda.empty_cache()
+                c5s = measure_training(cx, 32, 3, 3)
+                c5s["config"] = "C5 (reference batch size): 32 graphs/GPU (data/md.yaml:3)"
+                configs["C5_train4AA_batch32"] = c5s
+                torch.cuda.empty_cache()
+                c4 = measure_sampling(cx, model, "protein1000", 512, 4, 2, 3, e2e=True)
+                c4.pop("_state")
+                c4["config"] = "C4: 1000-atom chains, 512 chains/GPU (512 k atoms, conv operand processed in row chunks), 4 steps " \
+                               "per bench step"
+                configs["C4_protein1000"] = c4
+                torch.cuda.empty_cache()
+        if cx.rank == 0:
+            if configs:
+                line["configs"] = configs
+            if not args.no_cpu_baseline and cx.world == 1:
+                o = oracle_from(model.state_dict())
+                line["cpu_baseline"] = cpu_baseline_block(args.workload, chains, args.cpu_sample_chains, o)
+                line["parity"] = parity_block(model, args.workload, chains, args.cpu_sample_chains, cx.dev, o)
+                if "C3_4AA" in configs:
+                    configs["C3_4AA"]["cpu_baseline"] = cpu_baseline_block("4AA", 1024, max(4, args.cpu_sample_chains // 2), o)
+                    configs["C3_4AA"]["speedup_vs_cpu_like_for_like"] = \
+                        configs["C3_4AA"]["e2e"]["value"] / configs["C3_4AA"]["cpu_baseline"]["value_without_redundant_jump"]
+    if cx.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def main():

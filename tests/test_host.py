@@ -300,3 +300,51 @@ def test_load_state_dict_warns_on_unknown_tensor_product_entries(models):
         warnings.simplefilter("always")
         m.load_state_dict(sd)
     assert any("tp.mystery" in str(w.message) for w in rec) and not any("tp.weight" in str(w.message) for w in rec)
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from jamun_b200.ddp import GradientReducer, broadcast_parameters
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)  # replicas start different on purpose: broadcast_parameters must fix that
+    model = torch.nn.Sequential(torch.nn.Linear(6, 300), torch.nn.Tanh(), torch.nn.Linear(300, 5), torch.nn.Linear(5, 1))
+    broadcast_parameters(model)
+    red = GradientReducer(model, bucket_bytes=1024)  # several buckets; the 300x6 weight is a bucket of its own
+    data = [torch.randn(8, 6, generator=torch.Generator().manual_seed(7 + r)) for r in range(world)]
+    # reference: the mean over ranks of the local gradients, computed redundantly without any collective
+    ref = None
+    for r in range(world):
+        gs = torch.autograd.grad(model(data[r]).pow(2).mean(), list(model.parameters()))
+        ref = [g / world for g in gs] if ref is None else [a + g / world for a, g in zip(ref, gs)]
+    out = []
+    for step in range(2):  # second step: buckets re-zeroed, views still attached
+        red.reset()
+        model(data[rank]).pow(2).mean().backward()
+        red.finish()
+        out.append([p.grad.clone() for p in model.parameters()])
+    ok = all(torch.allclose(g, r_, rtol=1e-5, atol=1e-7) for g, r_ in zip(out[0], ref)) and \
+        all(torch.equal(a, b) for a, b in zip(out[0], out[1]))
+    flat = torch.cat([g.reshape(-1) for g in out[1]])
+    q.put((rank, ok, len(red.buckets), flat.tolist()))
+    dist.destroy_process_group()
+
+
+def test_ddp_gradient_allreduce_world2():
+    """DDP row (e2): after a step every rank holds the same gradients, equal to the mean of the per-rank gradients."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] and res[1][1]
+    assert res[0][2] >= 3
+    assert res[0][3] == res[1][3]  # bit-identical across ranks
