@@ -71,6 +71,14 @@ int jamun_radius_csr(const float* pos, const int* chain_of, const int* chain_ptr
                      int max_num_neighbors, const int* bond_rowptr, const int* bond_src, int* scratch,
                      int* rowptr, int* col, int* edst, unsigned char* ebond, jamun_stream_t stream);
 
+/* The same CSR from a cell-list search (north_star subsystem 1), for long chains: one CTA per chain bins the chain's atoms
+ * into cells of edge >= r_cut in shared memory and tests the 27 surrounding cells with the same fp32 predicate; the cap rule
+ * is applied as "the max_num_neighbors+1 smallest hit indices", which is what the ascending scan of torch_cluster's kernel
+ * keeps.  nbr: [N, max_num_neighbors+1] int scratch; max_chain <= 8192 atoms; 0 <= max_num_neighbors < 64. */
+int jamun_radius_csr_cells(const float* pos, const int* chain_ptr, int G, int N, int max_chain, float r2, float r_cut,
+                           int max_num_neighbors, const int* bond_rowptr, const int* bond_src, int* scratch, int* nbr,
+                           int* rowptr, int* col, int* edst, unsigned char* ebond, jamun_stream_t stream);
+
 /* Edge featurisation (arch/e3conv.py:110-127): for each CSR edge, rhat = (p[src]-p[dst])/|.| (so
  * sh = [1, sqrt3*rhat]) and the 32 Gaussian radial bases exp(-((d-mu_k)/step)^2)/1.12.
  * rhat: [cap,4] (x,y,z,d)  rb: [cap, JAMUN_NBASIS]  mu: [JAMUN_NBASIS]. */

@@ -29,6 +29,7 @@ _PROTOS = {
     "jamun_atom_embed": ([c_f] * 8 + [I] * 4 + [c_f, I, c_f, c_f], I),
     "jamun_center_scale": ([c_f, c_f, I, I, F, c_f, c_f, c_f], I),
     "jamun_radius_csr": ([c_f, c_f, c_f, I, F, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
+    "jamun_radius_csr_cells": ([c_f, c_f, I, I, I, F, F, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f], I),
     "jamun_edge_geom": ([c_f, c_f, c_f, c_f, I, I, c_f, F, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden_all": ([c_f, c_f, c_f, I, I, c_f, c_f, I, c_f, c_f], I),

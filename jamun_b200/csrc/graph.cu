@@ -101,6 +101,169 @@ __global__ void radius_kernel(const float* __restrict__ pos, const int* __restri
     }
 }
 
+// ---- K1 (long chains): cell-list neighbour search -------------------------------------------------------------------------------
+// One CTA per chain.  The chain's atoms are binned into cubic cells of edge >= r_cut held in shared memory (counting sort by
+// cell: count -> exclusive scan -> fill); a receiver then tests only the atoms of the 27 cells around its own with the same
+// unfused-fp32 predicate as the brute-force kernel, so the hit set is identical.  The reference's cap rule ("the first
+// max_hits hits scanning the chain in ascending index, self included, then self removed" -- torch_cluster's radius kernel,
+// SURVEY A.3) is restated as "the max_hits smallest hit indices": every thread keeps its hits in a sorted insertion buffer.
+// Neighbour lists go to a fixed-stride scratch (nbr [N][max_hits]) and are compacted into the CSR after the row scan, so the
+// search runs once.  Atomics are used on integer counters only and the per-receiver lists are sorted: the CSR is deterministic.
+constexpr int kCellMaxHits = 64;   // max_num_neighbors + 1 <= 64
+constexpr int kCellMaxCells = 4096;
+constexpr int kCellMaxAtoms = 8192;
+
+__global__ void __launch_bounds__(256)
+radius_cell_kernel(const float* __restrict__ pos, const int* __restrict__ chain_ptr, float r2, float r_cut, int max_hits,
+                   const int* __restrict__ bond_rowptr, int* __restrict__ count, int* __restrict__ nbr) {
+    extern __shared__ __align__(16) unsigned char cell_smem[];
+    const int c = blockIdx.x;
+    const int lo = chain_ptr[c], n = chain_ptr[c + 1] - lo;
+    if (n <= 0) return;
+    float* px = reinterpret_cast<float*>(cell_smem);  // [3][n] coordinates (SoA)
+    float* py = px + n;
+    float* pz = py + n;
+    int* cell_of = reinterpret_cast<int*>(pz + n);    // [n]
+    int* sorted = cell_of + n;                        // [n] atom indices (chain-local) grouped by cell
+    int* cstart = sorted + n;                         // [ncell + 1]
+    __shared__ float red[6][8];
+    __shared__ float bb[6];
+    __shared__ int dims[3];
+    __shared__ float cell_edge;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int a = tid; a < n; a += 256) {
+        const float x = pos[3 * (size_t)(lo + a)], y = pos[3 * (size_t)(lo + a) + 1], z = pos[3 * (size_t)(lo + a) + 2];
+        px[a] = x, py[a] = y, pz[a] = z;
+        mn[0] = fminf(mn[0], x), mn[1] = fminf(mn[1], y), mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x), mx[1] = fmaxf(mx[1], y), mx[2] = fmaxf(mx[2], z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        if (lane == 0) red[k][warp] = mn[k], red[3 + k][warp] = mx[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ext = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            float a = red[k][0], b = red[3 + k][0];
+            for (int w = 1; w < 8; ++w) a = fminf(a, red[k][w]), b = fmaxf(b, red[3 + k][w]);
+            bb[k] = a, bb[3 + k] = b;
+            ext = fmaxf(ext, b - a);
+        }
+        // cell edge: r_cut (slightly enlarged so that rounding of the cell index can never hide an in-range pair), grown
+        // until the grid fits the shared-memory budget
+        float edge = r_cut * 1.0001f + 1e-6f;
+        for (;;) {
+            int tot = 1;
+            for (int k = 0; k < 3; ++k) {
+                dims[k] = (int)floorf((bb[3 + k] - bb[k]) / edge) + 1;
+                tot *= dims[k];
+            }
+            if (tot <= kCellMaxCells) break;
+            edge *= 1.26f;
+        }
+        cell_edge = edge;
+    }
+    __syncthreads();
+    const int nx = dims[0], ny = dims[1], nz = dims[2], ncell = nx * ny * nz;
+    const float inv_edge = 1.0f / cell_edge;
+    for (int q = tid; q <= ncell; q += 256) cstart[q] = 0;
+    __syncthreads();
+    for (int a = tid; a < n; a += 256) {
+        const int cx = min(nx - 1, (int)((px[a] - bb[0]) * inv_edge)), cy = min(ny - 1, (int)((py[a] - bb[1]) * inv_edge)),
+                  cz = min(nz - 1, (int)((pz[a] - bb[2]) * inv_edge));
+        const int cid = (cz * ny + cy) * nx + cx;
+        cell_of[a] = cid;
+        atomicAdd(&cstart[cid + 1], 1);  // integer histogram: order-independent
+    }
+    __syncthreads();
+    if (warp == 0) {  // inclusive scan of the histogram by one warp (ncell <= 4096)
+        int carry = 0;
+        for (int base = 1; base <= ncell; base += 32) {
+            const int idx = base + lane;
+            int v = idx <= ncell ? cstart[idx] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (idx <= ncell) cstart[idx] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    // fill: cursor = cstart copy held in `count` scratch?  no global traffic: reuse cell_of as (cell id) and a second histogram
+    // pass with atomic cursors kept in the upper half of cstart's allocation
+    int* cursor = cstart + ncell + 1;
+    for (int q = tid; q < ncell; q += 256) cursor[q] = cstart[q];
+    __syncthreads();
+    for (int a = tid; a < n; a += 256) sorted[atomicAdd(&cursor[cell_of[a]], 1)] = a;
+    __syncthreads();
+    // search
+    for (int a = tid; a < n; a += 256) {
+        const float xi = px[a], yi = py[a], zi = pz[a];
+        const int cid = cell_of[a];
+        const int cx = cid % nx, cy = (cid / nx) % ny, cz = cid / (nx * ny);
+        int best[kCellMaxHits];  // ascending; best[cnt-1] is the largest kept index
+        int cnt = 0;
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= nz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= ny) continue;
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nx - 1);
+                const int row = (z * ny + y) * nx;
+                for (int q = cstart[row + x0]; q < cstart[row + x1 + 1]; ++q) {  // the x-neighbours are contiguous in `sorted`
+                    const int j = sorted[q];
+                    const float ddx = __fsub_rn(xi, px[j]), ddy = __fsub_rn(yi, py[j]), ddz = __fsub_rn(zi, pz[j]);
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                    if (!(d2 < r2)) continue;
+                    if (cnt == max_hits && j > best[cnt - 1]) continue;
+                    int k = cnt < max_hits ? cnt++ : cnt - 1;  // insertion into the sorted buffer (drops the largest when full)
+                    while (k > 0 && best[k - 1] > j) {
+                        best[k] = best[k - 1];
+                        --k;
+                    }
+                    best[k] = j;
+                }
+            }
+        }
+        const int i = lo + a;
+        int m = 0;
+        for (int k = 0; k < cnt; ++k)
+            if (best[k] != a) nbr[(size_t)i * max_hits + m++] = lo + best[k];
+        count[i] = m + (bond_rowptr ? bond_rowptr[i + 1] - bond_rowptr[i] : 0);
+    }
+}
+
+// rows of the fixed-stride neighbour scratch -> CSR (radial sources ascending, then the bonded in-edges in their original order)
+__global__ void radius_compact_kernel(const int* __restrict__ nbr, int max_hits, const int* __restrict__ bond_rowptr,
+                                      const int* __restrict__ bond_src, const int* __restrict__ rowptr, int N, int* __restrict__ col,
+                                      int* __restrict__ edst, unsigned char* __restrict__ ebond) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int w = rowptr[i];
+    const int b0 = bond_rowptr ? bond_rowptr[i] : 0, b1 = bond_rowptr ? bond_rowptr[i + 1] : 0;
+    const int m = rowptr[i + 1] - w - (b1 - b0);
+    for (int k = 0; k < m; ++k) {
+        col[w + k] = nbr[(size_t)i * max_hits + k];
+        edst[w + k] = i;
+        ebond[w + k] = 0;
+    }
+    for (int b = b0; b < b1; ++b) {
+        col[w + m + b - b0] = bond_src[b];
+        edst[w + m + b - b0] = i;
+        ebond[w + m + b - b0] = 1;
+    }
+}
+
 // single-CTA exclusive scan; out[n] = total.  n <= a few 1e5, off the critical path.
 __global__ void exclusive_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
     __shared__ int warp_tot[32];
@@ -369,6 +532,39 @@ extern "C" int jamun_radius_csr(const float* pos, const int* chain_of, const int
     if (N > 0) {
         radius_kernel<true><<<blocks, 128, 0, s>>>(pos, chain_of, chain_ptr, N, r2, max_hits, bond_rowptr, bond_src,
                                                    nullptr, rowptr, col, edst, ebond);
+        JB_CHECK_LAUNCH();
+    }
+    return JAMUN_OK;
+}
+
+// Cell-list form of jamun_radius_csr for long chains (same CSR, bit for bit).  nbr: [N, max_num_neighbors + 1] int scratch;
+// max_chain: longest chain of the batch (host-side constant of the topology).
+extern "C" int jamun_radius_csr_cells(const float* pos, const int* chain_ptr, int G, int N, int max_chain, float r2, float r_cut,
+                                      int max_num_neighbors, const int* bond_rowptr, const int* bond_src, int* scratch, int* nbr,
+                                      int* rowptr, int* col, int* edst, unsigned char* ebond, jamun_stream_t stream) {
+    JB_CHECK_ARG(pos && chain_ptr && scratch && nbr && rowptr && col && edst && ebond, "null argument");
+    JB_CHECK_ARG(max_num_neighbors >= 0 && max_num_neighbors + 1 <= kCellMaxHits, "the cell-list search needs 0 <= max_num_neighbors < 64");
+    JB_CHECK_ARG(max_chain <= kCellMaxAtoms, "chains longer than 8192 atoms: use jamun_radius_csr");
+    cudaStream_t s = jb::as_stream(stream);
+    const int max_hits = max_num_neighbors + 1;
+    if (N > 0 && G > 0) {
+        const size_t smem = (size_t)max_chain * 20 + (size_t)(2 * kCellMaxCells + 2) * sizeof(int);
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(radius_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                jb::set_error("jamun_radius_csr_cells: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+                return JAMUN_ECUDA;
+            }
+            smem_set = smem;
+        }
+        radius_cell_kernel<<<G, 256, smem, s>>>(pos, chain_ptr, r2, r_cut, max_hits, bond_rowptr, scratch, nbr);
+        JB_CHECK_LAUNCH();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, s>>>(scratch, rowptr, N);
+    JB_CHECK_LAUNCH();
+    if (N > 0) {
+        radius_compact_kernel<<<(N + 127) / 128, 128, 0, s>>>(nbr, max_hits, bond_rowptr, bond_src, rowptr, N, col, edst, ebond);
         JB_CHECK_LAUNCH();
     }
     return JAMUN_OK;

@@ -24,6 +24,7 @@ CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
 # aggregate builder of the tensor-core path: "tc" = tcgen05 per-node products (jamun_conv_build_tc) with the 0e(x)1e->1e
 # gather (jamun_conv_p2) on a side stream; "ffma" = the FP32-pipe builder jamun_conv_build_a (exact fp32 aggregate)
 BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
+CELL_LIST_MIN_CHAIN = 64  # chains longer than this use the cell-list neighbour search (jamun_radius_csr_cells)
 Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
 
@@ -47,6 +48,7 @@ class Topology:
         ptr = torch.zeros(G + 1, dtype=torch.long)
         ptr[1:] = torch.cumsum(counts, 0)
         self.N, self.G = N, G
+        self.max_chain = int(counts.max().item()) if N else 0
         self.device = dev
         self.max_num_neighbors = max_num_neighbors
         self.chain_ptr = ptr.to(dev, torch.int32)
@@ -113,8 +115,16 @@ class Topology:
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
         r2 = float(torch.tensor(float(r_cut) * float(r_cut), dtype=torch.float64).to(torch.float32))
         mnn = -1 if self.max_num_neighbors is None else int(self.max_num_neighbors)
-        ops.radius_csr(pos, self.chain_of, self.chain_ptr, r2, mnn, self.bond_rowptr, self.bond_src, self.scratch,
-                       self.rowptr, self.col, self.edst, self.ebond)
+        impl = os.environ.get("JAMUN_B200_RADIUS", "auto")  # "brute" | "cells" | "auto" (cell list for chains of > 64 atoms)
+        cells_ok = 0 <= mnn < 64 and self.max_chain <= 8192
+        if cells_ok and (impl == "cells" or (impl == "auto" and self.max_chain > CELL_LIST_MIN_CHAIN)):
+            if getattr(self, "nbr_tmp", None) is None:
+                self.nbr_tmp = torch.zeros(max(self.N, 1) * (mnn + 1), dtype=torch.int32, device=self.device)
+            ops.radius_csr_cells(pos, self.chain_ptr, self.max_chain, r2, float(r_cut), mnn, self.bond_rowptr, self.bond_src,
+                                 self.scratch, self.nbr_tmp, self.rowptr, self.col, self.edst, self.ebond)
+        else:
+            ops.radius_csr(pos, self.chain_of, self.chain_ptr, r2, mnn, self.bond_rowptr, self.bond_src, self.scratch,
+                           self.rowptr, self.col, self.edst, self.ebond)
         ops.csr_by_source(self.rowptr, self.col, self.scratch, self.src_rowptr, self.src_eid)
         self.csr_generation += 1
 

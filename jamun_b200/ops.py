@@ -86,6 +86,18 @@ def radius_csr(pos, chain_of, chain_ptr, r2: float, max_num_neighbors: int, bond
     _count(3)
 
 
+def radius_csr_cells(pos, chain_ptr, max_chain: int, r2: float, r_cut: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch,
+                     nbr, rowptr, col, edst, ebond):
+    N, G = pos.shape[0], chain_ptr.numel() - 1
+    i32 = torch.int32
+    rc = _lib.lib().jamun_radius_csr_cells(_ptr(pos), _ptr(chain_ptr, i32), G, N, int(max_chain), float(r2), float(r_cut),
+                                           int(max_num_neighbors), _ptr(bond_rowptr, i32), _ptr(bond_src, i32), _ptr(scratch, i32),
+                                           _ptr(nbr, i32), _ptr(rowptr, i32), _ptr(col, i32), _ptr(edst, i32),
+                                           _ptr(ebond, torch.uint8), _stream())
+    _lib.check(rc, "jamun_radius_csr_cells")
+    _count(3)
+
+
 def edge_geom(p, rowptr, col, edst, mu, step: float, rhat, rb):
     N, cap = p.shape[0], col.numel()
     i32 = torch.int32

@@ -45,7 +45,7 @@ def test_center_scale(sizes):
 
 
 @pytest.mark.parametrize("sizes,cap", [([22, 15, 9, 30], 32), ([60, 57, 3, 1, 2], 32), ([150, 40], 32), ([150, 40], 8),
-                                       ([150, 40], None), ([300], 32)])
+                                       ([150, 40], None), ([300], 32), ([1000] * 4, 32), ([3000], 32), ([300, 5, 70, 1, 2], 8)])
 def test_radius_csr_bit_exact(sizes, cap):
     """Edge sets identical to the oracle's radius_graph + bonded concatenation (compared after sorting), and the
     within-row order is the documented one (radial ascending, then bonded)."""
@@ -72,6 +72,23 @@ def test_radius_csr_bit_exact(sizes, cap):
     assert torch.equal(ei.cpu(), ref[:, order])
     rowptr = topo.rowptr.cpu().long()
     assert torch.equal(rowptr[1:] - rowptr[:-1], torch.bincount(ref[1], minlength=N))
+
+
+@pytest.mark.parametrize("sizes,cap", [([22, 15, 9, 30, 1, 2], 32), ([1000, 200, 64, 65], 32), ([500] * 3, 5)])
+def test_radius_cell_list_equals_brute_force(sizes, cap, monkeypatch):
+    """The cell-list search (long chains) and the ascending brute-force scan (short chains) emit the same CSR, bit for bit."""
+    from jamun_b200 import data, engine, synthetic
+
+    t = synthetic.make_tensors(sizes)
+    out = {}
+    for impl in ("brute", "cells"):
+        monkeypatch.setenv("JAMUN_B200_RADIUS", impl)
+        topo = engine.Topology(data.Batch.from_tensors(t), "cuda", max_num_neighbors=cap)
+        topo.build_csr(t["pos"].cuda(), 0.5872642993927002)
+        E = int(topo.rowptr[-1])
+        out[impl] = (topo.rowptr.cpu(), topo.col[:E].cpu(), topo.edst[:E].cpu(), topo.ebond[:E].cpu())
+    for a, b in zip(out["brute"], out["cells"]):
+        assert torch.equal(a, b)
 
 
 def test_radius_empty_and_single():
