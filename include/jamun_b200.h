@@ -342,6 +342,11 @@ int jamun_loss_bwd(const float* xhat, const float* x, const int* chain_of, const
  * H = sum y_c x_c^T (one-sided Jacobi in fp64).  rot (optional): [G, 9] rotation matrices. */
 int jamun_kabsch_align(const float* y, const float* x, const int* chain_ptr, int G, float* out, float* rot,
                        jamun_stream_t stream);
+/* Per chain: (sum of |x_i - x_j|^2 over pairs i > j with |x_i - x_j| < cutoff, number of such pairs) as two doubles
+ * (utils/average_squared_distance.py:154-177; cutoff <= 0: all pairs).  sums: [G, 2] double. */
+int jamun_avg_sq_dist(const float* pos, const int* chain_ptr, int G, float cutoff, double* sums, jamun_stream_t stream);
+/* ema = decay*ema + (1-decay)*p over a flat buffer (callbacks/_ema.py, EMAOptimizer). */
+int jamun_ema_update(float* ema, const float* p, float decay, long long n, jamun_stream_t stream);
 /* out[:, col0 : col0+n] += add[:, :n]. */
 int jamun_add_cols(float* out, int ld, int col0, const float* add, int add_ld, int n, int N, jamun_stream_t stream);
 

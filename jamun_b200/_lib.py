@@ -61,6 +61,8 @@ _PROTOS = {
     "jamun_loss_fwd": ([c_f, c_f, c_f, I, F, F, c_f, c_f, c_f, c_f, c_f], I),
     "jamun_loss_bwd": ([c_f, c_f, c_f, c_f, I, F, c_f, c_f, c_f, c_f], I),
     "jamun_kabsch_align": ([c_f, c_f, c_f, I, c_f, c_f, c_f], I),
+    "jamun_avg_sq_dist": ([c_f, c_f, I, F, c_f, c_f], I),
+    "jamun_ema_update": ([c_f, c_f, F, C.c_longlong, c_f], I),
     "jamun_add_cols": ([c_f, I, I, c_f, I, I, I, c_f], I),
     "jamun_pack_rows": ([c_f, I, I, I, I, I, c_f, c_f], I),
     "jamun_gemm_tf32x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),

@@ -112,6 +112,7 @@ __global__ void radius_kernel(const float* __restrict__ pos, const int* __restri
 constexpr int kCellMaxHits = 64;   // max_num_neighbors + 1 <= 64
 constexpr int kCellMaxCells = 4096;
 constexpr int kCellMaxAtoms = 8192;
+constexpr int kHitBuf = 160;       // per-warp hit buffer (>= max_hits + 32, multiple of 32)
 
 __global__ void __launch_bounds__(256)
 radius_cell_kernel(const float* __restrict__ pos, const int* __restrict__ chain_ptr, float r2, float r_cut, int max_hits,
@@ -205,13 +206,36 @@ radius_cell_kernel(const float* __restrict__ pos, const int* __restrict__ chain_
     __syncthreads();
     for (int a = tid; a < n; a += 256) sorted[atomicAdd(&cursor[cell_of[a]], 1)] = a;
     __syncthreads();
-    // search
-    for (int a = tid; a < n; a += 256) {
+    // search: one warp per receiver.  Lanes test 32 candidates at a time and append the hits to a per-warp buffer; the hits are
+    // then ranked by counting (rank = number of smaller hit indices), which orders them without a sort and makes "keep the
+    // max_hits smallest" a comparison of the rank.  A nearly full buffer is compacted the same way and the scan continues.
+    int* hitbuf = cursor + ncell + (size_t)warp * kHitBuf;  // [8 warps][kHitBuf]
+    for (int a = warp; a < n; a += 8) {
         const float xi = px[a], yi = py[a], zi = pz[a];
         const int cid = cell_of[a];
         const int cx = cid % nx, cy = (cid / nx) % ny, cz = cid / (nx * ny);
-        int best[kCellMaxHits];  // ascending; best[cnt-1] is the largest kept index
         int cnt = 0;
+        auto compact = [&](bool final_pass) {
+            // rank every buffered hit; keep those of rank < max_hits at position rank (ascending)
+            __syncwarp();
+            int keep_val[kHitBuf / 32], keep_rank[kHitBuf / 32];
+#pragma unroll
+            for (int t = 0; t < kHitBuf / 32; ++t) {
+                const int idx = lane + 32 * t;
+                keep_val[t] = idx < cnt ? hitbuf[idx] : 0x7fffffff;
+                int rk = 0;
+                if (idx < cnt)
+                    for (int q = 0; q < cnt; ++q) rk += hitbuf[q] < keep_val[t];
+                keep_rank[t] = idx < cnt ? rk : 0x7fffffff;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < kHitBuf / 32; ++t)
+                if (keep_rank[t] < max_hits) hitbuf[keep_rank[t]] = keep_val[t];
+            cnt = min(cnt, max_hits);
+            __syncwarp();
+            (void)final_pass;
+        };
         for (int dz = -1; dz <= 1; ++dz) {
             const int z = cz + dz;
             if (z < 0 || z >= nz) continue;
@@ -220,26 +244,36 @@ radius_cell_kernel(const float* __restrict__ pos, const int* __restrict__ chain_
                 if (y < 0 || y >= ny) continue;
                 const int x0 = max(cx - 1, 0), x1 = min(cx + 1, nx - 1);
                 const int row = (z * ny + y) * nx;
-                for (int q = cstart[row + x0]; q < cstart[row + x1 + 1]; ++q) {  // the x-neighbours are contiguous in `sorted`
-                    const int j = sorted[q];
-                    const float ddx = __fsub_rn(xi, px[j]), ddy = __fsub_rn(yi, py[j]), ddz = __fsub_rn(zi, pz[j]);
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
-                    if (!(d2 < r2)) continue;
-                    if (cnt == max_hits && j > best[cnt - 1]) continue;
-                    int k = cnt < max_hits ? cnt++ : cnt - 1;  // insertion into the sorted buffer (drops the largest when full)
-                    while (k > 0 && best[k - 1] > j) {
-                        best[k] = best[k - 1];
-                        --k;
+                const int q1 = cstart[row + x1 + 1];
+                for (int q0 = cstart[row + x0]; q0 < q1; q0 += 32) {  // the x-neighbours are contiguous in `sorted`
+                    const int q = q0 + lane;
+                    bool hit = false;
+                    int j = 0;
+                    if (q < q1) {
+                        j = sorted[q];
+                        const float ddx = __fsub_rn(xi, px[j]), ddy = __fsub_rn(yi, py[j]), ddz = __fsub_rn(zi, pz[j]);
+                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+                        hit = d2 < r2;
                     }
-                    best[k] = j;
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (cnt + 32 > kHitBuf) compact(false);
+                    if (hit) hitbuf[cnt + __popc(m & ((1u << lane) - 1))] = j;
+                    cnt += __popc(m);
                 }
             }
         }
+        compact(true);
+        // hitbuf[0 .. cnt) ascending; drop self, write the row
         const int i = lo + a;
-        int m = 0;
-        for (int k = 0; k < cnt; ++k)
-            if (best[k] != a) nbr[(size_t)i * max_hits + m++] = lo + best[k];
-        count[i] = m + (bond_rowptr ? bond_rowptr[i + 1] - bond_rowptr[i] : 0);
+        int self_pos = cnt;
+        for (int t = lane; t < cnt; t += 32)
+            if (hitbuf[t] == a) self_pos = t;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) self_pos = min(self_pos, __shfl_xor_sync(0xffffffffu, self_pos, o));
+        for (int t = lane; t < cnt; t += 32)
+            if (t != self_pos) nbr[(size_t)i * max_hits + (t < self_pos ? t : t - 1)] = lo + hitbuf[t];
+        if (lane == 0) count[i] = cnt - (self_pos < cnt ? 1 : 0) + (bond_rowptr ? bond_rowptr[i + 1] - bond_rowptr[i] : 0);
+        __syncwarp();
     }
 }
 
@@ -363,18 +397,37 @@ __global__ void fill_sources_kernel(const int* __restrict__ rowptr, const int* _
 // The atomic cursor above leaves each source's out-edge list in arrival order; an insertion sort of every (short) list makes
 // src_eid ascending per source, i.e. bit-reproducible, so source-major reductions (backward dx) are deterministic.
 __global__ void sort_sources_kernel(const int* __restrict__ src_rowptr, int N, int* __restrict__ src_eid) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per source: out-degree <= 64 is ranked by counting in registers (two entries per lane); longer lists fall
+    // back to an insertion sort by lane 0
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= N) return;
     const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
-    for (int a = s0 + 1; a < s1; ++a) {
-        const int v = src_eid[a];
-        int b = a - 1;
-        while (b >= s0 && src_eid[b] > v) {
-            src_eid[b + 1] = src_eid[b];
-            --b;
+    const int n = s1 - s0;
+    if (n <= 1) return;
+    if (n <= 64) {
+        const int v0 = lane < n ? src_eid[s0 + lane] : 0x7fffffff, v1 = lane + 32 < n ? src_eid[s0 + 32 + lane] : 0x7fffffff;
+        int r0 = 0, r1 = 0;
+        for (int q = 0; q < 32; ++q) {
+            const int a = __shfl_sync(0xffffffffu, v0, q), b = __shfl_sync(0xffffffffu, v1, q);
+            r0 += (a < v0) + (b < v0);
+            r1 += (a < v1) + (b < v1);
         }
-        src_eid[b + 1] = v;
+        __syncwarp();
+        if (lane < n) src_eid[s0 + r0] = v0;
+        if (lane + 32 < n) src_eid[s0 + r1] = v1;
+        return;
     }
+    if (lane == 0)
+        for (int a = s0 + 1; a < s1; ++a) {
+            const int v = src_eid[a];
+            int b = a - 1;
+            while (b >= s0 && src_eid[b] > v) {
+                src_eid[b + 1] = src_eid[b];
+                --b;
+            }
+            src_eid[b + 1] = v;
+        }
 }
 
 // ---- K2b: radial MLP hidden layer: h[e][o] = SiLU(sum_k w0rt[k][o] rb[e][k] + b0eff[flag][o]) --------
@@ -548,7 +601,7 @@ extern "C" int jamun_radius_csr_cells(const float* pos, const int* chain_ptr, in
     cudaStream_t s = jb::as_stream(stream);
     const int max_hits = max_num_neighbors + 1;
     if (N > 0 && G > 0) {
-        const size_t smem = (size_t)max_chain * 20 + (size_t)(2 * kCellMaxCells + 2) * sizeof(int);
+        const size_t smem = (size_t)max_chain * 20 + (size_t)(2 * kCellMaxCells + 2 + 8 * kHitBuf) * sizeof(int);
         static size_t smem_set = 0;
         if (smem > smem_set) {
             cudaError_t e = cudaFuncSetAttribute(radius_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -582,7 +635,7 @@ extern "C" int jamun_csr_by_source(const int* rowptr, const int* col, int N, int
     exclusive_scan_kernel<<<1, 1024, 0, s>>>(scratch, src_rowptr, N);
     cudaMemsetAsync(scratch, 0, (size_t)(N + 1) * sizeof(int), s);
     fill_sources_kernel<<<blocks, 256, 0, s>>>(rowptr, col, N, src_rowptr, scratch, src_eid);
-    sort_sources_kernel<<<(N + 127) / 128, 128, 0, s>>>(src_rowptr, N, src_eid);
+    sort_sources_kernel<<<(int)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(src_rowptr, N, src_eid);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

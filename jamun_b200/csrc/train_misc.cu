@@ -373,6 +373,46 @@ kabsch_kernel(const float* __restrict__ y, const float* __restrict__ x, const in
     if (rot && lane < 9) rot[9 * c + lane] = R[lane];
 }
 
+// ---- average squared pair distance below a cutoff, per chain (utils/average_squared_distance.py:154-177) -------------------------
+// sums[c] = (sum_{i>j, |x_i-x_j| < cutoff} |x_i-x_j|^2, number of such pairs); one CTA per chain, fixed-order reduction.
+__global__ void __launch_bounds__(256)
+avg_sq_dist_kernel(const float* __restrict__ pos, const int* __restrict__ chain_ptr, float cutoff, double* __restrict__ sums) {
+    __shared__ double s_sum[8], s_cnt[8];
+    const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a0 = chain_ptr[c], a1 = chain_ptr[c + 1];
+    double sum = 0.0, cnt = 0.0;
+    for (int i = a0 + threadIdx.x; i < a1; i += 256) {
+        const float xi = pos[3 * (size_t)i], yi = pos[3 * (size_t)i + 1], zi = pos[3 * (size_t)i + 2];
+        for (int j = a0; j < i; ++j) {
+            const float dx = xi - pos[3 * (size_t)j], dy = yi - pos[3 * (size_t)j + 1], dz = zi - pos[3 * (size_t)j + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (cutoff <= 0.f || sqrtf(d2) < cutoff) {
+                sum += (double)d2;
+                cnt += 1.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) s_sum[warp] = sum, s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) a += s_sum[w], b += s_cnt[w];
+        sums[2 * c] = a;
+        sums[2 * c + 1] = b;
+    }
+}
+
+// ema = decay * ema + (1 - decay) * p over a flat parameter buffer (callbacks/_ema.py: EMAOptimizer.update)
+__global__ void ema_update_kernel(float* __restrict__ ema, const float* __restrict__ p, float decay, size_t n) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        ema[t] = fmaf(decay, ema[t] - p[t], p[t]);
+}
+
 // out[:, col0 : col0 + n] += add[:, :n]
 __global__ void add_cols_kernel(float* __restrict__ out, int ld, int col0, const float* __restrict__ add, int add_ld, int n, int N) {
     const size_t total = (size_t)N * n;
@@ -507,6 +547,22 @@ extern "C" int jamun_kabsch_align(const float* y, const float* x, const int* cha
     JB_CHECK_ARG(y && x && chain_ptr && out, "null argument");
     if (G == 0) return JAMUN_OK;
     kabsch_kernel<<<(G * 32 + 255) / 256, 256, 0, jb::as_stream(stream)>>>(y, x, chain_ptr, G, out, rot);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_avg_sq_dist(const float* pos, const int* chain_ptr, int G, float cutoff, double* sums, jamun_stream_t stream) {
+    JB_CHECK_ARG(pos && chain_ptr && sums, "null argument");
+    if (G == 0) return JAMUN_OK;
+    avg_sq_dist_kernel<<<G, 256, 0, jb::as_stream(stream)>>>(pos, chain_ptr, cutoff, sums);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_ema_update(float* ema, const float* p, float decay, long long n, jamun_stream_t stream) {
+    JB_CHECK_ARG(ema && p && n >= 0, "bad argument");
+    if (n == 0) return JAMUN_OK;
+    ema_update_kernel<<<ew_blocks((size_t)n), 256, 0, jb::as_stream(stream)>>>(ema, p, decay, (size_t)n);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

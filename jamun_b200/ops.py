@@ -503,3 +503,19 @@ def add_cols(out, col0: int, add, n: int):
     rc = _lib.lib().jamun_add_cols(_ptr(out), out.stride(0), col0, _ptr(add), add.stride(0), n, out.shape[0], _stream())
     _lib.check(rc, "jamun_add_cols")
     _count()
+
+
+def avg_sq_dist(pos, chain_ptr, cutoff: float):
+    """[G, 2] double: per chain (sum of squared pair distances below the cutoff, number of such pairs)."""
+    G = chain_ptr.numel() - 1
+    sums = torch.zeros(G, 2, dtype=torch.float64, device=pos.device)
+    rc = _lib.lib().jamun_avg_sq_dist(_ptr(pos), _ptr(chain_ptr, torch.int32), G, float(cutoff), sums.data_ptr(), _stream())
+    _lib.check(rc, "jamun_avg_sq_dist")
+    _count()
+    return sums
+
+
+def ema_update(ema, p, decay: float):
+    rc = _lib.lib().jamun_ema_update(_ptr(ema), _ptr(p), float(decay), ema.numel(), _stream())
+    _lib.check(rc, "jamun_ema_update")
+    _count()
