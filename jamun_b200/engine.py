@@ -24,7 +24,7 @@ CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
 # aggregate builder of the tensor-core path: "tc" = tcgen05 per-node products (jamun_conv_build_tc) with the 0e(x)1e->1e
 # gather (jamun_conv_p2) on a side stream; "ffma" = the FP32-pipe builder jamun_conv_build_a (exact fp32 aggregate)
 BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
-CELL_LIST_MIN_CHAIN = 1536  # longer chains use the cell-list search; measured on B200 (tools/time_radius.py): n=1000 brute 0.97 ms vs cells 1.8 ms per 512 k atoms, the O(n^2) scan loses beyond ~2 k atoms
+CELL_LIST_MIN_CHAIN = 2560  # longer chains use the cell-list search.  Measured on B200 (tools/time_radius.py, 512 k atoms, CSR build incl. the out-edge index): n=1000 brute 2.37 ms / cells 2.99 ms; n=3000 3.89 / 3.75; n=6000 6.21 / 5.59 -- the ascending scan stops after 33 hits, so the O(n^2) bound only bites beyond ~2.5 k atoms
 Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
 

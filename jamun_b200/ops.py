@@ -7,7 +7,7 @@ device memory.  CPU tensors are rejected: there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import List, Optional
 
 import torch
 
@@ -16,6 +16,20 @@ from . import _lib
 S, V, HID, GATE_IN, S0, EDGE_HID, NBASIS = 120, 32, 216, 248, 56, 64, 32
 
 LAUNCHES = 0  # number of kernel launches issued through this module (bench.py's gpu_launches claim)
+
+Tensor = torch.Tensor
+_T = torch.ops.jamun_b200
+
+
+def _op(name: str, mutates=()):
+    """Register a launcher as the torch.library operator jamun_b200::<name> (SURVEY 8(b): thin custom-op layer over the C ABI).
+    Launchers write into caller-owned buffers (declared in `mutates`) and return nothing, so their fake implementation is
+    empty; operators that allocate their result are registered with an explicit fake below."""
+    def deco(fn):
+        op = torch.library.custom_op(f"jamun_b200::{name}", fn, mutates_args=tuple(mutates), device_types="cuda")
+        op.register_fake(lambda *a, **k: None)
+        return op
+    return deco
 
 
 def _count(n: int = 1) -> None:
@@ -39,20 +53,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def noise_mlp(w1, b1, w2, b2, c_noise: float, apply_sigmoid: bool, out=None):
+@_op("noise_mlp_", mutates=("out",))
+def _noise_mlp(w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c_noise: float, apply_sigmoid: bool, out: Tensor) -> None:
     n = b1.numel()
-    out = torch.empty(n, device=b1.device, dtype=torch.float32) if out is None else out
     rc = _lib.lib().jamun_noise_mlp(_ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), float(c_noise), n, int(apply_sigmoid),
                                     _ptr(out), _stream())
     _lib.check(rc, "jamun_noise_mlp")
     _count()
+
+
+def noise_mlp(w1, b1, w2, b2, c_noise: float, apply_sigmoid: bool, out=None):
+    out = torch.empty(b1.numel(), device=b1.device, dtype=torch.float32) if out is None else out
+    _T.noise_mlp_(w1, b1, w2, b2, float(c_noise), bool(apply_sigmoid), out)
     return out
 
 
-def atom_embed(idx, tabs, scale, out=None):
+@_op("atom_embed_", mutates=("out",))
+def _atom_embed(idx: List[Optional[Tensor]], tabs: List[Tensor], scale: Optional[Tensor], out: Tensor) -> None:
     N = idx[0].numel()
     dims = [t.shape[1] for t in tabs]
-    out = torch.empty(N, sum(dims), device=tabs[0].device, dtype=torch.float32) if out is None else out
     i32 = torch.int32
     rc = _lib.lib().jamun_atom_embed(_ptr(idx[0], i32), _ptr(idx[1], i32), _ptr(idx[2], i32),
                                      _ptr(idx[3], i32) if idx[3] is not None else None,
@@ -60,22 +79,33 @@ def atom_embed(idx, tabs, scale, out=None):
                                      _ptr(scale), N, _ptr(out), _stream())
     _lib.check(rc, "jamun_atom_embed")
     _count()
+
+
+def atom_embed(idx, tabs, scale, out=None):
+    out = torch.empty(idx[0].numel(), sum(t.shape[1] for t in tabs), device=tabs[0].device, dtype=torch.float32) if out is None else out
+    _T.atom_embed_(list(idx), list(tabs), scale, out)
     return out
 
 
-def center_scale(y, chain_ptr, c_in: float, ybar=None, p=None, center: bool = True):
+@_op("center_scale_", mutates=("ybar", "p"))
+def _center_scale(y: Tensor, chain_ptr: Tensor, c_in: float, ybar: Tensor, p: Tensor, center: bool) -> None:
     G = chain_ptr.numel() - 1
-    ybar = torch.empty_like(y) if ybar is None else ybar
-    p = torch.empty_like(y) if p is None else p
     rc = _lib.lib().jamun_center_scale(_ptr(y), _ptr(chain_ptr, torch.int32), G, int(center), float(c_in), _ptr(ybar), _ptr(p),
                                        _stream())
     _lib.check(rc, "jamun_center_scale")
     _count()
+
+
+def center_scale(y, chain_ptr, c_in: float, ybar=None, p=None, center: bool = True):
+    ybar = torch.empty_like(y) if ybar is None else ybar
+    p = torch.empty_like(y) if p is None else p
+    _T.center_scale_(y, chain_ptr, float(c_in), ybar, p, bool(center))
     return ybar, p
 
 
-def radius_csr(pos, chain_of, chain_ptr, r2: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch, rowptr,
-               col, edst, ebond):
+@_op("radius_csr", mutates=("scratch", "rowptr", "col", "edst", "ebond"))
+def _radius_csr(pos: Tensor, chain_of: Tensor, chain_ptr: Tensor, r2: float, max_num_neighbors: int, bond_rowptr: Tensor,
+                bond_src: Tensor, scratch: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, ebond: Tensor) -> None:
     N = pos.shape[0]
     i32 = torch.int32
     rc = _lib.lib().jamun_radius_csr(_ptr(pos), _ptr(chain_of, i32), _ptr(chain_ptr, i32), N, float(r2),
@@ -86,8 +116,14 @@ def radius_csr(pos, chain_of, chain_ptr, r2: float, max_num_neighbors: int, bond
     _count(3)
 
 
-def radius_csr_cells(pos, chain_ptr, max_chain: int, r2: float, r_cut: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch,
-                     nbr, rowptr, col, edst, ebond):
+def radius_csr(pos, chain_of, chain_ptr, r2: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch, rowptr, col, edst, ebond):
+    _T.radius_csr(pos, chain_of, chain_ptr, float(r2), int(max_num_neighbors), bond_rowptr, bond_src, scratch, rowptr, col, edst, ebond)
+
+
+@_op("radius_csr_cells", mutates=("scratch", "nbr", "rowptr", "col", "edst", "ebond"))
+def _radius_csr_cells(pos: Tensor, chain_ptr: Tensor, max_chain: int, r2: float, r_cut: float, max_num_neighbors: int,
+                      bond_rowptr: Tensor, bond_src: Tensor, scratch: Tensor, nbr: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor,
+                      ebond: Tensor) -> None:
     N, G = pos.shape[0], chain_ptr.numel() - 1
     i32 = torch.int32
     rc = _lib.lib().jamun_radius_csr_cells(_ptr(pos), _ptr(chain_ptr, i32), G, N, int(max_chain), float(r2), float(r_cut),
@@ -98,7 +134,14 @@ def radius_csr_cells(pos, chain_ptr, max_chain: int, r2: float, r_cut: float, ma
     _count(3)
 
 
-def edge_geom(p, rowptr, col, edst, mu, step: float, rhat, rb):
+def radius_csr_cells(pos, chain_ptr, max_chain: int, r2: float, r_cut: float, max_num_neighbors: int, bond_rowptr, bond_src, scratch,
+                     nbr, rowptr, col, edst, ebond):
+    _T.radius_csr_cells(pos, chain_ptr, int(max_chain), float(r2), float(r_cut), int(max_num_neighbors), bond_rowptr, bond_src, scratch,
+                        nbr, rowptr, col, edst, ebond)
+
+
+@_op("edge_geom", mutates=("rhat", "rb"))
+def _edge_geom(p: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, mu: Tensor, step: float, rhat: Tensor, rb: Tensor) -> None:
     N, cap = p.shape[0], col.numel()
     i32 = torch.int32
     rc = _lib.lib().jamun_edge_geom(_ptr(p), _ptr(rowptr, i32), _ptr(col, i32), _ptr(edst, i32), N, cap, _ptr(mu),
@@ -107,7 +150,12 @@ def edge_geom(p, rowptr, col, edst, mu, step: float, rhat, rb):
     _count()
 
 
-def edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h):
+def edge_geom(p, rowptr, col, edst, mu, step: float, rhat, rb):
+    _T.edge_geom(p, rowptr, col, edst, mu, float(step), rhat, rb)
+
+
+@_op("edge_radial_hidden", mutates=("h",))
+def _edge_radial_hidden(rb: Tensor, ebond: Tensor, rowptr: Tensor, w0r: Tensor, b0eff: Tensor, h: Tensor) -> None:
     N, cap = rowptr.numel() - 1, ebond.numel()
     rc = _lib.lib().jamun_edge_radial_hidden(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap,
                                              _ptr(w0r), _ptr(b0eff), _ptr(h), _stream())
@@ -115,7 +163,12 @@ def edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h):
     _count()
 
 
-def edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all):
+def edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h):
+    _T.edge_radial_hidden(rb, ebond, rowptr, w0r, b0eff, h)
+
+
+@_op("edge_radial_hidden_all", mutates=("h_all",))
+def _edge_radial_hidden_all(rb: Tensor, ebond: Tensor, rowptr: Tensor, w0r_all: Tensor, b0eff_all: Tensor, h_all: Tensor) -> None:
     N, cap, layers = rowptr.numel() - 1, ebond.numel(), w0r_all.shape[0]
     assert h_all.shape[0] == layers and h_all.shape[1] == cap
     rc = _lib.lib().jamun_edge_radial_hidden_all(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap,
@@ -124,7 +177,13 @@ def edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all):
     _count()
 
 
-def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: float, alpha1: float, out):
+def edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all):
+    _T.edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all)
+
+
+@_op("conv_fwd_simt", mutates=("out",))
+def _conv_fwd(x: Tensor, s_in: int, v_in: int, rowptr: Tensor, col: Tensor, h: Tensor, rhat: Tensor, m0: Tensor, m1: Tensor,
+              alpha0: float, alpha1: float, out: Tensor) -> None:
     N = x.shape[0]
     assert x.shape[1] == s_in + 3 * v_in and out.shape == (N, GATE_IN)
     i32 = torch.int32
@@ -132,6 +191,10 @@ def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: floa
                                    _ptr(m0), _ptr(m1), float(alpha0), float(alpha1), N, _ptr(out), _stream())
     _lib.check(rc, "jamun_conv_fwd")
     _count()
+
+
+def conv_fwd(x, s_in: int, v_in: int, rowptr, col, h, rhat, m0, m1, alpha0: float, alpha1: float, out):
+    _T.conv_fwd_simt(x, int(s_in), int(v_in), rowptr, col, h, rhat, m0, m1, float(alpha0), float(alpha1), out)
     return out
 
 
@@ -163,7 +226,8 @@ def conv_p2(rowptr, src_rowptr, src_eid, h, rhat, y, t_edge, p2_ptr: int, p2_ld:
     _count(2 if p2_ptr else 1)
 
 
-def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
+@_op("csr_by_source", mutates=("scratch", "src_rowptr", "src_eid"))
+def _csr_by_source(rowptr: Tensor, col: Tensor, scratch: Tensor, src_rowptr: Tensor, src_eid: Tensor) -> None:
     i32 = torch.int32
     rc = _lib.lib().jamun_csr_by_source(_ptr(rowptr, i32), _ptr(col, i32), rowptr.numel() - 1, col.numel(), _ptr(scratch, i32),
                                         _ptr(src_rowptr, i32), _ptr(src_eid, i32), _stream())
@@ -171,10 +235,19 @@ def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
     _count(4)
 
 
-def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
+def csr_by_source(rowptr, col, scratch, src_rowptr, src_eid):
+    _T.csr_by_source(rowptr, col, scratch, src_rowptr, src_eid)
+
+
+@_op("pack_rows", mutates=("a",))
+def _pack_rows(x: Tensor, col0: int, ncols: int, rows_pad: int, a: Tensor) -> None:
     rc = _lib.lib().jamun_pack_rows(_ptr(x), x.shape[1], col0, ncols, x.shape[0], rows_pad, _ptr(a), _stream())
     _lib.check(rc, "jamun_pack_rows")
     _count()
+
+
+def pack_rows(x, col0: int, ncols: int, rows_pad: int, a):
+    _T.pack_rows(x, int(col0), int(ncols), int(rows_pad), a)
 
 
 def pack_b(src, n_stages: int, n_pad: int, row_map=None, k_src: Optional[int] = None, n_valid: Optional[int] = None,
@@ -220,14 +293,22 @@ def gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha,
     _count(2 if k_splits > 1 else 1)
 
 
-def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
-               c_act: float, c_gate: float, x_new, x_scaled, vadd=None):
+@_op("block_tail_", mutates=("x_new", "x_scaled"))
+def _block_tail(conv: Tensor, x_in: Tensor, s_in: int, v_in: int, x_res: Optional[Tensor], wself_s: Tensor, wself_v: Tensor,
+                wskip_s: Tensor, wskip_v: Optional[Tensor], skip_w: Optional[Tensor], s_next: Optional[Tensor], c_act: float,
+                c_gate: float, x_new: Tensor, x_scaled: Optional[Tensor], vadd: Optional[Tensor]) -> None:
     N = conv.shape[0]
     rc = _lib.lib().jamun_block_tail(_ptr(conv), _ptr(vadd), _ptr(x_in), s_in, v_in, _ptr(x_res), _ptr(wself_s), _ptr(wself_v),
                                      _ptr(wskip_s), _ptr(wskip_v), _ptr(skip_w), _ptr(s_next), float(c_act),
                                      float(c_gate), N, _ptr(x_new), _ptr(x_scaled), _stream())
     _lib.check(rc, "jamun_block_tail")
     _count()
+
+
+def block_tail(conv, x_in, s_in: int, v_in: int, x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next,
+               c_act: float, c_gate: float, x_new, x_scaled, vadd=None):
+    _T.block_tail_(conv, x_in, int(s_in), int(v_in), x_res, wself_s, wself_v, wskip_s, wskip_v, skip_w, s_next, float(c_act),
+                   float(c_gate), x_new, x_scaled, vadd)
 
 
 def tail_pack(conv, vadd, x_in, s_in: int, v_in: int, c_act: float, c_gate: float, rows_pad: int, a_s_ptr: int, a_v_ptr: int,
@@ -239,22 +320,48 @@ def tail_pack(conv, vadd, x_in, s_in: int, v_in: int, c_act: float, c_gate: floa
     _count()
 
 
-def tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled, xs_op=None, rows_pad: int = 0):
+@_op("tail_mix", mutates=("x_new", "x_scaled", "xs_op"))
+def _tail_mix(y: Tensor, x_res: Optional[Tensor], skip_w: Optional[Tensor], s_next: Optional[Tensor], x_new: Tensor,
+              x_scaled: Optional[Tensor], xs_op: Optional[Tensor], rows_pad: int) -> None:
     rc = _lib.lib().jamun_tail_mix(_ptr(y), _ptr(x_res), _ptr(skip_w), _ptr(s_next), y.shape[0], _ptr(x_new), _ptr(x_scaled),
                                    _ptr(xs_op), rows_pad, _stream())
     _lib.check(rc, "jamun_tail_mix")
     _count()
 
 
-def head(x, w1_s, w1_v, w2, c_gate: float, g):
+def tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled, xs_op=None, rows_pad: int = 0):
+    _T.tail_mix(y, x_res, skip_w, s_next, x_new, x_scaled, xs_op, int(rows_pad))
+
+
+@_op("head_", mutates=("g",))
+def _head(x: Tensor, w1_s: Tensor, w1_v: Tensor, w2: Tensor, c_gate: float, g: Tensor) -> None:
     rc = _lib.lib().jamun_head(_ptr(x), _ptr(w1_s), _ptr(w1_v), _ptr(w2), float(c_gate), x.shape[0], _ptr(g), _stream())
     _lib.check(rc, "jamun_head")
     _count()
+
+
+def head(x, w1_s, w1_v, w2, c_gate: float, g):
+    _T.head_(x, w1_s, w1_v, w2, float(c_gate), g)
     return g
 
 
-def walk_step(y, v, ybar, p, g, chain_ptr, prm: "_lib.WalkParams", noise, xhat, score, traj_y=None, traj_xhat=None,
-              traj_score=None, score_in=None, dev_state=None):
+_WP_FLOATS = ("c_in", "c_skip", "c_out", "sigma2", "delta", "u", "a", "z_sqrt_u", "beta", "clip")
+_WP_INTS = ("first", "last", "center", "seed", "step")
+_U64 = (1 << 64) - 1
+
+
+def _signed64(v: int) -> int:  # operator arguments are int64: 64-bit seeds travel as two's complement
+    v &= _U64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+@_op("baoab_step", mutates=("y", "v", "ybar", "p", "xhat", "score", "traj_y", "traj_xhat", "traj_score"))
+def _walk_step(y: Tensor, v: Tensor, ybar: Tensor, p: Tensor, g: Optional[Tensor], chain_ptr: Tensor, fparams: List[float],
+               iparams: List[int], noise: Optional[Tensor], xhat: Optional[Tensor], score: Optional[Tensor],
+               traj_y: Optional[Tensor], traj_xhat: Optional[Tensor], traj_score: Optional[Tensor], score_in: Optional[Tensor],
+               dev_state: Optional[Tensor]) -> None:
+    prm = _lib.WalkParams(**dict(zip(_WP_FLOATS, fparams)), first=iparams[0], last=iparams[1], center=iparams[2],
+                          seed=iparams[3] & _U64, step=iparams[4] & _U64)
     G = chain_ptr.numel() - 1
     rc = _lib.lib().jamun_walk_step(_ptr(y), _ptr(v), _ptr(ybar), _ptr(p), _ptr(g), _ptr(score_in),
                                     _ptr(chain_ptr, torch.int32), G,
@@ -264,34 +371,66 @@ def walk_step(y, v, ybar, p, g, chain_ptr, prm: "_lib.WalkParams", noise, xhat, 
     _count()
 
 
-def walk_advance(dev_state, slot_inc: int):
+def walk_step(y, v, ybar, p, g, chain_ptr, prm: "_lib.WalkParams", noise, xhat, score, traj_y=None, traj_xhat=None,
+              traj_score=None, score_in=None, dev_state=None):
+    """One fused walk-jump step (jamun_walk_step) as the operator jamun_b200::baoab_step."""
+    _T.baoab_step(y, v, ybar, p, g, chain_ptr, [float(getattr(prm, k)) for k in _WP_FLOATS],
+                  [int(prm.first), int(prm.last), int(prm.center), _signed64(int(prm.seed)), _signed64(int(prm.step))], noise, xhat,
+                  score, traj_y, traj_xhat, traj_score, score_in, dev_state)
+
+
+@_op("walk_advance", mutates=("dev_state",))
+def _walk_advance(dev_state: Tensor, slot_inc: int) -> None:
     rc = _lib.lib().jamun_walk_advance(_ptr(dev_state, torch.int64), int(slot_inc), _stream())
     _lib.check(rc, "jamun_walk_advance")
     _count()
 
 
-def aboba_drift(y, v, half_delta: float):
+def walk_advance(dev_state, slot_inc: int):
+    _T.walk_advance(dev_state, int(slot_inc))
+
+
+@_op("aboba_drift", mutates=("y",))
+def _aboba_drift(y: Tensor, v: Tensor, half_delta: float) -> None:
     rc = _lib.lib().jamun_aboba_drift(_ptr(y), _ptr(v), float(half_delta), y.shape[0], _stream())
     _lib.check(rc, "jamun_aboba_drift")
     _count()
 
 
-def aboba_kick(y, v, score, prm: "_lib.WalkParams", noise):
+def aboba_drift(y, v, half_delta: float):
+    _T.aboba_drift(y, v, float(half_delta))
+
+
+@_op("aboba_kick", mutates=("y", "v"))
+def _aboba_kick(y: Tensor, v: Tensor, score: Tensor, fparams: List[float], iparams: List[int], noise: Optional[Tensor]) -> None:
+    prm = _lib.WalkParams(**dict(zip(_WP_FLOATS, fparams)), first=iparams[0], last=iparams[1], center=iparams[2],
+                          seed=iparams[3] & _U64, step=iparams[4] & _U64)
     rc = _lib.lib().jamun_aboba_kick(_ptr(y), _ptr(v), _ptr(score), C.byref(prm), _ptr(noise), y.shape[0], _stream())
     _lib.check(rc, "jamun_aboba_kick")
     _count()
 
 
-def gaussian_axpy(x, a: float, b: float, noise, seed: int, step: int, out):
+def aboba_kick(y, v, score, prm: "_lib.WalkParams", noise):
+    _T.aboba_kick(y, v, score, [float(getattr(prm, k)) for k in _WP_FLOATS],
+                  [int(prm.first), int(prm.last), int(prm.center), _signed64(int(prm.seed)), _signed64(int(prm.step))], noise)
+
+
+@_op("gaussian_axpy", mutates=("out",))
+def _gaussian_axpy(x: Optional[Tensor], a: float, b: float, noise: Optional[Tensor], seed: int, step: int, out: Tensor) -> None:
     n_atoms = out.shape[0]
-    rc = _lib.lib().jamun_gaussian_axpy(_ptr(x), float(a), float(b), _ptr(noise), int(seed), int(step), n_atoms,
+    rc = _lib.lib().jamun_gaussian_axpy(_ptr(x), float(a), float(b), _ptr(noise), int(seed) & _U64, int(step) & _U64, n_atoms,
                                         _ptr(out), _stream())
     _lib.check(rc, "jamun_gaussian_axpy")
     _count()
+
+
+def gaussian_axpy(x, a: float, b: float, noise, seed: int, step: int, out):
+    _T.gaussian_axpy(x, float(a), float(b), noise, _signed64(int(seed)), _signed64(int(step)), out)
     return out
 
 
-def layout_to_soa(x, s: int, v: int):
+@torch.library.custom_op("jamun_b200::layout_to_soa", mutates_args=(), device_types="cuda")
+def layout_to_soa(x: Tensor, s: int, v: int) -> Tensor:
     out = torch.empty_like(x)
     rc = _lib.lib().jamun_layout_to_soa(_ptr(x), s, v, x.shape[0], _ptr(out), _stream())
     _lib.check(rc, "jamun_layout_to_soa")
@@ -299,7 +438,8 @@ def layout_to_soa(x, s: int, v: int):
     return out
 
 
-def layout_from_soa(x, s: int, v: int):
+@torch.library.custom_op("jamun_b200::layout_from_soa", mutates_args=(), device_types="cuda")
+def layout_from_soa(x: Tensor, s: int, v: int) -> Tensor:
     out = torch.empty_like(x)
     rc = _lib.lib().jamun_layout_from_soa(_ptr(x), s, v, x.shape[0], _ptr(out), _stream())
     _lib.check(rc, "jamun_layout_from_soa")
@@ -307,7 +447,12 @@ def layout_from_soa(x, s: int, v: int):
     return out
 
 
-def linear_act(x, w, b, act: int = 0):
+layout_to_soa.register_fake(lambda x, s, v: torch.empty_like(x))
+layout_from_soa.register_fake(lambda x, s, v: torch.empty_like(x))
+
+
+@torch.library.custom_op("jamun_b200::linear_act", mutates_args=(), device_types="cuda")
+def linear_act(x: Tensor, w: Tensor, b: Tensor, act: int = 0) -> Tensor:
     out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
     rc = _lib.lib().jamun_linear_act(_ptr(x), _ptr(w), _ptr(b), x.shape[0], x.shape[1], w.shape[0], int(act), _ptr(out), _stream())
     _lib.check(rc, "jamun_linear_act")
@@ -315,7 +460,11 @@ def linear_act(x, w, b, act: int = 0):
     return out
 
 
-def tensor_product(x1, x2, weight, table, d_out: int):
+linear_act.register_fake(lambda x, w, b, act=0: x.new_empty(x.shape[0], w.shape[0]))
+
+
+@torch.library.custom_op("jamun_b200::tensor_product", mutates_args=(), device_types="cuda")
+def tensor_product(x1: Tensor, x2: Tensor, weight: Tensor, table: Tensor, d_out: int) -> Tensor:
     Z = x1.shape[0]
     out = torch.empty(Z, d_out, device=x1.device, dtype=torch.float32)
     rc = _lib.lib().jamun_tensor_product(_ptr(x1), x1.shape[1], _ptr(x2), x2.shape[1], _ptr(weight), weight.stride(0),
@@ -519,3 +668,6 @@ def ema_update(ema, p, decay: float):
     rc = _lib.lib().jamun_ema_update(_ptr(ema), _ptr(p), float(decay), ema.numel(), _stream())
     _lib.check(rc, "jamun_ema_update")
     _count()
+
+
+tensor_product.register_fake(lambda x1, x2, weight, table, d_out: x1.new_empty(x1.shape[0], d_out))

@@ -149,3 +149,29 @@ def test_plan_build_is_a_few_dozen_library_launches(models):
                and "noise_mlp" not in e.name]
     assert ours <= 50, ours
     assert len(foreign) <= 10, foreign[:10]
+
+
+def test_sampling_launchers_are_torch_library_operators(models):
+    """the tensor front end is a thin torch.library layer over the C ABI -- schema, fake (meta) implementation and
+    mutation annotations of a representative set of the sampling-path operators."""
+    from jamun_b200 import ops
+
+    T = torch.ops.jamun_b200
+    for name in ("radius_csr", "radius_csr_cells", "csr_by_source", "edge_geom", "edge_radial_hidden_all", "baoab_step", "center_scale_",
+                 "atom_embed_", "noise_mlp_", "head_", "block_tail_", "tail_mix", "pack_rows", "tensor_product", "layout_to_soa"):
+        assert hasattr(T, name), name
+    assert "Tensor(a" in str(T.center_scale_.default._schema)  # mutated outputs are declared
+    # opcheck of a mutating launcher and of a functional one (schema + fake tensor)
+    y = torch.randn(30, 3, device="cuda")
+    ptr = torch.tensor([0, 12, 30], dtype=torch.int32, device="cuda")
+    torch.library.opcheck(T.center_scale_.default, (y, ptr, 1.7, torch.empty_like(y), torch.empty_like(y), True),
+                          test_utils=("test_schema", "test_faketensor"))
+    x = torch.randn(7, 216, device="cuda")
+    torch.library.opcheck(T.layout_to_soa.default, (x, 120, 32), test_utils=("test_schema", "test_faketensor"))
+    # fake-tensor propagation through a functional operator: shapes without running a kernel
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    with FakeTensorMode():
+        w = torch.empty(9, 64, device="cuda")
+        out = T.linear_act(torch.empty(5, 64, device="cuda"), w, torch.empty(9, device="cuda"), 1)
+        assert out.shape == (5, 9)
