@@ -410,34 +410,47 @@ def roofline_block(model, state, workload, chains, dev):
                                                      base + 4 * a1_off, comp, topo.inv_deg))
     p2_ms = time_kernel(lambda: ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, topo.y, topo.t_edge,
                                             topo.p2.data_ptr(), 96, blk["alpha1"]))
-    gemm_ms = time_kernel(lambda: ops.gemm_tf32x3(
-        [base] + [base + 4 * (a1_off + c * comp) for c in range(3)], [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3,
-        [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216], [1.0] * 4, nrows, rp,
-        topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
+    kind, sc = blk["gemm_kind"], blk["f16_scales"]
+    gemm_ms = time_kernel(lambda: _engine._gemm(
+        topo, kind, [base] + [base + 4 * (a1_off + c * comp) for c in range(3)],
+        [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32],
+        [0, 152, 184, 216], [1.0 / sc[0]] + [1.0 / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
     rows_all = (atoms + 127) // 128 * 128
-    ygemm_ms = time_kernel(lambda: ops.gemm_tf32x3([topo.xs_op.data_ptr()], [blk["wy_img"].data_ptr()], [4], [128], [128], [0], [1.0],
-                                                   atoms, rows_all, None, topo.y.data_ptr(), _engine.Y_LD, col_blocks=17,
-                                                   b_block_floats=4 * 2 * 128 * 32))
+    ygemm_ms = time_kernel(lambda: _engine._gemm(topo, kind, [topo.xs_op.data_ptr()], [blk["wy_img"].data_ptr()], [4], [128], [128], [0],
+                                                 [1.0 / sc[1]], atoms, rows_all, None, topo.y.data_ptr(), _engine.Y_LD, col_blocks=17,
+                                                 b_block_floats=4 * 128 * 32 * (1 if kind == "f16" else 2)))
     # algorithmic work per launch: the aggregated contraction 2*65*(152*152 + 3*64*32) FLOP per atom on the
-    # tensor pipe (the x3 TF32 passes needed for fp32 parity are NOT counted); its A operand 65*(160+3*64)*4 B per atom via HBM
+    # tensor pipe (the three split products needed for fp32 parity are NOT counted); its A operand 65*(160+3*64)*4 B per atom via HBM
     gemm_flop = nrows * 2.0 * 65 * (152 * 152 + 3 * 64 * 32)
     a_bytes = nrows * 65.0 * (160 + 3 * 64) * 4
-    tf32_peak = pk["bf16_tflops"] / 2.0
-    return {"kernel": "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
-            "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": gemm_flop / (gemm_ms * 1e-3) / 1e12 / tf32_peak, "traffic": measured_traffic(workload, chains),
-            "peak_source": f"{pk_src} bf16 burst / 2 (dense tf32 rate; fp32-parity 3xTF32 needs 3 passes, so 1/3 is the ceiling)",
-            "ms_per_launch": gemm_ms, "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9,
-            "hbm_frac_of_measured": a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "mean_in_degree": deg,
+    f16 = kind == "f16"
+    tensor_peak = pk["bf16_tflops"] / (1.0 if f16 else 2.0)  # dense fp16 rate = measured bf16 rate; tf32 runs at half of it
+    tensor_frac = gemm_flop / (gemm_ms * 1e-3) / 1e12 / tensor_peak
+    hbm_frac = a_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"]
+    kname = ("gemm_tf32x3_kernel<.., F16=true> (hidden ConvBlock contraction, tcgen05 kind::f16, fp16 hi/lo split = 3 products)" if f16
+             else "gemm_tf32x3_kernel (hidden ConvBlock contraction, tcgen05 kind::tf32, 3xTF32)")
+    head = ({"kernel": kname, "bound": "hbm", "achieved": a_bytes / (gemm_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+             "frac": hbm_frac, "traffic": measured_traffic(workload, chains),
+             "peak_source": f"{pk_src} HBM copy bandwidth (the launch streams its {a_bytes / 1e9:.2f} GB A operand once; the tensor "
+                            f"pipe needs 3 fp16 products per algorithmic FLOP, ceiling 1/3 of {tensor_peak:.0f} TFLOP/s)",
+             "tensor_TFLOPs": gemm_flop / (gemm_ms * 1e-3) / 1e12, "tensor_frac_of_dense_fp16": tensor_frac}
+            if hbm_frac >= 3.0 * tensor_frac else
+            {"kernel": kname, "bound": "tensor", "achieved": gemm_flop / (gemm_ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+             "frac": tensor_frac, "traffic": measured_traffic(workload, chains),
+             "peak_source": f"{pk_src} bf16 burst{'' if f16 else ' / 2'} (dense {'fp16' if f16 else 'tf32'} rate; fp32 parity needs 3 "
+                            "split products per FLOP, so 1/3 is the ceiling)",
+             "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9, "hbm_frac_of_measured": hbm_frac})
+    head.update({"ms_per_launch": gemm_ms, "mean_in_degree": deg, "gemm_kind": kind,
             "second_kernel": {"kernel": "conv_build_tc_kernel<120,32> (per-node aggregate F^T.H on tcgen05, 3xTF32; writes the A operand)",
                               "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                               "tensor_TFLOPs": nrows * deg * 2 * 65 * (152 + 3 * 64) / (build_ms * 1e-3) / 1e12},
             "fourth_kernel": {"kernel": "conv_p2_edge_kernel + conv_p2_reduce_kernel (0e(x)1e->1e, source-major)",
                               "ms_per_launch": p2_ms, "fma_TFLOPs": nrows * deg * 2 * 65 * 32 / (p2_ms * 1e-3) / 1e12},
-            "third_kernel": {"kernel": "gemm_tf32x3_kernel, 17 column-block passes, A-stationary (per-node transform Y = x_s.W, N=2080)",
+            "third_kernel": {"kernel": "gemm kernel, 17 column-block passes, A-stationary (per-node transform Y = x_s.W, N=2080)",
                              "ms_per_launch": ygemm_ms, "achieved": atoms * 2.0 * 120 * 2080 / (ygemm_ms * 1e-3) / 1e12,
-                             "unit": "TFLOP/s"}}
+                             "unit": "TFLOP/s"}})
+    return head
 
 
 def parity_block(model, workload: str, chains: int, n_sample: int, dev, o):

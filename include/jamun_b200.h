@@ -173,6 +173,23 @@ int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const float* const
                              const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
                              jamun_stream_t stream);
 
+/* fp16-split form of the same GEMM (the default of the sampling path; csrc/gemm_tf32x3.cu): the operands are split as
+ * hi = rn16(v), lo = rn16(v - hi) -- fp16 and tf32 both carry an 11-bit significand, so a_hi.b_hi + a_hi.b_lo + a_lo.b_hi has
+ * the accuracy of the 3xTF32 form -- and contracted with tcgen05.mma kind::f16 (K = 16 per instruction, twice the tf32 rate).
+ * a: the same fp32 stage-major operand; b: images from jamun_pack_b_f16 (n_pad rows x 128 bytes [hi k0..31 | lo k0..31] per
+ * stage, K-major SWIZZLE_128B; b_block_floats counts 4-byte words).  The weights are pre-scaled by a power of two when packed
+ * (fp16 range), the caller folds 1/scale into alpha and passes the scale as addend_scale[s] (the addend joins the scaled
+ * accumulator: out = (acc + addend_scale * addend) * alpha * row_scale; NULL: 1).  status (or NULL): bit 0 is OR-ed in when an element of a exceeds the fp16
+ * range (the result is then invalid and the caller must use jamun_gemm_tf32x3).  k_splits > 1: split-K as
+ * jamun_gemm_tf32x3_splitk (partial scratch, no addend, no column blocks). */
+int jamun_pack_b_f16(const float* src, int ld, const int* row_map, int K_src, int n_stages, int N_valid, int n_inner,
+                     int outer_rows, int n_pad, int col_blocks, int transpose, float scale, float* out, jamun_stream_t stream);
+int jamun_gemm_f16x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                     const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                     const int* addend_ld, const float* addend_scale, int col_blocks, long long b_block_floats, int rows,
+                     int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
+                     jamun_stream_t stream);
+
 /* Gate + self-interaction + skip Linear + noise-conditional skip/scale
  * (e3tools/nn/_gate.py:63-64, _interaction.py:26-30, model/noise_conditioning.py:50-73,
  * arch/e3conv.py:131-133).  y = Lin_self(Gate(conv)) + Lin_skip(x_in);
@@ -295,6 +312,16 @@ int jamun_conv_bwd_scale(const float* dout, const float* inv_deg, float alpha0, 
 int jamun_stage_atb(const float* a, long long a_comp_stride, int ncomp, int n_stages, int nslots, int rows, int rows_pad,
                     const float* b, int ldb, int b_col0, int b_comp_stride, int W, float* out, int mode, int out_rows,
                     const int* slot_row0, const int* slot_rows, jamun_stream_t stream);
+/* Tensor-core form of jamun_stage_atb (tcgen05 kind::tf32, 3xTF32, TS mode; both operands MN-major, see csrc/gemm_atb.cu):
+ * jamun_pack_rows_split writes the (hi | lo) images [2][nslots][rows_pad][32] of x[:, col0:col0+ncols] (one call per component,
+ * images consecutive); jamun_stage_atb_tc consumes them.  The node range is split over k_splits CTAs per 128-row tile and the
+ * partial tiles are summed in ascending order.  partial: jamun_stage_atb_tc_scratch(n_stages, W, k_splits) floats. */
+int jamun_pack_rows_split(const float* x, int ld, int col0, int ncols, int rows, int rows_pad, int nslots, float* out,
+                          jamun_stream_t stream);
+long long jamun_stage_atb_tc_scratch(int n_stages, int W, int k_splits);
+int jamun_stage_atb_tc(const float* a, long long a_comp_stride, int ncomp, int n_stages, int nslots, int rows, int rows_pad,
+                       const float* bsplit, int W, float* out, int mode, int out_rows, const int* slot_row0,
+                       const int* slot_rows, int k_splits, float* partial, jamun_stream_t stream);
 int jamun_conv_bwd_edge(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
                         const float* rhat, const float* dA0, int ld0, const float* dA1, int ld1, long long dA1_comp_stride,
                         int N, float* dh, float* dxe, jamun_stream_t stream);

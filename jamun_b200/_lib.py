@@ -47,6 +47,9 @@ _PROTOS = {
     "jamun_colsum": ([c_f, I, I, c_f, I, c_f, I, I, I, c_f, I, c_f, c_f], I),
     "jamun_conv_bwd_scale": ([c_f, c_f, F, F, I, c_f, c_f], I),
     "jamun_stage_atb": ([c_f, C.c_longlong, I, I, I, I, I, c_f, I, I, I, I, c_f, I, I, C.POINTER(I), C.POINTER(I), c_f], I),
+    "jamun_pack_rows_split": ([c_f, I, I, I, I, I, I, c_f, c_f], I),
+    "jamun_stage_atb_tc_scratch": ([I, I, I], C.c_longlong),
+    "jamun_stage_atb_tc": ([c_f, C.c_longlong, I, I, I, I, I, c_f, I, c_f, I, I, C.POINTER(I), C.POINTER(I), I, c_f, c_f], I),
     "jamun_conv_bwd_edge": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, c_f, I, C.c_longlong, I, c_f, c_f, c_f], I),
     "jamun_conv_bwd_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, I, I, c_f, c_f, c_f], I),
     "jamun_conv_bwd_gather": ([c_f, c_f, c_f, I, c_f, I, I, I, c_f, c_f], I),
@@ -69,6 +72,9 @@ _PROTOS = {
                            C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), I, C.c_longlong, I, I, c_f, c_f, I, c_f], I),
     "jamun_gemm_tf32x3_splitk": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                                   C.POINTER(F), I, I, c_f, c_f, I, I, c_f, c_f], I),
+    "jamun_gemm_f16x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
+                          C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(F), I, C.c_longlong, I, I, c_f, c_f, I, I, c_f, c_f, c_f], I),
+    "jamun_pack_b_f16": ([c_f, I, c_f, I, I, I, I, I, I, I, I, F, c_f, c_f], I),
     "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f, c_f, c_f, F, I, c_f], I),
     "jamun_tail_mix": ([c_f, c_f, c_f, c_f, I, c_f, c_f, c_f, I, c_f], I),

@@ -147,9 +147,9 @@ def conv_bwd(dout: Tensor, x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, c
     rows0[-1] = s_in - 32 * (ns - 1)
     slot_row0 = [32 * s for s in range(ns)] + ([s_in] if v_in else [])
     slot_rows = rows0 + ([v_in] if v_in else [])
-    ops.stage_atb(base, 0, 1, 65 * nsl0, nsl0, N, rows_pad, g, 0, 0, SO, dm0, 0, u0, slot_row0, slot_rows)
+    ops.stage_atb_auto(base, 0, 1, 65 * nsl0, nsl0, N, rows_pad, g, 0, 0, SO, dm0, 0, u0, slot_row0, slot_rows)
     if v_in:
-        ops.stage_atb(base + 4 * a1_off, comp, 3, 65 * 2, 2, N, rows_pad, g, SO, V, V, dm1, 0, u1, [s_in, s_in + v_in], [v_in, v_in])
+        ops.stage_atb_auto(base + 4 * a1_off, comp, 3, 65 * 2, 2, N, rows_pad, g, SO, V, V, dm1, 0, u1, [s_in, s_in + v_in], [v_in, v_in])
     # dA = G . M^T (column blocks of 128 over the (k', u') index, same order as the forward K axis)
     map0, map1 = packing.conv_row_maps(s_in, v_in, x.device)
     k0 = 65 * nsl0 * 32
@@ -179,7 +179,7 @@ def conv_bwd(dout: Tensor, x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, c
     # path 0e(x)1e->1e: dY (source-major), dM2 = x_s^T . dY, dx_s += dY . M2^T
     dy_op = _empty(65 * rows_pad * 32, like=x)
     ops.conv_bwd_p2(src_rowptr, src_eid, edst, h, rhat, y, g, rows_pad, dh, dy_op)
-    ops.stage_atb(dy_op.data_ptr(), 0, 1, 65, 1, N, rows_pad, x, 0, 0, s_in, dm1, 1, u1)
+    ops.stage_atb_auto(dy_op.data_ptr(), 0, 1, 65, 1, N, rows_pad, x, 0, 0, s_in, dm1, 1, u1)
     m2t = m1[:, :s_in, :].permute(1, 0, 2).reshape(s_in, 65 * V).contiguous()  # [u, (k', w)] (re-layout only)
     bt2 = ops.pack_b(m2t, n_stages=65, n_pad=128, k_src=s_in, n_valid=65 * V, transpose=True)
     dxs2 = _empty(N, 128, like=x)

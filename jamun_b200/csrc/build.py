@@ -7,7 +7,7 @@ import sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SOURCES = ["graph.cu", "conv_simt.cu", "langevin.cu", "conv_build.cu", "conv_build_tc.cu", "gemm_tf32x3.cu", "pack.cu", "tensor_product.cu", "train_generic.cu", "train_conv_bwd.cu", "train_misc.cu"]
+SOURCES = ["graph.cu", "conv_simt.cu", "langevin.cu", "conv_build.cu", "conv_build_tc.cu", "gemm_tf32x3.cu", "pack.cu", "tensor_product.cu", "train_generic.cu", "train_conv_bwd.cu", "train_misc.cu", "gemm_atb.cu"]
 LIB = HERE / "libjamun_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

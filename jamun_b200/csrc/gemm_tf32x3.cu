@@ -13,6 +13,15 @@
 //              to the stage's "empty" mbarriers.
 // Up to four K-segments, each with its own A, B, N and TMEM accumulator columns, run back to back in one launch
 // (conv: one 0e segment with N=160 and three 1e segments with N=32).
+//
+// F16 variant (jamun_gemm_f16x3): the same pipeline with the split taken in fp16 instead of tf32 -- both formats carry an 11-bit
+// significand, so a_hi*b_hi + a_hi*b_lo + a_lo*b_hi keeps the same ~2^-21 per-product accuracy, but kind::f16 contracts K = 16
+// per instruction at twice the tf32 rate: half the MMA instructions per stage.  fp16's range is the price: weights are
+// pre-scaled by a power of two when their images are packed (jamun_pack_b_f16; undone through `alpha`), and an operand value
+// beyond +-65504 raises bit 0 of the caller's status word (the caller then has to use the tf32 kernel).  A converter thread
+// packs its row as 16 (hi,hi) + 16 (lo,lo) half2 words -> one 32-column TMEM slot; a weight stage image is n_pad rows of
+// 128 bytes [hi k0..31 | lo k0..31] (K-major SWIZZLE_128B), half the bytes of the tf32 image.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -25,12 +34,17 @@ constexpr int kTSlots = 4;                 // A slots in TMEM
 #define JAMUN_GEMM_ASLOTS 6
 #define JAMUN_GEMM_BSLOTS 3
 #endif
-constexpr int kASlots = JAMUN_GEMM_ASLOTS;  // raw fp32 A tiles in shared memory (bulk-copied from HBM)
-constexpr int kBSlots = JAMUN_GEMM_BSLOTS;  // weight images in shared memory
-constexpr int kBK = 32;                    // K per stage (one 128-byte swizzle row of tf32)
+constexpr int kBK = 32;                    // K per stage (one 128-byte row of the fp32 A tile)
 constexpr int kMaxN = 160;
 constexpr int kATileBytes = 128 * kBK * 4;    // 16 KB
-constexpr int kBSlotBytes = 2 * kMaxN * 128;  // hi + lo images, 40 KB
+template <bool F16>
+struct Cfg {
+    static constexpr int kASlots = F16 ? 8 : JAMUN_GEMM_ASLOTS;  // raw fp32 A tiles in shared memory (bulk-copied from HBM)
+    static constexpr int kBSlots = F16 ? 4 : JAMUN_GEMM_BSLOTS;  // weight images in shared memory
+    static constexpr int kBRowBytes = F16 ? 128 : 256;           // image bytes per output column and stage (hi + lo)
+    static constexpr int kBSlotBytes = kMaxN * kBRowBytes;       // 20 KB (fp16) / 40 KB (tf32)
+    static constexpr int kASlotCols = F16 ? 32 : 64;             // TMEM columns of one converted A stage (hi | lo)
+};
 constexpr int kTmemCols = 512;
 constexpr int kACol0 = 256;                // A slots live in TMEM columns [256, 512): 64 columns (hi 32 | lo 32) each
 constexpr int kConvWarps = 8;              // two converter groups of 4 warps (TMEM lane quarters), alternating stages
@@ -43,6 +57,7 @@ struct Seg {
     const float* addend;  // optional [rows, addend_ld]: out = (acc + addend[row, n]) * alpha * row_scale
     int n_stages, n_pad, n_valid, d_col, out_col, addend_ld;
     float alpha;
+    float addend_scale;   // out = (acc + addend_scale * addend) * alpha * row_scale (fp16 form: the weights' pre-scale)
 };
 struct Params {
     Seg seg[4];
@@ -58,18 +73,25 @@ struct Params {
     int k_splits;
     float* partial;
     long long partial_stride;
+    int* status;  // F16 only: bit 0 is set when an A value does not fit fp16 (null: not reported)
 };
 
-struct __align__(1024) Smem {
-    uint8_t b[kBSlots][kBSlotBytes];
-    uint8_t a[kASlots][kATileBytes];
-    uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBSlots], b_empty[kBSlots], t_full[kTSlots], t_empty[kTSlots], d_full[2], d_empty[2];
+template <bool F16>
+struct __align__(1024) SmemT {
+    uint8_t b[Cfg<F16>::kBSlots][Cfg<F16>::kBSlotBytes];
+    uint8_t a[Cfg<F16>::kASlots][kATileBytes];
+    uint64_t a_full[Cfg<F16>::kASlots], a_empty[Cfg<F16>::kASlots], b_full[Cfg<F16>::kBSlots], b_empty[Cfg<F16>::kBSlots],
+        t_full[kTSlots], t_empty[kTSlots], d_full[2], d_empty[2];
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
 // COALESCE: epilogue variant for wide outputs in stationary mode (kept out of the contraction instantiation: +40 registers)
-template <bool COALESCE>
+template <bool COALESCE, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P) {
+    using Smem = SmemT<F16>;
+    constexpr int kASlots = Cfg<F16>::kASlots, kBSlots = Cfg<F16>::kBSlots, kASlotCols = Cfg<F16>::kASlotCols;
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5;
@@ -127,6 +149,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             const int sa = g % kASlots, st = g % kTSlots;
             umma::mbar_wait(&S.a_full[sa], (g / kASlots) & 1);
             const float4* row = reinterpret_cast<const float4*>(S.a[sa] + r * 128);
+            const uint32_t a_addr = tmem + lane_base + (uint32_t)(kACol0 + st * kASlotCols);
+            if constexpr (F16) {
+                // columns 0-15: (hi[2j], hi[2j+1]) packed halves, columns 16-31: the remainders; one 32-column store
+                uint32_t pk[32];
+                uint32_t ovf = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 c = row[q ^ sw];
+                    const __half2 h01 = __floats2half2_rn(c.x, c.y), h23 = __floats2half2_rn(c.z, c.w);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    pk[2 * q] = h2_bits(h01);
+                    pk[2 * q + 1] = h2_bits(h23);
+                    pk[16 + 2 * q] = h2_bits(__floats2half2_rn(c.x - f01.x, c.y - f01.y));
+                    pk[16 + 2 * q + 1] = h2_bits(__floats2half2_rn(c.z - f23.x, c.w - f23.y));
+                    // exponent field all ones (inf / nan) in either half sets bit 15 / 31
+                    ovf |= ((pk[2 * q] & 0x7C007C00u) + 0x04000400u) | ((pk[2 * q + 1] & 0x7C007C00u) + 0x04000400u);
+                }
+                if ((ovf & 0x80008000u) && P.status && tile_row0 + r < P.rows) atomicOr(P.status, 1);
+                umma::mbar_arrive(&S.a_empty[sa]);
+                umma::mbar_wait(&S.t_empty[st], ((g / kTSlots) & 1) ^ 1);
+                umma::fence_after_sync();
+                umma::tmem_st32(a_addr, pk);
+            } else {
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -142,9 +187,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             umma::mbar_arrive(&S.a_empty[sa]);
             umma::mbar_wait(&S.t_empty[st], ((g / kTSlots) & 1) ^ 1);
             umma::fence_after_sync();
-            const uint32_t a_addr = tmem + lane_base + (uint32_t)(kACol0 + st * 64);
             umma::tmem_st32(a_addr, hi);
             umma::tmem_st32(a_addr + 32, lo);
+            }
             umma::wait_st();
             umma::fence_before_sync();
             umma::mbar_arrive(&S.t_full[st]);
@@ -205,16 +250,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                         if (c0 + 4 * q + 3 < sg.n_valid) {
                             if (ad) {
                                 const float4 a4 = *reinterpret_cast<const float4*>(ad + 4 * q);
-                                f[0] += a4.x;
-                                f[1] += a4.y;
-                                f[2] += a4.z;
-                                f[3] += a4.w;
+                                f[0] += a4.x * sg.addend_scale;
+                                f[1] += a4.y * sg.addend_scale;
+                                f[2] += a4.z * sg.addend_scale;
+                                f[3] += a4.w * sg.addend_scale;
                             }
                             *reinterpret_cast<float4*>(o + 4 * q) = make_float4(f[0] * sc, f[1] * sc, f[2] * sc, f[3] * sc);
                         } else {
 #pragma unroll
                             for (int t = 0; t < 4; ++t)
-                                if (c0 + 4 * q + t < sg.n_valid) o[4 * q + t] = (f[t] + (ad ? ad[4 * q + t] : 0.f)) * sc;
+                                if (c0 + 4 * q + t < sg.n_valid) o[4 * q + t] = (f[t] + (ad ? ad[4 * q + t] * sg.addend_scale : 0.f)) * sc;
                         }
                     }
                 }
@@ -247,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
         for (int cb = 0; cb < ncb; ++cb) {
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
-                const uint32_t bytes = 2u * sg.n_pad * 128u;
+                const uint32_t bytes = (uint32_t)sg.n_pad * Cfg<F16>::kBRowBytes;
                 const int st_first = st_lo(sg);
                 for (int st = st_first, st_end = st_hi(sg); st < st_end; ++st, ++g) {
                     const int sb = g % kBSlots;
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
             }
             for (int s = 0; s < P.nseg; ++s) {
                 const Seg& sg = P.seg[s];
-                const uint32_t idesc = umma::make_idesc_tf32(128, sg.n_pad);
+                const uint32_t idesc = F16 ? umma::make_idesc_f16(128, sg.n_pad) : umma::make_idesc_tf32(128, sg.n_pad);
                 const uint32_t d_addr = tmem + (uint32_t)(sg.d_col + db * 128);
                 const uint32_t lo_off = (uint32_t)(sg.n_pad * 128) >> 4;
                 const int st_first = st_lo(sg);
@@ -282,8 +327,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                     umma::mbar_wait(&S.b_full[sb], (g / kBSlots) & 1);
                     umma::fence_after_sync();
                     if (umma::elect_one()) {
-                        const uint32_t a_hi = tmem + (uint32_t)(kACol0 + ts * 64), a_lo = a_hi + 32;
-                        const uint32_t bh = umma::desc_lo_kmajor_sw128(umma::smem_u32(S.b[sb])), bl = bh + lo_off;
+                        const uint32_t a_hi = tmem + (uint32_t)(kACol0 + ts * kASlotCols), a_lo = a_hi + kASlotCols / 2;
+                        const uint32_t bh = umma::desc_lo_kmajor_sw128(umma::smem_u32(S.b[sb]));
+                        if constexpr (F16) {
+                            // a row of the image: [hi k0..31 | lo k0..31] halves; a k-step is 16 halves = 32 bytes = 8 TMEM columns
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k) {
+                                const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
+                                const uint64_t dbl = umma::make_desc(bh + 4 + 2 * k, umma::kDescHiKmajorSw128);
+                                umma::mma_f16_ts(d_addr, a_lo + k * 8, dbh, idesc, (st != st_first) || k != 0);
+                                umma::mma_f16_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
+                                umma::mma_f16_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
+                            }
+                        } else {
+                        const uint32_t bl = bh + lo_off;
 #pragma unroll
                         for (int k = 0; k < kBK / 8; ++k) {
                             const uint64_t dbh = umma::make_desc(bh + 2 * k, umma::kDescHiKmajorSw128);
@@ -291,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                             umma::mma_tf32_ts(d_addr, a_lo + k * 8, dbh, idesc, (st != st_first) || k != 0);
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbl, idesc, 1);
                             umma::mma_tf32_ts(d_addr, a_hi + k * 8, dbh, idesc, 1);
+                        }
                         }
                         if (!stationary) umma::commit(&S.t_empty[ts]);
                         umma::commit(&S.b_empty[sb]);
@@ -332,17 +390,18 @@ __global__ void gemm_splitk_reduce_kernel(const float* __restrict__ partial, lon
 }
 }  // namespace
 
-static int gemm_launch(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+static int gemm_launch(bool f16, int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
-                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, jamun_stream_t stream);
+                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
+                       const float* addend_scale, jamun_stream_t stream);
 
 extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                                  const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                                  const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                                  const float* row_scale, float* out, int out_ld, jamun_stream_t stream) {
-    return gemm_launch(nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats, rows,
-                       rows_pad, row_scale, out, out_ld, 1, nullptr, stream);
+    return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats,
+                       rows, rows_pad, row_scale, out, out_ld, 1, nullptr, nullptr, nullptr, stream);
 }
 
 // Split-K form for small row counts (few 128-row tiles): k_splits CTAs per tile, partial: [k_splits, rows, out_ld] scratch.
@@ -351,14 +410,64 @@ extern "C" int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const f
                                         int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
                                         jamun_stream_t stream) {
     JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || partial), "bad k_splits / partial");
-    return gemm_launch(nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, nullptr, nullptr, 1, 0, rows, rows_pad, row_scale, out,
-                       out_ld, k_splits, partial, stream);
+    return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, nullptr, nullptr, 1, 0, rows, rows_pad, row_scale,
+                       out, out_ld, k_splits, partial, nullptr, nullptr, stream);
 }
 
-static int gemm_launch(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+// fp16-split form (same A operand; B images from jamun_pack_b_f16; k_splits == 1: plain launch, partial unused).
+extern "C" int jamun_gemm_f16x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                                const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                                const int* addend_ld, const float* addend_scale, int col_blocks, long long b_block_floats, int rows,
+                                int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
+                                int* status, jamun_stream_t stream) {
+    JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || (partial && !addend && col_blocks == 1)), "bad k_splits / partial");
+    return gemm_launch(true, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats, rows,
+                       rows_pad, row_scale, out, out_ld, k_splits, partial, status, addend_scale, stream);
+}
+
+template <bool F16>
+static int gemm_launch_t(Params& P, int nseg, const int* n_valid, const int* out_col, int col_blocks, int rows, int rows_pad, float* out,
+                         int out_ld, int k_splits, float* partial, jamun_stream_t stream) {
+    using Smem = SmemT<F16>;
+    const size_t smem = sizeof(Smem) + 1024;
+    static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "shared memory budget");
+    const bool wide = P.coalesce && col_blocks > 1;
+    cudaError_t e = wide ? cudaFuncSetAttribute(gemm_tf32x3_kernel<true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(gemm_tf32x3_kernel<false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        jb::set_error("jamun_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return JAMUN_ECUDA;
+    }
+    if (wide) {
+        const int tiles = rows_pad / 128;
+        int groups = jb::kNumSMs / tiles;  // few tiles: run the column-block passes of a tile on several CTAs
+        if (groups > col_blocks) groups = col_blocks;
+        if (groups < 1) groups = 1;
+        P.cb_groups = groups;
+        gemm_tf32x3_kernel<true, F16><<<dim3(tiles, groups), kThreads, smem, jb::as_stream(stream)>>>(P);
+    }
+    else gemm_tf32x3_kernel<false, F16><<<dim3(rows_pad / 128, k_splits), kThreads, smem, jb::as_stream(stream)>>>(P);
+    if (k_splits > 1) {
+        int4 c0 = {0, 0, 0, 0}, nc = {0, 0, 0, 0};
+        int* pc0 = &c0.x;
+        int* pnc = &nc.x;
+        long long width = 0;
+        for (int s = 0; s < nseg; ++s) pc0[s] = out_col[s], pnc[s] = n_valid[s], width += n_valid[s];
+        long long total = (long long)rows * width;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > jb::kNumSMs * 8) blocks = jb::kNumSMs * 8;
+        gemm_splitk_reduce_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(partial, P.partial_stride, k_splits, rows, out_ld, c0, nc,
+                                                                            nseg, out);
+    }
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+static int gemm_launch(bool f16, int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
-                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, jamun_stream_t stream) {
+                       const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
+                       const float* addend_scale, jamun_stream_t stream) {
     JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
     if (rows == 0) return JAMUN_OK;
@@ -368,6 +477,7 @@ static int gemm_launch(int nseg, const float* const* a, const float* const* b, c
     P.cb_groups = 1;
     P.partial = partial;
     P.partial_stride = (long long)rows * out_ld;
+    P.status = status;
     {
         const char* e = getenv("JAMUN_GEMM_COALESCE");
         P.coalesce = e ? atoi(e) : 1;
@@ -383,40 +493,10 @@ static int gemm_launch(int nseg, const float* const* a, const float* const* b, c
     for (int s = 0; s < nseg; ++s) {
         JB_CHECK_ARG(n_pad[s] % 16 == 0 && n_pad[s] >= 16 && n_pad[s] <= kMaxN && n_valid[s] <= n_pad[s], "n_pad out of range");
         P.seg[s] = Seg{a[s], b[s], out, addend ? addend[s] : nullptr, n_stages[s], n_pad[s], n_valid[s], dcol, out_col[s],
-                       addend_ld ? addend_ld[s] : 0, alpha[s]};
+                       addend_ld ? addend_ld[s] : 0, alpha[s], addend_scale ? addend_scale[s] : 1.0f};
         dcol += n_pad[s];
     }
     JB_CHECK_ARG(dcol <= kACol0, "accumulators exceed 256 TMEM columns");
-    const size_t smem = sizeof(Smem) + 1024;
-    static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "shared memory budget");
-    const bool wide = P.coalesce && col_blocks > 1;
-    cudaError_t e = wide ? cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        jb::set_error("jamun_gemm_tf32x3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return JAMUN_ECUDA;
-    }
-    if (wide) {
-        const int tiles = rows_pad / 128;
-        int groups = jb::kNumSMs / tiles;  // few tiles: run the column-block passes of a tile on several CTAs
-        if (groups > col_blocks) groups = col_blocks;
-        if (groups < 1) groups = 1;
-        P.cb_groups = groups;
-        gemm_tf32x3_kernel<true><<<dim3(tiles, groups), kThreads, smem, jb::as_stream(stream)>>>(P);
-    }
-    else gemm_tf32x3_kernel<false><<<dim3(rows_pad / 128, k_splits), kThreads, smem, jb::as_stream(stream)>>>(P);
-    if (k_splits > 1) {
-        int4 c0 = {0, 0, 0, 0}, nc = {0, 0, 0, 0};
-        int* pc0 = &c0.x;
-        int* pnc = &nc.x;
-        long long width = 0;
-        for (int s = 0; s < nseg; ++s) pc0[s] = out_col[s], pnc[s] = n_valid[s], width += n_valid[s];
-        long long total = (long long)rows * width;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > jb::kNumSMs * 8) blocks = jb::kNumSMs * 8;
-        gemm_splitk_reduce_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(partial, P.partial_stride, k_splits, rows, out_ld, c0, nc,
-                                                                            nseg, out);
-    }
-    JB_CHECK_LAUNCH();
-    return JAMUN_OK;
+    return f16 ? gemm_launch_t<true>(P, nseg, n_valid, out_col, col_blocks, rows, rows_pad, out, out_ld, k_splits, partial, stream)
+               : gemm_launch_t<false>(P, nseg, n_valid, out_col, col_blocks, rows, rows_pad, out, out_ld, k_splits, partial, stream);
 }

@@ -24,6 +24,10 @@ CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
 # aggregate builder of the tensor-core path: "tc" = tcgen05 per-node products (jamun_conv_build_tc) with the 0e(x)1e->1e
 # gather (jamun_conv_p2) on a side stream; "ffma" = the FP32-pipe builder jamun_conv_build_a (exact fp32 aggregate)
 BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
+# tensor-core split of the sampling path's GEMMs: "f16" = fp16 hi/lo split, tcgen05 kind::f16 (jamun_gemm_f16x3: half the MMA
+# instructions of the tf32 form at the same 11-bit significands; weights pre-scaled into the fp16 range when the plan is built,
+# operand overflow reported through Topology.gemm_status); "tf32" = jamun_gemm_tf32x3.  Read when a plan is built.
+GEMM_KIND = os.environ.get("JAMUN_B200_GEMM", "f16")
 CELL_LIST_MIN_CHAIN = 2560  # longer chains use the cell-list search.  Measured on B200 (tools/time_radius.py, 512 k atoms, CSR build incl. the out-edge index): n=1000 brute 2.37 ms / cells 2.99 ms; n=3000 3.89 / 3.75; n=6000 6.21 / 5.59 -- the ascending scan stops after 33 hits, so the O(n^2) bound only bites beyond ~2.5 k atoms
 Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
@@ -110,6 +114,14 @@ class Topology:
         self.y0 = None
         self.y0_key = None
         self.csr_generation = 0  # bumped by every writer of the CSR buffers (Denoiser.add_edges tags batches with it)
+        self.gemm_status = torch.zeros(1, dtype=torch.int32, device=dev)  # bit 0: an fp16-split GEMM operand left the fp16 range
+
+    def check_status(self) -> None:
+        """Host sync: raise if a kernel of the fp16-split path reported an operand outside the fp16 range since the last check."""
+        if int(self.gemm_status.item()) != 0:
+            self.gemm_status.zero_()
+            raise FloatingPointError("jamun_b200: an activation exceeded the fp16 range (65504) in the fp16-split tensor-core GEMM; "
+                                     "results of this call are invalid -- set JAMUN_B200_GEMM=tf32 and rebuild the plan")
 
     def build_csr(self, pos: torch.Tensor, r_cut: float):
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""
@@ -173,6 +185,9 @@ class E3ConvPlan:
         self.c_noise = float(c_noise)
         self.device = dev
         self.serial = next(E3ConvPlan._serials)  # cache key for plan-dependent constants held by topologies
+        self.gemm_kind = os.environ.get("JAMUN_B200_GEMM", GEMM_KIND)
+        if self.gemm_kind not in ("f16", "tf32"):
+            raise ValueError(f"JAMUN_B200_GEMM={self.gemm_kind!r}: expected f16 or tf32")
         # Parameter re-layout happens on a host copy of the module (pure indexing, once per plan) and the results are uploaded;
         # the (hi | lo) operand images are produced on the device by jamun_pack_b -- one launch per operand, so building a
         # plan issues a few dozen launches of this library's kernels and no framework indexing kernels.
@@ -204,10 +219,20 @@ class E3ConvPlan:
                 ws[128:128 + host["s_in"]] = host["wskip_s"]
                 wv = host["wself_v"] if host["wskip_v"] is None else torch.cat([host["wself_v"], host["wskip_v"]], dim=0)
                 blk = {k: (up(v) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
-                blk["b0_img"], blk["b1_img"], blk["wy_img"] = packing.pack_conv_operands_device(blk["m0"], blk["m1"], blk["s_in"],
-                                                                                                blk["v_in"])
-                blk["tail_bs_img"] = ops.pack_b(up(ws), n_stages=ws.shape[0] // 32, n_pad=128)
-                blk["tail_bv_img"] = ops.pack_b(up(wv), n_stages=wv.shape[0] // 32, n_pad=32)
+                blk["gemm_kind"] = self.gemm_kind
+                if self.gemm_kind == "f16":
+                    # power-of-two pre-scales from the host copies (no device sync); undone through the GEMMs' alpha
+                    sc = blk["f16_scales"] = (ops.f16_scale(host["m0"]), ops.f16_scale(host["m1"]), ops.f16_scale(ws), ops.f16_scale(wv))
+                    blk["b0_img"], blk["b1_img"], blk["wy_img"] = packing.pack_conv_operands_device(
+                        blk["m0"], blk["m1"], blk["s_in"], blk["v_in"], f16_scales=sc[:2])
+                    blk["tail_bs_img"] = ops.pack_b_f16(up(ws), ws.shape[0] // 32, 128, sc[2])
+                    blk["tail_bv_img"] = ops.pack_b_f16(up(wv), wv.shape[0] // 32, 32, sc[3])
+                else:
+                    blk["f16_scales"] = (1.0, 1.0, 1.0, 1.0)
+                    blk["b0_img"], blk["b1_img"], blk["wy_img"] = packing.pack_conv_operands_device(blk["m0"], blk["m1"], blk["s_in"],
+                                                                                                    blk["v_in"])
+                    blk["tail_bs_img"] = ops.pack_b(up(ws), n_stages=ws.shape[0] // 32, n_pad=128)
+                    blk["tail_bv_img"] = ops.pack_b(up(wv), n_stages=wv.shape[0] // 32, n_pad=32)
                 self.blocks.append(blk)
             self.w0r_all = up(torch.stack([b.pack(emb)["w0r"] for b in [gc.initial_projector, *gc.layers]]))      # [L, 32, 64]
             self.b0eff_all = up(torch.stack([b.pack(emb)["b0eff"] for b in [gc.initial_projector, *gc.layers]]))  # [L, 2, 64]
@@ -237,8 +262,19 @@ class E3ConvPlan:
         return hit
 
 
+def _gemm(topo: Topology, kind: str, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, rs_ptr, out_ptr,
+          out_ld: int, **kw) -> None:
+    """One launch of the node-tile GEMM in the plan's operand format (alpha already divided by the fp16 weight pre-scale)."""
+    if kind == "f16":
+        ops.gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows, rows_pad, rs_ptr, out_ptr, out_ld,
+                       status=topo.gemm_status, **kw)
+    else:
+        kw.pop("addend_scale", None)
+        ops.gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows, rows_pad, rs_ptr, out_ptr, out_ld, **kw)
+
+
 def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows: int, rp: int, rs_ptr, out_ptr,
-              addend=None) -> None:
+              addend=None, kind: str = "tf32", addend_scale=None) -> None:
     """The contraction GEMM; with few row tiles (small batches) the K stages are split over several CTAs per tile."""
     tiles = (nrows + 127) // 128
     if addend is not None:
@@ -253,11 +289,16 @@ def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col,
         need = ks * nrows * ops.GATE_IN
         if getattr(topo, "gemm_partial", None) is None or topo.gemm_partial.numel() < need:
             topo.gemm_partial = torch.empty(need, dtype=torch.float32, device=topo.device)
-        ops.gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, ks,
-                               topo.gemm_partial)
+        if kind == "f16":
+            ops.gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, k_splits=ks,
+                           partial=topo.gemm_partial, status=topo.gemm_status)
+        else:
+            ops.gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, ks,
+                                   topo.gemm_partial)
     else:
-        ops.gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN,
-                        addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96])
+        _gemm(topo, kind, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN,
+              addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96],
+              addend_scale=None if addend is None else addend_scale)
 
 
 def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False) -> None:
@@ -278,6 +319,8 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         topo.y = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
         topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
         topo.t_edge = torch.empty(topo.cap, 32, dtype=torch.float32, device=topo.device)
+    kind, sc = b.get("gemm_kind", "tf32"), b.get("f16_scales", (1.0, 1.0, 1.0, 1.0))
+    wy_block = ns * 128 * 32 * (1 if kind == "f16" else 2)  # 4-byte words per column block of the wy images
     # per-node transform of the scalar inputs.  For the initial block the input (atom embedding x noise scale) does not depend
     # on positions, so its transform is computed once per (topology, plan) and kept.
     y_buf = topo.y
@@ -285,16 +328,16 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         if topo.y0 is None or topo.y0_key != y_const_key:
             topo.y0 = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
             ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
-            ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0], N, rows_all, None,
-                            topo.y0.data_ptr(), Y_LD, col_blocks=17, b_block_floats=ns * 2 * 128 * 32)
+            _gemm(topo, kind, [topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0 / sc[1]], N, rows_all,
+                  None, topo.y0.data_ptr(), Y_LD, col_blocks=17, b_block_floats=wy_block)
             topo.y0_key = y_const_key
         y_buf = topo.y0
     else:
         if topo.xs_op_of is not x:  # else the previous block's tail_mix has already written the packed scalars of x
             ops.pack_rows(x, 0, s_in, rows_all, topo.xs_op)
         topo.xs_op_of = None
-        ops.gemm_tf32x3([topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0], N, rows_all, None,
-                        topo.y.data_ptr(), Y_LD, col_blocks=17, b_block_floats=ns * 2 * 128 * 32)
+        _gemm(topo, kind, [topo.xs_op.data_ptr()], [b["wy_img"].data_ptr()], [ns], [128], [128], [0], [1.0 / sc[1]], N, rows_all, None,
+              topo.y.data_ptr(), Y_LD, col_blocks=17, b_block_floats=wy_block)
     base = topo.a_ws.data_ptr()
     a1_off = st0 * rp * 32
     comp = st1 * rp * 32
@@ -332,14 +375,14 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
             p2 = topo.p2.data_ptr() + 4 * row0 * 96
             addend = None if build_impl == "tc" else [None, p2, p2 + 4 * 32, p2 + 4 * 64]
             _contract(topo, a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
-                      [b["alpha0"], b["alpha1"], b["alpha1"], b["alpha1"]], nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
-                      out.data_ptr() + 4 * row0 * ops.GATE_IN, addend=addend)
+                      [b["alpha0"] / sc[0]] + [b["alpha1"] / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
+                      out.data_ptr() + 4 * row0 * ops.GATE_IN, addend=addend, kind=kind, addend_scale=[sc[0]] + [sc[1]] * 3)
         else:  # initial block: the 1e output is the path-2 gather alone, written in place
             if build_impl != "tc":
                 ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base, None, 0,
                                  out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
-            _contract(topo, [base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"]], nrows, rp,
-                      topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN)
+            _contract(topo, [base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"] / sc[0]], nrows, rp,
+                      topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, kind=kind)
 
 
 def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:
@@ -382,9 +425,10 @@ def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_sc
                       rowptr=topo.rowptr, rhat=topo.rhat, t_edge=topo.t_edge, p2_scale=b["alpha1"], conv_has_v=bool(b["v_in"]))
     else:
         ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
-    ops.gemm_tf32x3([base] + [a_v + 4 * c * comp for c in range(3)], [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3,
-                    [st_s, st_v, st_v, st_v], [128, 32, 32, 32], [120, 32, 32, 32], [0, 120, 152, 184], [1.0] * 4, N, rows_all, None,
-                    topo.ytail.data_ptr(), ops.HID)
+    sc = b.get("f16_scales", (1.0, 1.0, 1.0, 1.0))
+    _gemm(topo, b.get("gemm_kind", "tf32"), [base] + [a_v + 4 * c * comp for c in range(3)],
+          [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3, [st_s, st_v, st_v, st_v], [128, 32, 32, 32],
+          [120, 32, 32, 32], [0, 120, 152, 184], [1.0 / sc[2]] + [1.0 / sc[3]] * 3, N, rows_all, None, topo.ytail.data_ptr(), ops.HID)
     pack = x_scaled is not None and getattr(topo, "xs_op", None) is not None
     ops.tail_mix(topo.ytail, x_res, skip_w, s_next, x_new, x_scaled, topo.xs_op if pack else None, rows_all)
     topo.xs_op_of = x_scaled if pack else None

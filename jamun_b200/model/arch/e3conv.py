@@ -50,8 +50,10 @@ class E3Conv(torch.nn.Module):
 
     # ---- plan cache: re-pack when a parameter changed in place or the noise level changed
     def plan(self, c_noise: float, device) -> "engine.E3ConvPlan":
+        import os
+
         key = (float(c_noise), str(device), tuple(p._version for p in self.parameters()),
-               tuple(p.data_ptr() for p in self.parameters()))
+               tuple(p.data_ptr() for p in self.parameters()), os.environ.get("JAMUN_B200_GEMM", engine.GEMM_KIND))
         if self._plan is None or self._plan_key != key:
             self._plan = engine.E3ConvPlan(self, float(c_noise), device)
             self._plan_key = key
@@ -75,5 +77,7 @@ class E3Conv(torch.nn.Module):
         plan = self.plan(float(torch.as_tensor(c_noise).reshape(-1)[0]), pos.device)
         g = torch.empty_like(pos)
         engine.e3conv_forward(plan, topo, pos.contiguous(), float(effective_radial_cutoff), g)
+        if plan.gemm_kind == "f16":
+            topo.check_status()
         data["pos"] = g
         return data

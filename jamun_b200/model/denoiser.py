@@ -159,6 +159,8 @@ class Denoiser(_Base):
                               seed=0, step=0)
         v_dummy = torch.zeros_like(y)
         ops.walk_step(y, v_dummy, ybar, p, g, topo.chain_ptr, prm, None, xhat, score)
+        if plan.gemm_kind == "f16" and not torch.cuda.is_current_stream_capturing():
+            topo.check_status()
         return xhat, score
 
     # ------------------------------------------------------------------ reference API

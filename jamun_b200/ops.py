@@ -266,6 +266,52 @@ def pack_b(src, n_stages: int, n_pad: int, row_map=None, k_src: Optional[int] = 
     return out
 
 
+def f16_scale(*weights) -> float:
+    """Power-of-two pre-scale for fp16-split weight images: the largest magnitude lands in [2^12, 2^13) (fp16 max 65504), so
+    every element within 2^-16 of it keeps a normal-range remainder.  Host sync (amax); call when a plan is built."""
+    import math
+
+    amax = max(float(w.detach().abs().max()) for w in weights if w is not None and w.numel())
+    if not math.isfinite(amax) or amax <= 0.0:
+        return 1.0
+    return float(2.0 ** (12 - math.floor(math.log2(amax))))
+
+
+def pack_b_f16(src, n_stages: int, n_pad: int, scale: float, row_map=None, k_src: Optional[int] = None, n_valid: Optional[int] = None,
+               n_inner: Optional[int] = None, outer_rows: int = 0, col_blocks: int = 1, transpose: bool = False, out=None):
+    """Row-major weights -> fp16-split stage images of jamun_gemm_f16x3 ([col_blocks, n_stages, n_pad*32] 4-byte words)."""
+    assert src.dim() == 2
+    k_src = src.shape[0] if k_src is None else k_src
+    n_valid = src.shape[1] if n_valid is None else n_valid
+    n_inner = max(n_valid, 1) if n_inner is None else n_inner
+    shape = (col_blocks, n_stages, n_pad * 32) if col_blocks > 1 else (n_stages, n_pad * 32)
+    out = torch.empty(shape, dtype=torch.float32, device=src.device) if out is None else out
+    rc = _lib.lib().jamun_pack_b_f16(_ptr(src), src.stride(0), _ptr(row_map, torch.int32), k_src, n_stages, n_valid, n_inner,
+                                     outer_rows, n_pad, col_blocks, int(transpose), float(scale), _ptr(out), _stream())
+    _lib.check(rc, "jamun_pack_b_f16")
+    _count()
+    return out
+
+
+def gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr, out_ptr,
+               out_ld: int, addend_ptrs=None, addend_ld=None, col_blocks: int = 1, b_block_floats: int = 0, k_splits: int = 1,
+               partial=None, status=None, addend_scale=None):
+    """fp16-split form of gemm_tf32x3 (B images from pack_b_f16, alpha already divided by their scale).  status: int32 device
+    word whose bit 0 reports an A value outside the fp16 range."""
+    n = len(a_ptrs)
+    VP, IA, FA = C.c_void_p * n, C.c_int * n, C.c_float * n
+    ad = VP(*addend_ptrs) if addend_ptrs is not None else None
+    adl = IA(*addend_ld) if addend_ld is not None else None
+    if k_splits > 1:
+        assert partial is not None and partial.numel() >= k_splits * rows * out_ld
+    ads = FA(*addend_scale) if addend_scale is not None else None
+    rc = _lib.lib().jamun_gemm_f16x3(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col), FA(*alpha),
+                                     ad, adl, ads, col_blocks, b_block_floats, rows, rows_pad, row_scale_ptr, out_ptr, out_ld,
+                                     int(k_splits), _ptr(partial), _ptr(status, torch.int32), _stream())
+    _lib.check(rc, "jamun_gemm_f16x3")
+    _count(2 if k_splits > 1 else 1)
+
+
 def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr,
                 out_ptr, out_ld: int, addend_ptrs=None, addend_ld=None, col_blocks: int = 1, b_block_floats: int = 0):
     """Raw-pointer front end (segments are slices of larger workspaces).  All lists have one entry per segment."""
@@ -536,6 +582,37 @@ def stage_atb(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, nslots:
                                     b_comp_stride, W, _ptr(out), mode, out_rows, r0, rn, _stream())
     _lib.check(rc, "jamun_stage_atb")
     _count()
+
+
+ATB_IMPL = None  # "tc" (tcgen05, default) | "simt"; read from JAMUN_B200_ATB at call time
+
+
+def stage_atb_auto(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, nslots: int, rows: int, rows_pad: int, b, b_col0: int,
+                   b_comp_stride: int, W: int, out, mode: int, out_rows: int, slot_row0=None, slot_rows=None):
+    """dW = A^T . B over the nodes: the tensor-core kernel (jamun_stage_atb_tc) unless JAMUN_B200_ATB=simt."""
+    import os
+
+    if (ATB_IMPL or os.environ.get("JAMUN_B200_ATB", "tc")) == "simt":
+        return stage_atb(a_ptr, a_comp_stride, ncomp, n_stages, nslots, rows, rows_pad, b, b_col0, b_comp_stride, W, out, mode, out_rows,
+                         slot_row0, slot_rows)
+    nslots_b = (W + 31) // 32
+    per = 2 * nslots_b * rows_pad * 32
+    bsplit = torch.empty(ncomp * per, dtype=torch.float32, device=b.device)
+    for c in range(ncomp):
+        rc = _lib.lib().jamun_pack_rows_split(_ptr(b), b.stride(0), b_col0 + c * b_comp_stride, W, rows, rows_pad, nslots_b,
+                                              bsplit.data_ptr() + 4 * c * per, _stream())
+        _lib.check(rc, "jamun_pack_rows_split")
+    m_tiles = (n_stages + 3) // 4
+    kq = ncomp * ((rows + 31) // 32)
+    k_splits = max(1, min(kq, (4 * 148 + m_tiles - 1) // m_tiles, 64))  # ~4 CTAs per SM, bounded accumulation length
+    partial = _scratch_for(int(_lib.lib().jamun_stage_atb_tc_scratch(n_stages, W, k_splits)), b.device)
+    IA = C.c_int * nslots
+    r0 = IA(*slot_row0) if slot_row0 is not None else None
+    rn = IA(*slot_rows) if slot_rows is not None else None
+    rc = _lib.lib().jamun_stage_atb_tc(a_ptr, int(a_comp_stride), ncomp, n_stages, nslots, rows, rows_pad, _ptr(bsplit), W, _ptr(out), mode,
+                                       out_rows, r0, rn, k_splits, _ptr(partial), _stream())
+    _lib.check(rc, "jamun_stage_atb_tc")
+    _count(ncomp + 2)
 
 
 def conv_bwd_edge(x, s_in: int, v_in: int, rowptr, col, h, rhat, dA0, dA1, dh, dxe):

@@ -93,15 +93,23 @@ def conv_row_maps(s_in: int, v_in: int, device):
     return hit
 
 
-def pack_conv_operands_device(m0: torch.Tensor, m1: torch.Tensor, s_in: int, v_in: int):
+def pack_conv_operands_device(m0: torch.Tensor, m1: torch.Tensor, s_in: int, v_in: int, f16_scales=None):
     """(b0_img, b1_img | None, wy_img) for CUDA tensors m0 [65, s_in+v_in, 152], m1 [65, s_in+2 v_in, 32] -- three launches
-    of jamun_pack_b.  Equal, bit for bit, to pack_b_images / pack_b_column_blocks of conv_k_layout(m0, m1, s_in, v_in)."""
+    of jamun_pack_b.  Equal, bit for bit, to pack_b_images / pack_b_column_blocks of conv_k_layout(m0, m1, s_in, v_in).
+    f16_scales = (scale of m0, scale of m1): the fp16-split images of jamun_gemm_f16x3 instead (jamun_pack_b_f16)."""
     from . import ops
 
     ns = (s_in + 31) // 32
     map0, map1 = conv_row_maps(s_in, v_in, m0.device)
     K = m0.shape[0]
     u0, u1 = s_in + v_in, s_in + 2 * v_in
+    if f16_scales is not None:
+        sc0, sc1 = f16_scales
+        b0 = ops.pack_b_f16(m0.reshape(K * u0, m0.shape[2]), K * (ns * 32 + v_in) // 32, 160, sc0, row_map=map0)
+        b1 = ops.pack_b_f16(m1.reshape(K * u1, m1.shape[2]), K * 2 * v_in // 32, 32, sc1, row_map=map1) if v_in else None
+        wy = ops.pack_b_f16(m1.reshape(K * u1, m1.shape[2]), ns, 128, sc1, k_src=s_in, n_valid=K * m1.shape[2], n_inner=m1.shape[2],
+                            outer_rows=u1, col_blocks=17)
+        return b0, b1, wy
     b0 = ops.pack_b(m0.reshape(K * u0, m0.shape[2]), n_stages=K * (ns * 32 + v_in) // 32, n_pad=160, row_map=map0)
     b1 = ops.pack_b(m1.reshape(K * u1, m1.shape[2]), n_stages=K * 2 * v_in // 32, n_pad=32, row_map=map1) if v_in else None
     # W_y[u, k'*32 + w] = m1[k', u, w] for the scalar rows u < s_in; 65*32 = 2080 columns in 17 blocks of 128

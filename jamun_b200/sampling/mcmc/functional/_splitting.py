@@ -246,6 +246,8 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
                 ops._count(ws.graph_launches[(gkey, i in slot)])
         if steps > 1:
             eager_step(steps - 1)
+    if plan.gemm_kind == "f16":
+        topo.check_status()  # 4-byte read-back: the fp16-split GEMMs report operands outside the fp16 range here
     out_y, out_v, out_x = ws.y.clone(), ws.v.clone(), ws.xhat.clone()
     y_traj = ws.y_traj.clone() if ws.y_traj is not None else None
     xhat_traj = ws.xhat_traj.clone() if ws.xhat_traj is not None else None

@@ -251,9 +251,22 @@ def test_walk_step_matches_oracle_baoab(models):
     for key in ("y", "v", "xhat", "y_traj", "xhat_traj", "score_traj"):
         got, want = out[key].cpu(), ref[key]
         assert got.shape == want.shape, key
+        # free-running: both walks integrate their own scores for 6 steps, so per-step differences compound (x2 allowance)
         tol = dict(rtol=2e-4, atol=2e-5 if "score" not in key else 2e-5 / SIGMA ** 2)
         assert torch.allclose(got, want, **tol), (key, (got - want).abs().max())
     assert out["sample"] is out["xhat"]
+    # teacher-forced, per step, at north_star's tolerance: the kernels evaluated at the oracle's own y_t
+    for i in range(steps):
+        yb = batch.clone("pos")
+        yb.pos = ref["y_traj"][i].cuda().contiguous()
+        xh = prod.xhat(yb, SIGMA).pos.cpu()
+        sc = prod.score(yb, SIGMA).cpu()
+        assert torch.allclose(xh, ref["xhat_traj"][i], rtol=1e-4, atol=1e-5), (i, (xh - ref["xhat_traj"][i]).abs().max())
+        sref = ref["score_traj"][i]
+        # score = (xhat - y) / sigma^2: an absolute error of 1e-5 on xhat is 1e-5 / sigma^2 on the score
+        assert torch.allclose(sc, sref, rtol=1e-4, atol=1e-5 / SIGMA ** 2), (i, (sc - sref).abs().max())
+        rel = ((sc - sref).norm() / sref.norm()).item()
+        assert rel <= 1e-4, f"step {i}: relative score error {rel:.2e}"
 
 
 def test_generic_baoab_and_aboba_protocol():
@@ -483,7 +496,8 @@ def test_dense_graph_tc_equals_exact_pipeline(models, monkeypatch):
     from jamun_b200 import data, engine, synthetic
 
     o32, o64, prod = models
-    t = synthetic.make_tensors([1000] * 5 + [333], n_res=100)
+    sizes = [1000] * 5 + [333, 150]
+    t = synthetic.make_tensors(sizes, n_res=100)
     gen = torch.Generator().manual_seed(23)
     y = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=gen)
     yb = data.Batch.from_tensors(t).to("cuda")
@@ -501,6 +515,38 @@ def test_dense_graph_tc_equals_exact_pipeline(models, monkeypatch):
     x_simt = run()
     assert torch.isfinite(x).all()
     assert torch.allclose(x, x_simt, rtol=1e-4, atol=1e-5), (x - x_simt).abs().max()
+    # the last (150-atom, in-degree ~ cap) chain alone against the oracle: chains are independent
+    n_tail = sizes[-1]
+    t_tail = synthetic.make_tensors(sizes[-1:], n_res=100, first_chain_id=len(sizes) - 1)
+    assert torch.equal(t_tail["pos"], t["pos"][-n_tail:])
+    with torch.no_grad():
+        ref = o32.xhat(make_oracle_batch(t_tail).with_pos(y[-n_tail:]), SIGMA)
+    assert torch.allclose(x[-n_tail:], ref, rtol=1e-4, atol=1e-5), (x[-n_tail:] - ref).abs().max()
+
+
+def test_4aa_size_oracle_slice(models):
+    """BASELINE config 3's per-GPU shape (1024 uncapped 4AA chains, ~35 k atoms, in-degree ~ 20): the last 8 chains against the
+    oracle at north_star's tolerance (xhat rtol 1e-4 / atol 1e-5; scores the same relative error)."""
+    from jamun_b200 import data, synthetic
+
+    o32, o64, prod = models
+    sizes = synthetic.workload_sizes("4AA", 1024)
+    t = synthetic.make_tensors(sizes, n_res=4)
+    y = t["pos"] + SIGMA * torch.randn(t["pos"].shape, generator=torch.Generator().manual_seed(29))
+    yb = data.Batch.from_tensors(t).to("cuda")
+    yb.pos = y.cuda().contiguous()
+    x = prod.xhat(yb, SIGMA).pos.cpu()
+    sc = prod.score(yb, SIGMA).cpu()
+    assert torch.isfinite(x).all()
+    k = 8
+    n_tail = sum(sizes[-k:])
+    t_tail = synthetic.make_tensors(sizes[-k:], n_res=4, first_chain_id=len(sizes) - k)
+    assert torch.equal(t_tail["pos"], t["pos"][-n_tail:])
+    with torch.no_grad():
+        ob = make_oracle_batch(t_tail).with_pos(y[-n_tail:])
+        ref, sref = o32.xhat(ob, SIGMA), o32.score(ob, SIGMA)
+    assert torch.allclose(x[-n_tail:], ref, rtol=1e-4, atol=1e-5), (x[-n_tail:] - ref).abs().max()
+    assert ((sc[-n_tail:] - sref).norm() / sref.norm()).item() <= 1e-4
 
 
 def test_full_size_graph_replay_equals_eager(models):

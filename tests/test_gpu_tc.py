@@ -6,12 +6,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run_gemm(A_list, B_list, n_pads, rows, row_scale=None, alphas=None):
+def _run_gemm(A_list, B_list, n_pads, rows, row_scale=None, alphas=None, kind="tf32"):
     from jamun_b200 import ops, packing
 
     rows_pad = (rows + 127) // 128 * 128
     dev = "cuda"
-    a_bufs, b_bufs, n_stages, n_valid, out_col = [], [], [], [], []
+    a_bufs, b_bufs, n_stages, n_valid, out_col, scales = [], [], [], [], [], []
     col = 0
     for A, B, n_pad in zip(A_list, B_list, n_pads):
         K = A.shape[1]
@@ -25,13 +25,25 @@ def _run_gemm(A_list, B_list, n_pads, rows, row_scale=None, alphas=None):
         pos = (((ll // 4) ^ (rr % 8)) * 4 + ll % 4).expand(S, rows_pad, 32)
         a_sw = torch.empty_like(a_sm).scatter_(2, pos, a_sm)
         a_bufs.append(a_sw.contiguous())
-        b_bufs.append(packing.pack_b_images(B.to(dev), n_pad))
+        if kind == "f16":
+            scales.append(ops.f16_scale(B))
+            b_bufs.append(ops.pack_b_f16(B.to(dev).contiguous(), S, n_pad, scales[-1]))
+        else:
+            b_bufs.append(packing.pack_b_images(B.to(dev), n_pad))
         n_stages.append(S)
         n_valid.append(B.shape[1])
         out_col.append(col)
         col += B.shape[1]
     out = torch.full((rows, col), float("nan"), device=dev)
     alphas = alphas or [1.0] * len(A_list)
+    if kind == "f16":
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.gemm_f16x3([a.data_ptr() for a in a_bufs], [b.data_ptr() for b in b_bufs], n_stages, list(n_pads), n_valid, out_col,
+                       [a / s for a, s in zip(alphas, scales)], rows, rows_pad, row_scale.data_ptr() if row_scale is not None else None,
+                       out.data_ptr(), col, status=status)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        return out
     ops.gemm_tf32x3([a.data_ptr() for a in a_bufs], [b.data_ptr() for b in b_bufs], n_stages, list(n_pads), n_valid, out_col,
                     alphas, rows, rows_pad, row_scale.data_ptr() if row_scale is not None else None, out.data_ptr(), col)
     torch.cuda.synchronize()
@@ -40,11 +52,12 @@ def _run_gemm(A_list, B_list, n_pads, rows, row_scale=None, alphas=None):
 
 @pytest.mark.parametrize("rows,K,N,n_pad", [(128, 32, 32, 32), (128, 64, 152, 160), (300, 32 * 9, 152, 160), (77, 32 * 13, 32, 32),
                                             (1000, 32 * 40, 16, 16)])
-def test_gemm_tf32x3_matches_fp64(rows, K, N, n_pad):
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_gemm_tf32x3_matches_fp64(rows, K, N, n_pad, kind):
     gen = torch.Generator().manual_seed(rows + K + N)
     A = torch.randn(rows, K, generator=gen)
     B = torch.randn(K, N, generator=gen) * 0.3
-    out = _run_gemm([A], [B], [n_pad], rows).cpu().double()
+    out = _run_gemm([A], [B], [n_pad], rows, kind=kind).cpu().double()
     ref = A.double() @ B.double()
     err = (out - ref).abs().max().item()
     scale = ref.abs().max().item()
@@ -54,33 +67,55 @@ def test_gemm_tf32x3_matches_fp64(rows, K, N, n_pad):
     assert err <= 1e-4 * (A.abs().double() @ B.abs().double()).max().item() / 30
 
 
-def test_gemm_multi_segment_scaling_and_wraparound():
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_gemm_multi_segment_scaling_and_wraparound(kind):
     gen = torch.Generator().manual_seed(7)
     rows = 260
     A0, A1, A2, A3 = (torch.randn(rows, 32 * s, generator=gen) for s in (7, 5, 5, 5))
     B0 = torch.randn(32 * 7, 152, generator=gen)
     B1 = torch.randn(32 * 5, 32, generator=gen)
     rs = torch.rand(rows, generator=gen) + 0.5
-    out = _run_gemm([A0, A1, A2, A3], [B0, B1, B1, B1], [160, 32, 32, 32], rows, row_scale=rs.cuda(), alphas=[0.5, 2.0, 2.0, 2.0])
+    out = _run_gemm([A0, A1, A2, A3], [B0, B1, B1, B1], [160, 32, 32, 32], rows, row_scale=rs.cuda(), alphas=[0.5, 2.0, 2.0, 2.0], kind=kind)
     ref = torch.cat([0.5 * A0.double() @ B0.double()] + [2.0 * a.double() @ B1.double() for a in (A1, A2, A3)], dim=1) * rs.double()[:, None]
     err = (out.cpu().double() - ref).abs().max().item()
     assert err <= 3e-6 * ref.abs().max().item(), err
 
 
-def test_gemm_hi_lo_exactness():
-    """Inputs exactly representable in tf32 x small integers: the result must be exact."""
+@pytest.mark.parametrize("kind", ["tf32", "f16"])
+def test_gemm_hi_lo_exactness(kind):
+    """Inputs exactly representable in tf32 / fp16 x small integers: the result must be exact."""
     A = torch.randint(-8, 9, (128, 64)).float()
     B = torch.randint(-8, 9, (64, 32)).float()
-    out = _run_gemm([A], [B], [32], 128).cpu()
+    out = _run_gemm([A], [B], [32], 128, kind=kind).cpu()
     assert torch.equal(out, A @ B)
 
 
+def test_gemm_f16x3_wide_dynamic_range_and_overflow_flag():
+    """fp16 split: elements 2^-20 .. 2^3 of the operand scale keep fp32-level accuracy (remainders go subnormal gracefully);
+    an operand value beyond the fp16 range raises the status bit instead of passing silently."""
+    from jamun_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    rows, K, N = 256, 32 * 20, 152
+    A = torch.randn(rows, K, generator=gen) * torch.exp2(torch.randint(-20, 4, (rows, K), generator=gen).float())
+    B = torch.randn(K, N, generator=gen) * torch.exp2(torch.randint(-12, 1, (K, N), generator=gen).float()) * 1e-2
+    out = _run_gemm([A], [B], [160], rows, kind="f16").cpu().double()
+    ref = A.double() @ B.double()
+    assert (out - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+    A[5, 7] = 1.0e5
+    with pytest.raises(AssertionError):
+        _run_gemm([A], [B], [160], rows, kind="f16")
+
+
+@pytest.mark.parametrize("gemm", ["f16", "tf32"])
 @pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31], [260, 2, 131]])
-def test_conv_tc_matches_simt_and_fp64(models, sizes):
-    """Two-launch tensor-core conv == exact-fp32 SIMT conv (same operands) to ~1e-6, for the initial and a hidden block."""
+def test_conv_tc_matches_simt_and_fp64(models, sizes, gemm, monkeypatch):
+    """Two-launch tensor-core conv == exact-fp32 SIMT conv (same operands) to ~1e-6, for the initial and a hidden block,
+    with the fp16-split (default) and the tf32-split contraction."""
     import kernel_model as KM
     from jamun_b200 import data, engine, ops, synthetic
 
+    monkeypatch.setenv("JAMUN_B200_GEMM", gemm)
     o32, o64, prod = models
     t = synthetic.make_tensors(sizes)
     gen = torch.Generator().manual_seed(1)
@@ -108,6 +143,7 @@ def test_conv_tc_matches_simt_and_fp64(models, sizes):
         torch.cuda.synchronize()
         err = (got - ref).abs().max().item()
         scale = ref.abs().max().item()
+        assert b["gemm_kind"] == gemm and int(topo.gemm_status.item()) == 0
         assert err <= 5e-5 * max(1.0, scale), f"block {l}: err {err} scale {scale}"  # tcgen05 fp32 accumulation truncates
 
 
@@ -136,6 +172,21 @@ def test_gemm_column_blocks_and_addend():
                     addend_ptrs=[addc.data_ptr()], addend_ld=[32])
     ref2 = 0.5 * (A.double() @ W[:, :32].double() + add.double())
     assert (out2.cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
+    # the fp16-split form: column blocks (image stride in 4-byte words is half the tf32 one) and the addend joining the
+    # pre-scaled accumulator
+    sc = ops.f16_scale(W)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out3 = torch.full((rows, N), float("nan"), device="cuda")
+    img3 = ops.pack_b_f16(W.cuda(), K // 32, 160, sc, n_valid=N, n_inner=N, col_blocks=3)
+    ops.gemm_f16x3([a_op.data_ptr()], [img3.data_ptr()], [K // 32], [160], [160], [0], [1.0 / sc], rows, rows_pad, None, out3.data_ptr(), N,
+                   col_blocks=3, b_block_floats=K // 32 * 160 * 32, status=status)
+    assert (out3.cpu().double() - ref).abs().max() <= 1e-5 * ref.abs().max()
+    out4 = torch.full((rows, 32), float("nan"), device="cuda")
+    img4 = ops.pack_b_f16(W[:, :32].contiguous().cuda(), K // 32, 32, sc)
+    ops.gemm_f16x3([a_op.data_ptr()], [img4.data_ptr()], [K // 32], [32], [32], [0], [0.5 / sc], rows, rows_pad, None, out4.data_ptr(), 32,
+                   addend_ptrs=[addc.data_ptr()], addend_ld=[32], addend_scale=[sc], status=status)
+    assert (out4.cpu().double() - ref2).abs().max() <= 1e-5 * ref2.abs().max()
+    assert int(status.item()) == 0
 
 
 @pytest.mark.parametrize("sizes", [[22, 15, 9, 30], [57, 3, 1, 40, 40, 17, 64, 65, 31]])

@@ -340,3 +340,51 @@ def test_operator_registrations_pass_opcheck(models):
     args = (x, h, topo.rhat, topo.rowptr, topo.col, topo.edst, topo.src_rowptr, topo.src_eid, pk["m0"].detach().requires_grad_(True),
             pk["m1"].detach().requires_grad_(True), 120, 32, pk["alpha0"], pk["alpha1"])
     torch.library.opcheck(torch.ops.jamun_b200.conv.default, args, test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+@pytest.mark.parametrize("rows,n_stages,nslots,ncomp,W,mode", [(300, 10, 5, 1, 152, 0), (1000, 6, 2, 3, 32, 0), (77, 65, 1, 1, 120, 1),
+                                                              (4000, 8, 2, 1, 56, 0)])
+def test_stage_atb_tensor_core_matches_simt_and_fp64(rows, n_stages, nslots, ncomp, W, mode):
+    """dW = A^T . B over the nodes: tcgen05 kernel (MN-major operands, TS mode, split over the node range) vs the CUDA-core
+    kernel vs fp64."""
+    from jamun_b200 import ops
+
+    gen = torch.Generator().manual_seed(rows + W)
+    rows_pad = (rows + 127) // 128 * 128
+    A = torch.randn(ncomp, n_stages * 32, rows, generator=gen)          # [c][(stage, u)][row]
+    B = torch.randn(rows, 40 + ncomp * W, generator=gen)
+    a_op = torch.full((ncomp, n_stages, rows_pad, 32), float("nan"))   # stale rows beyond `rows` must be ignored
+    a_op[:, :, :rows] = A.reshape(ncomp, n_stages, 32, rows).permute(0, 1, 3, 2)
+    rr = torch.arange(rows_pad)[:, None]
+    ll = torch.arange(32)[None, :]
+    pos = (((ll // 4) ^ (rr % 8)) * 4 + ll % 4).expand(ncomp, n_stages, rows_pad, 32)
+    a_sw = torch.empty_like(a_op).scatter_(3, pos, a_op).cuda().contiguous()
+    Bc = B.cuda().contiguous()
+    ref = sum(A[c].double() @ B[:, 40 + c * W: 40 + (c + 1) * W].double() for c in range(ncomp))  # [(stage,u), W]
+    K = n_stages // nslots
+    if mode == 0:
+        slot_row0, slot_rows = [40 * s for s in range(nslots)], [32 if s % 2 == 0 else 24 for s in range(nslots)]
+        out_rows = 40 * nslots
+    else:
+        slot_row0 = slot_rows = None
+        out_rows = W + 3
+    outs = {}
+    for impl in ("simt", "tc"):
+        ops.ATB_IMPL = impl
+        out = torch.zeros(K, out_rows, W if mode == 0 else 32, device="cuda")
+        ops.stage_atb_auto(a_sw.data_ptr(), n_stages * rows_pad * 32, ncomp, n_stages, nslots, rows, rows_pad, Bc, 40, W, W, out, mode,
+                           out_rows, slot_row0, slot_rows)
+        torch.cuda.synchronize()
+        outs[impl] = out.cpu()
+    ops.ATB_IMPL = None
+    r4 = ref.reshape(K, nslots, 32, W)
+    want = torch.zeros_like(outs["tc"], dtype=torch.float64)
+    if mode == 0:
+        for s in range(nslots):
+            want[:, slot_row0[s]:slot_row0[s] + slot_rows[s]] = r4[:, s, :slot_rows[s]]
+    else:
+        want[:, :W] = r4[:, 0].permute(0, 2, 1)
+    scale = ref.abs().max().item()
+    for impl in ("simt", "tc"):
+        assert torch.isfinite(outs[impl]).all(), impl
+        assert (outs[impl].double() - want).abs().max().item() <= 3e-5 * scale, impl
