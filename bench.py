@@ -406,15 +406,17 @@ def roofline_block(model, state, workload, chains, dev):
     nrows = min(rp, atoms)
     base = topo.a_ws.data_ptr()
     _engine.conv_tc_join(topo, blk)
+    tiled = blk["gemm_kind"] == "f16" and os.environ.get("JAMUN_B200_A_LAYOUT", _engine.A_LAYOUT) == "tile"
     build_ms = time_kernel(lambda: ops.conv_build_tc(x_in, 120, 32, topo.rowptr, topo.col, topo.h, topo.rhat, 0, nrows, rp, base,
-                                                     base + 4 * a1_off, comp, topo.inv_deg))
+                                                     base + 4 * a1_off, comp, topo.inv_deg, tiled=tiled))
     p2_ms = time_kernel(lambda: ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, topo.y, topo.t_edge,
                                             topo.p2.data_ptr(), 96, blk["alpha1"]))
     kind, sc = blk["gemm_kind"], blk["f16_scales"]
     gemm_ms = time_kernel(lambda: _engine._gemm(
         topo, kind, [base] + [base + 4 * (a1_off + c * comp) for c in range(3)],
         [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32],
-        [0, 152, 184, 216], [1.0 / sc[0]] + [1.0 / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248))
+        [0, 152, 184, 216], [1.0 / sc[0]] + [1.0 / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr(), topo.conv.data_ptr(), 248,
+        **({"a_tile_major": True} if tiled else {})))
     rows_all = (atoms + 127) // 128 * 128
     ygemm_ms = time_kernel(lambda: _engine._gemm(topo, kind, [topo.xs_op.data_ptr()], [blk["wy_img"].data_ptr()], [4], [128], [128], [0],
                                                  [1.0 / sc[1]], atoms, rows_all, None, topo.y.data_ptr(), _engine.Y_LD, col_blocks=17,
@@ -440,7 +442,7 @@ def roofline_block(model, state, workload, chains, dev):
              "peak_source": f"{pk_src} bf16 burst{'' if f16 else ' / 2'} (dense {'fp16' if f16 else 'tf32'} rate; fp32 parity needs 3 "
                             "split products per FLOP, so 1/3 is the ceiling)",
              "hbm_GBps_A_operand": a_bytes / (gemm_ms * 1e-3) / 1e9, "hbm_frac_of_measured": hbm_frac})
-    head.update({"ms_per_launch": gemm_ms, "mean_in_degree": deg, "gemm_kind": kind,
+    head.update({"ms_per_launch": gemm_ms, "mean_in_degree": deg, "gemm_kind": kind, "a_layout": "tile" if tiled else "stage",
             "second_kernel": {"kernel": "conv_build_tc_kernel<120,32> (per-node aggregate F^T.H on tcgen05, 3xTF32; writes the A operand)",
                               "bound": "hbm", "ms_per_launch": build_ms, "achieved": a_bytes / (build_ms * 1e-3) / 1e9,
                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / (build_ms * 1e-3) / 1e9 / pk["hbm_gbs"],

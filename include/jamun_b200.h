@@ -181,14 +181,21 @@ int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const float* const
  * (fp16 range), the caller folds 1/scale into alpha and passes the scale as addend_scale[s] (the addend joins the scaled
  * accumulator: out = (acc + addend_scale * addend) * alpha * row_scale; NULL: 1).  status (or NULL): bit 0 is OR-ed in when an element of a exceeds the fp16
  * range (the result is then invalid and the caller must use jamun_gemm_tf32x3).  k_splits > 1: split-K as
- * jamun_gemm_tf32x3_splitk (partial scratch, no addend, no column blocks). */
+ * jamun_gemm_tf32x3_splitk (partial scratch, no addend, no column blocks).  a_tile_major: the operand layout of
+ * jamun_conv_build_tc_tiled. */
 int jamun_pack_b_f16(const float* src, int ld, const int* row_map, int K_src, int n_stages, int N_valid, int n_inner,
                      int outer_rows, int n_pad, int col_blocks, int transpose, float scale, float* out, jamun_stream_t stream);
 int jamun_gemm_f16x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                      const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                      const int* addend_ld, const float* addend_scale, int col_blocks, long long b_block_floats, int rows,
                      int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
-                     jamun_stream_t stream);
+                     int a_tile_major, jamun_stream_t stream);
+/* jamun_conv_build_tc writing the tile-major operand layout [row / 128][stage][128][32] (all stages of a 128-row tile
+ * contiguous; rows_pad % 128 == 0), consumed by jamun_gemm_f16x3 with a_tile_major = 1: the 715 lines a node contributes then
+ * fall into one ~12 MB region instead of being rows_pad * 128 bytes apart, and a GEMM CTA streams its tile sequentially. */
+int jamun_conv_build_tc_tiled(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                              const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                              long long a1_comp_stride, float* inv_deg, jamun_stream_t stream);
 
 /* Gate + self-interaction + skip Linear + noise-conditional skip/scale
  * (e3tools/nn/_gate.py:63-64, _interaction.py:26-30, model/noise_conditioning.py:50-73,

@@ -36,6 +36,7 @@ _PROTOS = {
     "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
     "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
     "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
+    "jamun_conv_build_tc_tiled": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),
     "jamun_conv_p2": ([c_f, c_f, c_f, c_f, c_f, c_f, I, c_f, c_f, I, F, c_f, c_f], I),
     "jamun_csr_by_source": ([c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_pack_b": ([c_f, I, c_f, I, I, I, I, I, I, I, I, c_f, c_f], I),
@@ -73,7 +74,7 @@ _PROTOS = {
     "jamun_gemm_tf32x3_splitk": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                                   C.POINTER(F), I, I, c_f, c_f, I, I, c_f, c_f], I),
     "jamun_gemm_f16x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
-                          C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(F), I, C.c_longlong, I, I, c_f, c_f, I, I, c_f, c_f, c_f], I),
+                          C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(F), I, C.c_longlong, I, I, c_f, c_f, I, I, c_f, c_f, I, c_f], I),
     "jamun_pack_b_f16": ([c_f, I, c_f, I, I, I, I, I, I, I, I, F, c_f, c_f], I),
     "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f, c_f, c_f, F, I, c_f], I),

@@ -71,7 +71,8 @@ template <int S_IN, int V_IN, bool TRACE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                      const float* __restrict__ h, const float* __restrict__ rhat, int row0, int nrows, int rows_pad,
-                     float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride, float* __restrict__ inv_deg) {
+                     float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride, float* __restrict__ inv_deg,
+                     int tile_major, int pf_dist) {
     using SH = Shape<S_IN, V_IN>;
     constexpr int NS = SH::NS, NCOL = SH::NCOL, NT = SH::NT;
     constexpr int kBufs = 2 * NT;
@@ -137,7 +138,33 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             e0_nn = rowptr[row0 + r_begin + r_step];
             deg_nn = rowptr[row0 + r_begin + r_step + 1] - e0_nn;
         }
+        // L2 prefetch of the read-once streams: the radial channels h and unit vectors rhat of a node's in-edges are contiguous
+        // (receiver-sorted CSR) and are touched exactly once, so every gather of them is a compulsory L2 miss served by an HBM
+        // that is saturated with this kernel's own 1.6 GB of writes (measured: 31 % of the read sectors miss, the gather of an
+        // item takes ~5.5 k cycles and the epilogue / MMA roles starve behind it).  One lane asks the L2 for the rows of the
+        // item `pf_dist` nodes ahead (cp.async.bulk.prefetch.L2: no registers, no shared memory); its extents are loaded one
+        // iteration earlier so the request never waits on its own index loads.
+        int pf_a = 0, pf_b = 0;
+        if (pf_dist > 0 && w == 0 && lane == 0 && r_begin + pf_dist * r_step < r_end) {
+            pf_a = rowptr[row0 + r_begin + pf_dist * r_step];
+            pf_b = rowptr[row0 + r_begin + pf_dist * r_step + 1];
+        }
         for (int r = r_begin; r < r_end; r += r_step) {
+            if (pf_dist > 0 && w == 0 && lane == 0) {
+                if (pf_b > pf_a) {
+                    const uint32_t ne = (uint32_t)(pf_b - pf_a);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(h + (size_t)pf_a * JAMUN_EDGE_HID), "r"(ne * 256u)
+                                 : "memory");
+                    if constexpr (V_IN > 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rhat + 4 * (size_t)pf_a), "r"(ne * 16u) : "memory");
+                }
+                const int rn = r + (pf_dist + 1) * r_step;
+                pf_a = pf_b = 0;
+                if (rn < r_end) {
+                    pf_a = rowptr[row0 + rn];
+                    pf_b = rowptr[row0 + rn + 1];
+                }
+            }
             const int e0 = e0_n, deg = deg_n;
             int jc[4];
 #pragma unroll
@@ -315,18 +342,20 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                 const uint32_t b = es * NT + t;
                 const bool live = (int)wq < SH::tgroups(t);  // this warp's 32 feature columns exist
                 // operand row of channel k' for this warp's column group: base + k' * kstride
+                // stage-major: [stage][rows_pad][32];  tile-major: [row / 128][stage][128][32] (all stages of a 128-row tile
+                // contiguous: the 715 lines a node writes fall into ~12 MB instead of being 2.3 MB apart across 1.6 GB)
                 float* dst;
                 size_t kstride;
-                if (t == 0) {
-                    dst = a0 + ((size_t)wq * rows_pad + r) * 32;
-                    kstride = (size_t)SH::NSL0 * rows_pad * 32;
-                } else if (t == 1 && wq == 0) {
-                    dst = a0 + ((size_t)NS * rows_pad + r) * 32;
-                    kstride = (size_t)SH::NSL0 * rows_pad * 32;
+                const bool zero = t == 0 || (t == 1 && wq == 0);          // 0e operand (a0) or a 1e component (a1)
+                const int nsl = zero ? SH::NSL0 : SH::NSL1;
+                const int slot = t == 0 ? (int)wq : zero ? NS : (t == 1 ? 0 : 1);
+                float* base = zero ? a0 : a1 + (size_t)(t == 1 ? (int)wq - 1 : (int)wq) * a1_comp_stride;
+                if (tile_major) {
+                    dst = base + ((size_t)(r >> 7) * (65 * nsl) + slot) * 4096 + (size_t)(r & 127) * 32;
+                    kstride = (size_t)nsl * 4096;
                 } else {
-                    const int comp = t == 1 ? (int)wq - 1 : (int)wq;
-                    dst = a1 + (size_t)comp * a1_comp_stride + ((size_t)(t == 1 ? 0 : 1) * rows_pad + r) * 32;
-                    kstride = (size_t)SH::NSL1 * rows_pad * 32;
+                    dst = base + ((size_t)slot * rows_pad + r) * 32;
+                    kstride = (size_t)nsl * rows_pad * 32;
                 }
                 dst += swz;
                 if (wq == 0 && t == 0) TC_TRACE(na, 8);
@@ -453,7 +482,7 @@ conv_p2_reduce_kernel(const int* __restrict__ rowptr, const float* __restrict__ 
 
 template <int S_IN, int V_IN, bool TRACE>
 int launch_tc(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
-              int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, cudaStream_t s) {
+              int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, int tile_major, cudaStream_t s) {
     using SH = Shape<S_IN, V_IN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -466,19 +495,25 @@ int launch_tc(const float* x, const int* rowptr, const int* col, const float* h,
         attr_set = true;
     }
     const int blocks = nrows < jb::kNumSMs ? nrows : jb::kNumSMs;
+    static int pf_dist = -1;  // nodes of look-ahead of the L2 prefetch (JAMUN_BUILD_PF, 0 = off)
+    if (pf_dist < 0) {
+        const char* e = getenv("JAMUN_BUILD_PF");
+        pf_dist = e ? atoi(e) : 4;
+    }
     conv_build_tc_kernel<S_IN, V_IN, TRACE><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows,
-                                                                                     rows_pad, a0, a1, comp, inv_deg);
+                                                                                     rows_pad, a0, a1, comp, inv_deg, tile_major,
+                                                                                     pf_dist);
     return JAMUN_OK;
 }
 
 }  // namespace
 
 // a0: [65*nslots0][rows_pad][32]; a1: 3 x [65*2][rows_pad][32] (component stride a1_comp_stride floats; unused when v_in == 0)
-extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
-                                   const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
-                                   long long a1_comp_stride, float* inv_deg, jamun_stream_t stream) {
+static int build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h, const float* rhat,
+                    int row0, int nrows, int rows_pad, float* a0, float* a1, long long a1_comp_stride, float* inv_deg,
+                    int tile_major, jamun_stream_t stream) {
     JB_CHECK_ARG(x && rowptr && col && h && rhat && a0, "null argument");
-    JB_CHECK_ARG(nrows <= rows_pad, "nrows exceeds rows_pad");
+    JB_CHECK_ARG(nrows <= rows_pad && (!tile_major || rows_pad % 128 == 0), "nrows exceeds rows_pad / rows_pad not a multiple of 128");
     JB_CHECK_ARG(((size_t)a0 & 127) == 0 && ((size_t)rhat & 15) == 0, "a0 must be 128-byte, rhat 16-byte aligned");
     if (nrows == 0) return JAMUN_OK;
     cudaStream_t s = jb::as_stream(stream);
@@ -487,11 +522,11 @@ extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int
         JB_CHECK_ARG(a1 && ((size_t)a1 & 127) == 0, "a1 (128-byte aligned) required for vector inputs");
         const char* t = getenv("JAMUN_TC_TRACE");  // debug: per-item role timestamps of CTA 0 (jamun_debug_tc_trace)
         rc = (t && atoi(t)) ? launch_tc<JAMUN_S, JAMUN_V, true>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
-                                                                (size_t)a1_comp_stride, inv_deg, s)
+                                                                (size_t)a1_comp_stride, inv_deg, tile_major, s)
                             : launch_tc<JAMUN_S, JAMUN_V, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1,
-                                                                 (size_t)a1_comp_stride, inv_deg, s);
+                                                                 (size_t)a1_comp_stride, inv_deg, tile_major, s);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        rc = launch_tc<JAMUN_S0, 0, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, 0, inv_deg, s);
+        rc = launch_tc<JAMUN_S0, 0, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, 0, inv_deg, tile_major, s);
     } else {
         jb::set_error("jamun_conv_build_tc: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;
@@ -499,6 +534,19 @@ extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int
     if (rc != JAMUN_OK) return rc;
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
+}
+
+extern "C" int jamun_conv_build_tc(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                                   const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                                   long long a1_comp_stride, float* inv_deg, jamun_stream_t stream) {
+    return build_tc(x, s_in, v_in, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, a1_comp_stride, inv_deg, 0, stream);
+}
+
+// The same aggregate in the tile-major operand layout [row / 128][stage][128][32] (jamun_gemm_f16x3 with a_tile_major = 1).
+extern "C" int jamun_conv_build_tc_tiled(const float* x, int s_in, int v_in, const int* rowptr, const int* col, const float* h,
+                                         const float* rhat, int row0, int nrows, int rows_pad, float* a0, float* a1,
+                                         long long a1_comp_stride, float* inv_deg, jamun_stream_t stream) {
+    return build_tc(x, s_in, v_in, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, a1_comp_stride, inv_deg, 1, stream);
 }
 
 extern "C" int jamun_conv_p2(const int* rowptr, const int* src_rowptr, const int* src_eid, const float* h, const float* rhat,

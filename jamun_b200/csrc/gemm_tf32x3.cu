@@ -74,6 +74,7 @@ struct Params {
     float* partial;
     long long partial_stride;
     int* status;  // F16 only: bit 0 is set when an A value does not fit fp16 (null: not reported)
+    int a_tile_major;  // A is [row / 128][stage][128][32] (a tile's stages contiguous) instead of [stage][rows_pad][32]
 };
 
 template <bool F16>
@@ -280,7 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                     umma::mbar_wait(&S.a_empty[sa], ((g / kASlots) & 1) ^ 1);
                     if (umma::elect_one()) {
                         umma::mbar_arrive_expect_tx(&S.a_full[sa], kATileBytes);
-                        umma::bulk_g2s(S.a[sa], sg.a + ((size_t)st * P.rows_pad + tile_row0) * kBK, kATileBytes, &S.a_full[sa]);
+                        const float* src = P.a_tile_major ? sg.a + ((size_t)blockIdx.x * sg.n_stages + st) * (128 * kBK)
+                                                          : sg.a + ((size_t)st * P.rows_pad + tile_row0) * kBK;
+                        umma::bulk_g2s(S.a[sa], src, kATileBytes, &S.a_full[sa]);
                     }
                     __syncwarp();
                 }
@@ -394,14 +397,14 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                        const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
-                       const float* addend_scale, jamun_stream_t stream);
+                       const float* addend_scale, int a_tile_major, jamun_stream_t stream);
 
 extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                                  const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                                  const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                                  const float* row_scale, float* out, int out_ld, jamun_stream_t stream) {
     return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats,
-                       rows, rows_pad, row_scale, out, out_ld, 1, nullptr, nullptr, nullptr, stream);
+                       rows, rows_pad, row_scale, out, out_ld, 1, nullptr, nullptr, nullptr, 0, stream);
 }
 
 // Split-K form for small row counts (few 128-row tiles): k_splits CTAs per tile, partial: [k_splits, rows, out_ld] scratch.
@@ -411,7 +414,7 @@ extern "C" int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const f
                                         jamun_stream_t stream) {
     JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || partial), "bad k_splits / partial");
     return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, nullptr, nullptr, 1, 0, rows, rows_pad, row_scale,
-                       out, out_ld, k_splits, partial, nullptr, nullptr, stream);
+                       out, out_ld, k_splits, partial, nullptr, nullptr, 0, stream);
 }
 
 // fp16-split form (same A operand; B images from jamun_pack_b_f16; k_splits == 1: plain launch, partial unused).
@@ -419,10 +422,10 @@ extern "C" int jamun_gemm_f16x3(int nseg, const float* const* a, const float* co
                                 const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                                 const int* addend_ld, const float* addend_scale, int col_blocks, long long b_block_floats, int rows,
                                 int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial,
-                                int* status, jamun_stream_t stream) {
+                                int* status, int a_tile_major, jamun_stream_t stream) {
     JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || (partial && !addend && col_blocks == 1)), "bad k_splits / partial");
     return gemm_launch(true, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats, rows,
-                       rows_pad, row_scale, out, out_ld, k_splits, partial, status, addend_scale, stream);
+                       rows_pad, row_scale, out, out_ld, k_splits, partial, status, addend_scale, a_tile_major, stream);
 }
 
 template <bool F16>
@@ -467,7 +470,7 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                        const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
-                       const float* addend_scale, jamun_stream_t stream) {
+                       const float* addend_scale, int a_tile_major, jamun_stream_t stream) {
     JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
     if (rows == 0) return JAMUN_OK;
@@ -478,6 +481,7 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
     P.partial = partial;
     P.partial_stride = (long long)rows * out_ld;
     P.status = status;
+    P.a_tile_major = a_tile_major;
     {
         const char* e = getenv("JAMUN_GEMM_COALESCE");
         P.coalesce = e ? atoi(e) : 1;

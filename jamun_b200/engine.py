@@ -28,6 +28,9 @@ BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
 # instructions of the tf32 form at the same 11-bit significands; weights pre-scaled into the fp16 range when the plan is built,
 # operand overflow reported through Topology.gemm_status); "tf32" = jamun_gemm_tf32x3.  Read when a plan is built.
 GEMM_KIND = os.environ.get("JAMUN_B200_GEMM", "f16")
+# layout of the conv operand between the tensor-core builder and the fp16-split contraction: "tile" = [row/128][stage][128][32]
+# (a tile's stages contiguous), "stage" = [stage][rows_pad][32] (the layout of every other user of the GEMM).  Read at call time.
+A_LAYOUT = os.environ.get("JAMUN_B200_A_LAYOUT", "tile")
 CELL_LIST_MIN_CHAIN = 2560  # longer chains use the cell-list search.  Measured on B200 (tools/time_radius.py, 512 k atoms, CSR build incl. the out-edge index): n=1000 brute 2.37 ms / cells 2.99 ms; n=3000 3.89 / 3.75; n=6000 6.21 / 5.59 -- the ascending scan stops after 33 hits, so the O(n^2) bound only bites beyond ~2.5 k atoms
 Y_LD = 17 * 128  # row stride of the per-node transform Y (65*32 = 2080 columns padded to 17 column blocks of 128)
 
@@ -270,11 +273,12 @@ def _gemm(topo: Topology, kind: str, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, o
                        status=topo.gemm_status, **kw)
     else:
         kw.pop("addend_scale", None)
+        assert not kw.pop("a_tile_major", False), "the tile-major operand layout needs the fp16-split GEMM"
         ops.gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows, rows_pad, rs_ptr, out_ptr, out_ld, **kw)
 
 
 def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows: int, rp: int, rs_ptr, out_ptr,
-              addend=None, kind: str = "tf32", addend_scale=None) -> None:
+              addend=None, kind: str = "tf32", addend_scale=None, tiled: bool = False) -> None:
     """The contraction GEMM; with few row tiles (small batches) the K stages are split over several CTAs per tile."""
     tiles = (nrows + 127) // 128
     if addend is not None:
@@ -291,14 +295,14 @@ def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col,
             topo.gemm_partial = torch.empty(need, dtype=torch.float32, device=topo.device)
         if kind == "f16":
             ops.gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, k_splits=ks,
-                           partial=topo.gemm_partial, status=topo.gemm_status)
+                           partial=topo.gemm_partial, status=topo.gemm_status, a_tile_major=tiled)
         else:
             ops.gemm_tf32x3_splitk(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN, ks,
                                    topo.gemm_partial)
     else:
         _gemm(topo, kind, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, nrows, rp, rs_ptr, out_ptr, ops.GATE_IN,
               addend_ptrs=addend, addend_ld=None if addend is None else [0, 96, 96, 96],
-              addend_scale=None if addend is None else addend_scale)
+              addend_scale=None if addend is None else addend_scale, a_tile_major=tiled)
 
 
 def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False) -> None:
@@ -342,6 +346,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
     a1_off = st0 * rp * 32
     comp = st1 * rp * 32
     build_impl = os.environ.get("JAMUN_B200_BUILD", BUILD_IMPL)
+    tiled = build_impl == "tc" and kind == "f16" and os.environ.get("JAMUN_B200_A_LAYOUT", A_LAYOUT) == "tile"
     if build_impl == "tc":
         # the 0e(x)1e->1e gather needs only Y and h: it runs on the side stream under the builder and the contraction, and
         # its result joins in block_tail (hidden blocks: topo.p2 as the `vadd` operand; initial block: written in place)
@@ -365,7 +370,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         nrows = min(rp, N - row0)
         if build_impl == "tc":
             ops.conv_build_tc(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, row0, nrows, rp, base,
-                              base + 4 * a1_off if v_in else None, comp, topo.inv_deg)
+                              base + 4 * a1_off if v_in else None, comp, topo.inv_deg, tiled=tiled)
         if v_in:
             if build_impl != "tc":
                 ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base,
@@ -376,13 +381,13 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
             addend = None if build_impl == "tc" else [None, p2, p2 + 4 * 32, p2 + 4 * 64]
             _contract(topo, a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
                       [b["alpha0"] / sc[0]] + [b["alpha1"] / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
-                      out.data_ptr() + 4 * row0 * ops.GATE_IN, addend=addend, kind=kind, addend_scale=[sc[0]] + [sc[1]] * 3)
+                      out.data_ptr() + 4 * row0 * ops.GATE_IN, addend=addend, kind=kind, addend_scale=[sc[0]] + [sc[1]] * 3, tiled=tiled)
         else:  # initial block: the 1e output is the path-2 gather alone, written in place
             if build_impl != "tc":
                 ops.conv_build_a(x, s_in, v_in, topo.rowptr, topo.col, topo.h, topo.rhat, y_buf, topo.max_degree, row0, nrows, rp, base, None, 0,
                                  out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"], topo.inv_deg)
             _contract(topo, [base], [b["b0_img"].data_ptr()], [st0], [160], [152], [0], [b["alpha0"] / sc[0]], nrows, rp,
-                      topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, kind=kind)
+                      topo.inv_deg.data_ptr() + 4 * row0, out.data_ptr() + 4 * row0 * ops.GATE_IN, kind=kind, tiled=tiled)
 
 
 def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:

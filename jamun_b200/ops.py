@@ -209,10 +209,12 @@ def conv_build_a(x, s_in: int, v_in: int, rowptr, col, h, rhat, y, max_degree: i
 
 
 def conv_build_tc(x, s_in: int, v_in: int, rowptr, col, h, rhat, row0: int, nrows: int, rows_pad: int, a0_ptr: int, a1_ptr: int,
-                  a1_comp_stride: int, inv_deg=None):
+                  a1_comp_stride: int, inv_deg=None, tiled: bool = False):
+    """tiled: write the tile-major operand layout [row / 128][stage][128][32] (gemm_f16x3(a_tile_major=True))."""
     i32 = torch.int32
-    rc = _lib.lib().jamun_conv_build_tc(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), row0, nrows,
-                                        rows_pad, a0_ptr, a1_ptr, int(a1_comp_stride), _ptr(inv_deg), _stream())
+    fn = _lib.lib().jamun_conv_build_tc_tiled if tiled else _lib.lib().jamun_conv_build_tc
+    rc = fn(_ptr(x), s_in, v_in, _ptr(rowptr, i32), _ptr(col, i32), _ptr(h), _ptr(rhat), row0, nrows, rows_pad, a0_ptr, a1_ptr,
+            int(a1_comp_stride), _ptr(inv_deg), _stream())
     _lib.check(rc, "jamun_conv_build_tc")
     _count()
 
@@ -295,7 +297,7 @@ def pack_b_f16(src, n_stages: int, n_pad: int, scale: float, row_map=None, k_src
 
 def gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr, out_ptr,
                out_ld: int, addend_ptrs=None, addend_ld=None, col_blocks: int = 1, b_block_floats: int = 0, k_splits: int = 1,
-               partial=None, status=None, addend_scale=None):
+               partial=None, status=None, addend_scale=None, a_tile_major: bool = False):
     """fp16-split form of gemm_tf32x3 (B images from pack_b_f16, alpha already divided by their scale).  status: int32 device
     word whose bit 0 reports an A value outside the fp16 range."""
     n = len(a_ptrs)
@@ -307,7 +309,7 @@ def gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: i
     ads = FA(*addend_scale) if addend_scale is not None else None
     rc = _lib.lib().jamun_gemm_f16x3(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col), FA(*alpha),
                                      ad, adl, ads, col_blocks, b_block_floats, rows, rows_pad, row_scale_ptr, out_ptr, out_ld,
-                                     int(k_splits), _ptr(partial), _ptr(status, torch.int32), _stream())
+                                     int(k_splits), _ptr(partial), _ptr(status, torch.int32), int(a_tile_major), _stream())
     _lib.check(rc, "jamun_gemm_f16x3")
     _count(2 if k_splits > 1 else 1)
 
@@ -584,7 +586,7 @@ def stage_atb(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, nslots:
     _count()
 
 
-ATB_IMPL = None  # "tc" (tcgen05, default) | "simt"; read from JAMUN_B200_ATB at call time
+ATB_IMPL = None  # "tc" (tcgen05) | "simt" | "auto" (default: tc from 4096 nodes); read from JAMUN_B200_ATB at call time
 
 
 def stage_atb_auto(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, nslots: int, rows: int, rows_pad: int, b, b_col0: int,
@@ -592,7 +594,10 @@ def stage_atb_auto(a_ptr: int, a_comp_stride: int, ncomp: int, n_stages: int, ns
     """dW = A^T . B over the nodes: the tensor-core kernel (jamun_stage_atb_tc) unless JAMUN_B200_ATB=simt."""
     import os
 
-    if (ATB_IMPL or os.environ.get("JAMUN_B200_ATB", "tc")) == "simt":
+    impl = ATB_IMPL or os.environ.get("JAMUN_B200_ATB", "auto")
+    if impl == "auto":  # short reductions (reference batch size 32: ~1 k nodes) do not amortise the operand split + split-K reduce
+        impl = "tc" if rows >= 4096 else "simt"
+    if impl == "simt":
         return stage_atb(a_ptr, a_comp_stride, ncomp, n_stages, nslots, rows, rows_pad, b, b_col0, b_comp_stride, W, out, mode, out_rows,
                          slot_row0, slot_rows)
     nslots_b = (W + 31) // 32

@@ -214,8 +214,9 @@ def test_build_tc_matches_ffma_builder(models, sizes, monkeypatch):
         if topo.a_ws is None:
             engine.conv_tc(topo, b, x, torch.empty(N, 248, device="cuda"))  # allocates the operand workspace
             engine.conv_tc_join(topo, b)
-        for variant in ("ffma", "tc"):
-            monkeypatch.setenv("JAMUN_B200_BUILD", variant)
+        for variant in ("ffma", "tc", "tc_tiled"):
+            monkeypatch.setenv("JAMUN_B200_BUILD", variant.split("_")[0])
+            monkeypatch.setenv("JAMUN_B200_A_LAYOUT", "tile" if variant == "tc_tiled" else "stage")
             out = torch.full((N, 248), float("nan"), device="cuda")
             topo.a_ws.fill_(float("nan"))
             engine.conv_tc(topo, b, x, out)
@@ -234,6 +235,20 @@ def test_build_tc_matches_ffma_builder(models, sizes, monkeypatch):
         assert err <= 2e-6 * max(1.0, scale), f"block {l}: A operand err {err} scale {scale}"
         err_o = (out_tc - out_ref).abs().max().item()
         assert err_o <= 2e-5 * max(1.0, out_ref.abs().max().item()), f"block {l}: conv err {err_o}"
+        # the tile-major layout (default of the fp16-split path) holds the same numbers, [row/128][stage][128][32] per segment
+        a_tl, out_tl = res["tc_tiled"]
+        rp = topo.chunk_rows
+        segs = [65 * 2] if d_in == 56 else [65 * 5, 65 * 2, 65 * 2, 65 * 2]
+        off = 0
+        for nst_seg in segs:
+            n = nst_seg * rp * 32
+            st_major = a_tc[off:off + n].view(nst_seg, rp // 128, 128, 32).permute(1, 0, 2, 3).reshape(-1)
+            tl = a_tl[off:off + n]
+            assert torch.equal(torch.isnan(tl), torch.isnan(st_major))
+            assert torch.equal(torch.nan_to_num(tl), torch.nan_to_num(st_major))
+            off += n
+        if plan.gemm_kind == "f16":
+            assert torch.equal(out_tl, out_tc)
 
 
 def test_block_tail_tc_matches_simt(models, monkeypatch):
