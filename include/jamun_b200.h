@@ -190,6 +190,34 @@ int jamun_gemm_f16x3(int nseg, const float* const* a, const float* const* b, con
                      const int* addend_ld, const float* addend_scale, int col_blocks, long long b_block_floats, int rows,
                      int rows_pad, const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
                      int a_tile_major, jamun_stream_t stream);
+/* Fused ConvBlock epilogues of jamun_gemm_f16x3 (the accumulators never leave the SM un-activated):
+ * mode 1 (contraction, segments [160 | 32 | 32 | 32]): Gate (e3tools/nn/_gate.py:63) -> the block-tail operands
+ *        op_s stages 0-3 (activated scalars, zero padded to 128) and op_v[c] stage 0 (gated vectors); addend[1..3] carries the
+ *        receiver-side sums of the 0e(x)1e->1e path (jamun_conv_p2 with p2_scale = 0).  Replaces jamun_tail_pack.
+ * mode 2 (block tail, segments [128 | 32 | 32 | 32], out_col [0,120,152,184]): x_new = skip_w ? x_res*w + y*(1-w) : y and
+ *        x_scaled = x_new * s_next (model/noise_conditioning.py:50-73, arch/e3conv.py:131-133; weights per irrep [120 | 32]),
+ *        both row-major [rows, 216], plus x_scaled packed as the x_in halves of the next block's operands: op_s stages 4-7
+ *        (also the per-node transform's operand) and op_v[c] stage 1.  x_scaled / op_s may be NULL (last block).  Replaces
+ *        jamun_tail_mix.
+ * op_s: [8][op_rows_pad][32], op_v: 3 x [2][op_rows_pad][32] (component stride op_v_comp_stride floats), stage-major, 16-byte
+ * chunks XOR-ed with row & 7 -- the A layout of this GEMM. */
+typedef struct {
+    int mode;
+    float* op_s;
+    float* op_v;
+    long long op_v_comp_stride;
+    int op_rows_pad;
+    float c_act, c_gate;   /* mode 1: normalize2mom constants of the Gate */
+    const float* x_res;    /* mode 2 */
+    const float* skip_w;
+    const float* s_next;
+    float* x_new;
+    float* x_scaled;
+} jamun_gemm_epilogue;
+int jamun_gemm_f16x3_fused(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                           const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                           const int* addend_ld, const float* addend_scale, int rows, int rows_pad, const float* row_scale,
+                           int* status, int a_tile_major, const jamun_gemm_epilogue* epi, jamun_stream_t stream);
 /* jamun_conv_build_tc writing the tile-major operand layout [row / 128][stage][128][32] (all stages of a 128-row tile
  * contiguous; rows_pad % 128 == 0), consumed by jamun_gemm_f16x3 with a_tile_major = 1: the 715 lines a node contributes then
  * fall into one ~12 MB region instead of being rows_pad * 128 bytes apart, and a GEMM CTA streams its tile sequentially. */

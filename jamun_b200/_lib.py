@@ -22,6 +22,13 @@ class WalkParams(C.Structure):
                 ("first", I), ("last", I), ("center", I), ("seed", ULL), ("step", ULL)]
 
 
+class GemmEpilogue(C.Structure):
+    """jamun_gemm_epilogue (include/jamun_b200.h): fused ConvBlock epilogues of jamun_gemm_f16x3_fused."""
+    _fields_ = [("mode", I), ("op_s", C.c_void_p), ("op_v", C.c_void_p), ("op_v_comp_stride", C.c_longlong), ("op_rows_pad", I),
+                ("c_act", F), ("c_gate", F), ("x_res", C.c_void_p), ("skip_w", C.c_void_p), ("s_next", C.c_void_p),
+                ("x_new", C.c_void_p), ("x_scaled", C.c_void_p)]
+
+
 _PROTOS = {
     "jamun_abi_version": ([], I),
     "jamun_last_error": ([], C.c_char_p),
@@ -75,6 +82,9 @@ _PROTOS = {
                                   C.POINTER(F), I, I, c_f, c_f, I, I, c_f, c_f], I),
     "jamun_gemm_f16x3": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
                           C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(F), I, C.c_longlong, I, I, c_f, c_f, I, I, c_f, c_f, I, c_f], I),
+    "jamun_gemm_f16x3_fused": ([I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
+                                C.POINTER(F), C.POINTER(C.c_void_p), C.POINTER(I), C.POINTER(F), I, I, c_f, c_f, I,
+                                C.POINTER(GemmEpilogue), c_f], I),
     "jamun_pack_b_f16": ([c_f, I, c_f, I, I, I, I, I, I, I, I, F, c_f, c_f], I),
     "jamun_block_tail": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f, c_f], I),
     "jamun_tail_pack": ([c_f, c_f, c_f, I, I, F, F, I, I, c_f, c_f, C.c_longlong, c_f, c_f, c_f, F, I, c_f], I),

@@ -75,6 +75,7 @@ struct Params {
     long long partial_stride;
     int* status;  // F16 only: bit 0 is set when an A value does not fit fp16 (null: not reported)
     int a_tile_major;  // A is [row / 128][stage][128][32] (a tile's stages contiguous) instead of [stage][rows_pad][32]
+    jamun_gemm_epilogue epi;  // fused ConvBlock epilogues (mode 0: plain store)
 };
 
 template <bool F16>
@@ -87,6 +88,99 @@ struct __align__(1024) SmemT {
 };
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// one 128-byte row of a stage-major operand ([stage][rows_pad][32], 16-byte chunks XOR-ed with row & 7) from 32 registers
+__device__ __forceinline__ void store_op_row(float* row_base, int sw, const float (&f)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(row_base + ((q ^ sw) << 2)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+}
+
+// Fused epilogue of the ConvBlock contraction (mode 1): Gate (e3tools/nn/_gate.py:63: LeakyReLU on the 120 scalars, sigmoid
+// gates on the vectors) applied to the accumulators and written straight into the block-tail GEMM's operands -- the conv
+// output never reaches memory.  Segment 0 = [120 scalars | 32 gate scalars | pad], segments 1-3 = the 1e components (their
+// addend is the receiver-side sum of the 0e(x)1e->1e path).  `row` is the operand row (== output row of this launch).
+__device__ __forceinline__ void epi_gate(const Params& P, int s, int c0, const uint32_t (&v)[32], int row, bool live, float rs_own,
+                                         uint32_t tmem_lane) {
+    const jamun_gemm_epilogue& E = P.epi;
+    const Seg& sg = P.seg[s];
+    const float sc = sg.alpha * rs_own;
+    const int sw = row & 7;
+    float f[32];
+    if (s == 0) {
+        if (c0 >= 128 || !live) return;  // the gate scalars are consumed by the vector chunks below
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const float x = __uint_as_float(v[q]) * sc;
+            f[q] = (c0 + q < JAMUN_S) ? E.c_act * (x > 0.f ? x : 0.01f * x) : 0.f;
+        }
+        store_op_row(E.op_s + ((size_t)(c0 >> 5) * E.op_rows_pad + row) * 32, sw, f);
+    } else {
+        uint32_t g[32];
+        umma::tmem_ld32(tmem_lane + (uint32_t)(P.seg[0].d_col + JAMUN_S), g);  // this row's 32 gate pre-activations
+        umma::wait_ld();
+        if (!live) return;
+        const float sc0 = P.seg[0].alpha * rs_own;
+        const float* ad = sg.addend ? sg.addend + (size_t)row * sg.addend_ld : nullptr;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            float x = __uint_as_float(v[q]);
+            if (ad) x += ad[q] * sg.addend_scale;
+            f[q] = x * sc * (E.c_gate * sigmoidf_acc(__uint_as_float(g[q]) * sc0));
+        }
+        store_op_row(E.op_v + (size_t)(s - 1) * E.op_v_comp_stride + (size_t)row * 32, sw, f);
+    }
+}
+
+// Fused epilogue of the block-tail GEMM (mode 2): noise-conditional skip x_new = x_res*w + y*(1-w) and the next block's
+// input scaling x_scaled = x_new * s_next (model/noise_conditioning.py:50-73, arch/e3conv.py:131-133), written row-major for
+// the gathers of the next aggregate and, packed, as the x_in halves of the next block-tail operands (scalars: stages 4-7 of
+// op_s, which are also the per-node transform's operand; vectors: stage 1 of op_v).  Weights are per irrep: [120 | 32].
+__device__ __forceinline__ void epi_mix(const Params& P, int s, int c0, const uint32_t (&v)[32], int row) {
+    const jamun_gemm_epilogue& E = P.epi;
+    const Seg& sg = P.seg[s];
+    const int nval = sg.n_valid - c0 < 32 ? sg.n_valid - c0 : 32;  // 24 in the last scalar chunk
+    if (nval <= 0) return;
+    const int j0 = sg.out_col + c0;                        // column of the [216]-wide node row
+    const int w0 = s == 0 ? c0 : JAMUN_S;                  // first per-irrep weight of this chunk
+    const float* xr = E.skip_w ? E.x_res + (size_t)row * JAMUN_HID + j0 : nullptr;
+    float xn[32], xs[32];
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xr && 4 * q4 < nval) r4 = *reinterpret_cast<const float4*>(xr + 4 * q4);
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int q = 4 * q4 + t;
+            float y = __uint_as_float(v[q]) * sg.alpha;
+            if (q < nval) {
+                if (E.skip_w) {
+                    const float w = E.skip_w[w0 + q];
+                    y = rr[t] * w + y * (1.0f - w);
+                }
+                xn[q] = y;
+                xs[q] = E.s_next ? y * E.s_next[w0 + q] : y;
+            } else {
+                xn[q] = 0.f;
+                xs[q] = 0.f;
+            }
+        }
+    }
+    float* on = E.x_new + (size_t)row * JAMUN_HID + j0;
+    float* os = E.x_scaled ? E.x_scaled + (size_t)row * JAMUN_HID + j0 : nullptr;
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4)
+        if (4 * q4 < nval) {
+            *reinterpret_cast<float4*>(on + 4 * q4) = make_float4(xn[4 * q4], xn[4 * q4 + 1], xn[4 * q4 + 2], xn[4 * q4 + 3]);
+            if (os) *reinterpret_cast<float4*>(os + 4 * q4) = make_float4(xs[4 * q4], xs[4 * q4 + 1], xs[4 * q4 + 2], xs[4 * q4 + 3]);
+        }
+    if (E.x_scaled && E.op_s) {
+        const int sw = row & 7;
+        if (s == 0) store_op_row(E.op_s + ((size_t)(4 + (c0 >> 5)) * E.op_rows_pad + row) * 32, sw, xs);
+        else store_op_row(E.op_v + (size_t)(s - 1) * E.op_v_comp_stride + ((size_t)E.op_rows_pad + row) * 32, sw, xs);
+    }
+}
 
 // COALESCE: epilogue variant for wide outputs in stationary mode (kept out of the contraction instantiation: +40 registers)
 template <bool COALESCE, bool F16>
@@ -235,6 +329,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                 // thread = row: 8 x 16-byte stores per 32-column chunk (few instructions; the 8 pieces of a 128-byte line
                 // merge in L2)
                 const int row = tile_row0 + r;
+                if (P.epi.mode != 0) {
+                    // (epi_gate reads TMEM with a warp-collective tcgen05.ld: every thread calls it, rows beyond the batch only
+                    // skip the memory accesses)
+                    if (P.epi.mode == 1) epi_gate(P, s, c0, v, row, row < P.rows, rs_own, tmem + lane_base);
+                    else if (row < P.rows) epi_mix(P, s, c0, v, row);
+                    continue;
+                }
                 if (row < P.rows) {
                     const float sc = sg.alpha * rs_own;
                     float* o = (ksp > 1 ? P.partial + (size_t)ky * P.partial_stride : sg.out) + (size_t)row * P.out_ld + sg.out_col +
@@ -397,14 +498,14 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                        const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
-                       const float* addend_scale, int a_tile_major, jamun_stream_t stream);
+                       const float* addend_scale, int a_tile_major, const jamun_gemm_epilogue* epi, jamun_stream_t stream);
 
 extern "C" int jamun_gemm_tf32x3(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
                                  const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                                  const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                                  const float* row_scale, float* out, int out_ld, jamun_stream_t stream) {
     return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats,
-                       rows, rows_pad, row_scale, out, out_ld, 1, nullptr, nullptr, nullptr, 0, stream);
+                       rows, rows_pad, row_scale, out, out_ld, 1, nullptr, nullptr, nullptr, 0, nullptr, stream);
 }
 
 // Split-K form for small row counts (few 128-row tiles): k_splits CTAs per tile, partial: [k_splits, rows, out_ld] scratch.
@@ -414,7 +515,7 @@ extern "C" int jamun_gemm_tf32x3_splitk(int nseg, const float* const* a, const f
                                         jamun_stream_t stream) {
     JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || partial), "bad k_splits / partial");
     return gemm_launch(false, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, nullptr, nullptr, 1, 0, rows, rows_pad, row_scale,
-                       out, out_ld, k_splits, partial, nullptr, nullptr, 0, stream);
+                       out, out_ld, k_splits, partial, nullptr, nullptr, 0, nullptr, stream);
 }
 
 // fp16-split form (same A operand; B images from jamun_pack_b_f16; k_splits == 1: plain launch, partial unused).
@@ -425,7 +526,30 @@ extern "C" int jamun_gemm_f16x3(int nseg, const float* const* a, const float* co
                                 int* status, int a_tile_major, jamun_stream_t stream) {
     JB_CHECK_ARG(k_splits >= 1 && k_splits <= 64 && (k_splits == 1 || (partial && !addend && col_blocks == 1)), "bad k_splits / partial");
     return gemm_launch(true, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, col_blocks, b_block_floats, rows,
-                       rows_pad, row_scale, out, out_ld, k_splits, partial, status, addend_scale, a_tile_major, stream);
+                       rows_pad, row_scale, out, out_ld, k_splits, partial, status, addend_scale, a_tile_major, nullptr, stream);
+}
+
+// jamun_gemm_f16x3 with one of the fused ConvBlock epilogues (include/jamun_b200.h: jamun_gemm_epilogue); `out` is not
+// written (may be NULL).  mode 1 expects the contraction's segments [160 | 32 | 32 | 32], mode 2 the block tail's
+// [128 | 32 | 32 | 32] with out_col [0, 120, 152, 184].  Single pass only: no split-K, no column blocks.
+extern "C" int jamun_gemm_f16x3_fused(int nseg, const float* const* a, const float* const* b, const int* n_stages, const int* n_pad,
+                                      const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
+                                      const int* addend_ld, const float* addend_scale, int rows, int rows_pad,
+                                      const float* row_scale, int* status, int a_tile_major, const jamun_gemm_epilogue* epi,
+                                      jamun_stream_t stream) {
+    JB_CHECK_ARG(epi && (epi->mode == 1 || epi->mode == 2) && nseg == 4 && n_pad && n_valid, "bad epilogue / segments");
+    JB_CHECK_ARG(n_pad[1] == 32 && n_pad[2] == 32 && n_pad[3] == 32 && n_valid[1] == 32, "segments 1-3 must be 32 columns wide");
+    if (epi->mode == 1) {
+        JB_CHECK_ARG(n_pad[0] == 160 && n_valid[0] == JAMUN_S + JAMUN_V && epi->op_s && epi->op_v, "mode 1: contraction segments");
+    } else {
+        JB_CHECK_ARG(n_pad[0] == 128 && n_valid[0] == JAMUN_S && out_col && out_col[0] == 0 && out_col[1] == JAMUN_S && epi->x_new &&
+                         (!epi->skip_w || epi->x_res) && (!epi->op_s || epi->op_v),
+                     "mode 2: block-tail segments");
+    }
+    JB_CHECK_ARG(epi->op_rows_pad % 8 == 0 && (((size_t)epi->op_s | (size_t)epi->op_v) & 127) == 0, "operand buffers must be 128-byte aligned");
+    float dummy;
+    return gemm_launch(true, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, 1, 0, rows, rows_pad, row_scale,
+                       &dummy, 0, 1, nullptr, status, addend_scale, a_tile_major, epi, stream);
 }
 
 template <bool F16>
@@ -470,7 +594,7 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
                        const int* n_valid, const int* out_col, const float* alpha, const float* const* addend,
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                        const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
-                       const float* addend_scale, int a_tile_major, jamun_stream_t stream) {
+                       const float* addend_scale, int a_tile_major, const jamun_gemm_epilogue* epi, jamun_stream_t stream) {
     JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
     if (rows == 0) return JAMUN_OK;
@@ -482,6 +606,7 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
     P.partial_stride = (long long)rows * out_ld;
     P.status = status;
     P.a_tile_major = a_tile_major;
+    if (epi) P.epi = *epi;
     {
         const char* e = getenv("JAMUN_GEMM_COALESCE");
         P.coalesce = e ? atoi(e) : 1;

@@ -106,10 +106,12 @@ __global__ void __launch_bounds__(256) stage_atb_kernel(const AtbParams P) {
 
 // ---- per-edge backward of the aggregated paths ---------------------------------------------------------------------------------
 // One CTA per receiver i.  dA0_i [65][NSL0*32] and dA1_i[c] [65][64] (rows of the column-block GEMM outputs) are staged in shared
-// memory once and reused by all in-edges of i:
+// memory once and reused by all in-edges of i, which are processed four at a time (features / gradients of the batch live in
+// shared memory as float4 = one value per edge, so every dA element read from shared memory feeds four FMAs):
 //   df0[u'] = sum_k' h'[k'] dA0[k'][u']      df1[c][u'] = sum_k' h'[k'] dA1[c][k'][u']        (threads over u')
 //   dh[k']  = sum_u' f0[u'] dA0[k'][u'] + sum_c sum_u' f1[c][u'] dA1[c][k'][u']   (k' < 64)   (warps over k', lanes over u')
 //   dxe[e]  = J_e^T df  (row of the per-edge input gradient, SoA layout; summed per source by jamun_conv_bwd_gather)
+// The raw gathers (x row of the source, rhat, h) of batch b+1 are issued into registers before the arithmetic of batch b.
 template <int S_IN, int V_IN>
 __global__ void __launch_bounds__(384)
 conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -118,15 +120,19 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                      float* __restrict__ dxe) {
     constexpr int D_IN = S_IN + 3 * V_IN;
     constexpr int NS = (S_IN + 31) / 32;
+    constexpr int NS32 = NS * 32;
     constexpr int W0 = (NS + (V_IN > 0 ? 1 : 0)) * 32;  // padded 0e feature columns
     constexpr int W1 = V_IN > 0 ? 64 : 0;
     constexpr int NF = W0 + 3 * W1;
+    constexpr int EB = 4;                                // edges per batch
+    constexpr int XS_PER = (EB * NS32 + 383) / 384;      // scalar gathers per thread and batch
     extern __shared__ __align__(16) float sm[];
-    float* sA0 = sm;                       // [65][W0]
-    float* sA1 = sA0 + 65 * W0;            // [3][65][W1]
-    float* sf = sA1 + 3 * 65 * W1;         // [NF] features of the current edge
-    float* sdf = sf + NF;                  // [NF] their gradients
-    float* sh = sdf + NF;                  // [65] h'
+    float* sA0 = sm;                                         // [65][W0]
+    float* sA1 = sA0 + 65 * W0;                              // [3][65][W1]
+    float4* sf = reinterpret_cast<float4*>(sA1 + 3 * 65 * W1);  // [NF] features, one lane of the float4 per edge of the batch
+    float4* sdf = sf + NF;                                   // [NF] their gradients
+    float4* sh = sdf + NF;                                   // [65] h'
+    float4* srh = sh + 65;                                   // [EB] rhat of the batch's edges
     const int i = blockIdx.x;
     if (i >= N) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -136,63 +142,120 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
     if (V_IN > 0)
         for (int c = 0; c < 3; ++c)
             for (int t = tid; t < 65 * W1; t += 384) sA1[c * 65 * W1 + t] = dA1[(size_t)c * dA1_comp_stride + (size_t)i * ld1 + t];
-    for (int e = e0; e < e1; ++e) {
-        __syncthreads();  // previous edge done with sf / sdf / sh (and the dA tiles are loaded)
-        const int j = col[e];
-        const float* xr = x + (size_t)j * D_IN;
-        const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
-        for (int t = tid; t < NS * 32; t += 384) sf[t] = t < S_IN ? xr[t] : 0.f;
-        if (V_IN > 0 && tid < V_IN) {
-            const float vx = xr[S_IN + tid], vy = xr[S_IN + V_IN + tid], vz = xr[S_IN + 2 * V_IN + tid];
-            sf[NS * 32 + tid] = vx * rh.x + vy * rh.y + vz * rh.z;
-            sf[W0 + 0 * 64 + tid] = vx * kInvSqrt3;
-            sf[W0 + 1 * 64 + tid] = vy * kInvSqrt3;
-            sf[W0 + 2 * 64 + tid] = vz * kInvSqrt3;
-            sf[W0 + 0 * 64 + 32 + tid] = (vy * rh.z - vz * rh.y) * kInvSqrt2;
-            sf[W0 + 1 * 64 + 32 + tid] = (vz * rh.x - vx * rh.z) * kInvSqrt2;
-            sf[W0 + 2 * 64 + 32 + tid] = (vx * rh.y - vy * rh.x) * kInvSqrt2;
+
+    // raw gathers of one batch, held in registers: scalars (XS_PER per thread), vectors + rhat (threads < EB*32), h (threads >= 128)
+    float r_xs[XS_PER], r_v[3] = {0.f, 0.f, 0.f}, r_h = 0.f;
+    float4 r_rh = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gather = [&](int eb) {
+#pragma unroll
+        for (int m = 0; m < XS_PER; ++m) {
+            const int t = tid + 384 * m, q = t / NS32, c = t - q * NS32;
+            r_xs[m] = (t < EB * NS32 && eb + q < e1 && c < S_IN) ? x[(size_t)col[eb + q] * D_IN + c] : 0.f;
         }
-        if (tid >= 320 && tid < 384) sh[tid - 320] = h[(size_t)e * JAMUN_EDGE_HID + tid - 320];
-        if (tid == 319) sh[64] = 1.f;
-        __syncthreads();
-        // df: one feature column per thread
-        if (tid < NF) {
-            float acc = 0.f;
-            if (tid < W0) {
-#pragma unroll 5
-                for (int k = 0; k < 65; ++k) acc = fmaf(sh[k], sA0[k * W0 + tid], acc);
+        if (V_IN > 0 && tid < EB * 32) {
+            const int q = tid >> 5, w = tid & 31;
+            if (eb + q < e1) {
+                const float* xr = x + (size_t)col[eb + q] * D_IN + S_IN + w;
+                r_v[0] = xr[0], r_v[1] = xr[V_IN], r_v[2] = xr[2 * V_IN];
+                r_rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(eb + q));
             } else {
-                const int c = (tid - W0) / 64, u = (tid - W0) % 64;
-                const float* A = sA1 + c * 65 * W1;
+                r_v[0] = r_v[1] = r_v[2] = 0.f;
+                r_rh = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (tid >= 128) {
+            const int t2 = tid - 128, q = t2 >> 6, k = t2 & 63;
+            r_h = eb + q < e1 ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + k] : 0.f;
+        }
+    };
+    gather(e0);
+    for (int eb = e0; eb < e1; eb += EB) {
+        const int nb = e1 - eb < EB ? e1 - eb : EB;
+        __syncthreads();  // previous batch done with sf / sdf / sh (and the dA tiles are loaded)
+        float* sff = reinterpret_cast<float*>(sf);
+#pragma unroll
+        for (int m = 0; m < XS_PER; ++m) {
+            const int t = tid + 384 * m, q = t / NS32, c = t - q * NS32;
+            if (t < EB * NS32) sff[4 * c + q] = r_xs[m];
+        }
+        if (V_IN > 0 && tid < EB * 32) {
+            const int q = tid >> 5, w = tid & 31;
+            const float vx = r_v[0], vy = r_v[1], vz = r_v[2];
+            const float4 rh = r_rh;
+            sff[4 * (NS32 + w) + q] = vx * rh.x + vy * rh.y + vz * rh.z;
+            sff[4 * (W0 + 0 * 64 + w) + q] = vx * kInvSqrt3;
+            sff[4 * (W0 + 1 * 64 + w) + q] = vy * kInvSqrt3;
+            sff[4 * (W0 + 2 * 64 + w) + q] = vz * kInvSqrt3;
+            sff[4 * (W0 + 0 * 64 + 32 + w) + q] = (vy * rh.z - vz * rh.y) * kInvSqrt2;
+            sff[4 * (W0 + 1 * 64 + 32 + w) + q] = (vz * rh.x - vx * rh.z) * kInvSqrt2;
+            sff[4 * (W0 + 2 * 64 + 32 + w) + q] = (vx * rh.y - vy * rh.x) * kInvSqrt2;
+            if (w == 0) srh[q] = rh;
+        }
+        if (tid >= 128) {
+            const int t2 = tid - 128, q = t2 >> 6, k = t2 & 63;
+            reinterpret_cast<float*>(sh)[4 * k + q] = r_h;
+        }
+        if (tid < EB) reinterpret_cast<float*>(sh)[4 * 64 + tid] = tid < nb ? 1.f : 0.f;  // bias channel h' = 1
+        __syncthreads();
+        if (eb + EB < e1) gather(eb + EB);  // next batch's loads fly under this batch's arithmetic
+        // df: one feature column per thread, four edges at once
+        if (tid < NF) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* A = tid < W0 ? sA0 + tid : sA1 + ((tid - W0) / 64) * 65 * W1 + (tid - W0) % 64;
+            const int lda = tid < W0 ? W0 : W1;
 #pragma unroll 5
-                for (int k = 0; k < 65; ++k) acc = fmaf(sh[k], A[k * W1 + u], acc);
+            for (int k = 0; k < 65; ++k) {
+                const float a = A[k * lda];
+                const float4 hk = sh[k];
+                acc.x = fmaf(hk.x, a, acc.x);
+                acc.y = fmaf(hk.y, a, acc.y);
+                acc.z = fmaf(hk.z, a, acc.z);
+                acc.w = fmaf(hk.w, a, acc.w);
             }
             sdf[tid] = acc;
         }
-        // dh: warp per channel
+        // dh: warp per channel, four edges at once
         for (int k = warp; k < 64; k += 12) {
-            float acc = 0.f;
-            for (int u = lane; u < W0; u += 32) acc = fmaf(sf[u], sA0[k * W0 + u], acc);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = lane; u < W0; u += 32) {
+                const float a = sA0[k * W0 + u];
+                const float4 f = sf[u];
+                acc.x = fmaf(f.x, a, acc.x), acc.y = fmaf(f.y, a, acc.y), acc.z = fmaf(f.z, a, acc.z), acc.w = fmaf(f.w, a, acc.w);
+            }
             if (V_IN > 0)
+#pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float* A = sA1 + (c * 65 + k) * W1;
-                    acc = fmaf(sf[W0 + c * 64 + lane], A[lane], acc);
-                    acc = fmaf(sf[W0 + c * 64 + 32 + lane], A[32 + lane], acc);
+#pragma unroll
+                    for (int hv = 0; hv < 2; ++hv) {
+                        const float a = A[32 * hv + lane];
+                        const float4 f = sf[W0 + c * 64 + 32 * hv + lane];
+                        acc.x = fmaf(f.x, a, acc.x), acc.y = fmaf(f.y, a, acc.y), acc.z = fmaf(f.z, a, acc.z), acc.w = fmaf(f.w, a, acc.w);
+                    }
                 }
-            acc = warp_sum(acc);
-            if (lane == 0) dh[(size_t)e * JAMUN_EDGE_HID + k] = acc;
+            acc.x = warp_sum(acc.x), acc.y = warp_sum(acc.y), acc.z = warp_sum(acc.z), acc.w = warp_sum(acc.w);
+            if (lane < nb) dh[(size_t)(eb + lane) * JAMUN_EDGE_HID + k] = lane == 0 ? acc.x : lane == 1 ? acc.y : lane == 2 ? acc.z : acc.w;
         }
         __syncthreads();
         // dxe = J^T df
-        float* o = dxe + (size_t)e * D_IN;
-        for (int t = tid; t < S_IN; t += 384) o[t] = sdf[t];
-        if (V_IN > 0 && tid < V_IN) {
-            const float dd = sdf[NS * 32 + tid];
-            const float cx = sdf[W0 + 0 * 64 + 32 + tid], cy = sdf[W0 + 1 * 64 + 32 + tid], cz = sdf[W0 + 2 * 64 + 32 + tid];
-            // cross = x_v x rhat  =>  d x_v = rhat x d cross
-            o[S_IN + tid] = dd * rh.x + sdf[W0 + 0 * 64 + tid] * kInvSqrt3 + (rh.y * cz - rh.z * cy) * kInvSqrt2;
-            o[S_IN + V_IN + tid] = dd * rh.y + sdf[W0 + 1 * 64 + tid] * kInvSqrt3 + (rh.z * cx - rh.x * cz) * kInvSqrt2;
-            o[S_IN + 2 * V_IN + tid] = dd * rh.z + sdf[W0 + 2 * 64 + tid] * kInvSqrt3 + (rh.x * cy - rh.y * cx) * kInvSqrt2;
+        const float* sdff = reinterpret_cast<const float*>(sdf);
+        for (int t = tid; t < EB * S_IN; t += 384) {
+            const int q = t / S_IN, c = t - q * S_IN;
+            if (q < nb) dxe[(size_t)(eb + q) * D_IN + c] = sdff[4 * c + q];
+        }
+        if (V_IN > 0 && tid < EB * 32) {
+            const int q = tid >> 5, w = tid & 31;
+            if (q < nb) {
+                const float4 rh = srh[q];
+                float* o = dxe + (size_t)(eb + q) * D_IN;
+                const float dd = sdff[4 * (NS32 + w) + q];
+                const float cx = sdff[4 * (W0 + 0 * 64 + 32 + w) + q], cy = sdff[4 * (W0 + 1 * 64 + 32 + w) + q],
+                            cz = sdff[4 * (W0 + 2 * 64 + 32 + w) + q];
+                // cross = x_v x rhat  =>  d x_v = rhat x d cross
+                o[S_IN + w] = dd * rh.x + sdff[4 * (W0 + 0 * 64 + w) + q] * kInvSqrt3 + (rh.y * cz - rh.z * cy) * kInvSqrt2;
+                o[S_IN + V_IN + w] = dd * rh.y + sdff[4 * (W0 + 1 * 64 + w) + q] * kInvSqrt3 + (rh.z * cx - rh.x * cz) * kInvSqrt2;
+                o[S_IN + 2 * V_IN + w] = dd * rh.z + sdff[4 * (W0 + 2 * 64 + w) + q] * kInvSqrt3 + (rh.x * cy - rh.y * cx) * kInvSqrt2;
+            }
         }
     }
 }
@@ -273,7 +336,7 @@ int launch_edge(const float* x, const int* rowptr, const int* col, const float* 
                 const float* dA1, int ld1, long long comp, int N, float* dh, float* dxe, cudaStream_t s) {
     constexpr int NS = (S_IN + 31) / 32;
     constexpr int W0 = (NS + (V_IN > 0 ? 1 : 0)) * 32, W1 = V_IN > 0 ? 64 : 0, NF = W0 + 3 * W1;
-    constexpr size_t smem = (size_t)(65 * W0 + 3 * 65 * W1 + 2 * NF + 65 + 3) * sizeof(float);
+    constexpr size_t smem = (size_t)(65 * W0 + 3 * 65 * W1 + 4 * (2 * NF + 65 + 4)) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_bwd_edge_kernel<S_IN, V_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -305,7 +305,27 @@ def _contract(topo: Topology, a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col,
               addend_scale=None if addend is None else addend_scale, a_tile_major=tiled)
 
 
-def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False) -> None:
+def _ensure_tail_operands(topo: Topology) -> None:
+    """Block-tail operands (stage-major, rows_all rows): tail_s = [activated scalars (4 stages) | input scalars (4 stages)],
+    tail_v = 3 components x [gated vectors | input vectors].  The input-scalar half doubles as the per-node transform's operand
+    xs_op.  Written by the fused GEMM epilogues (jamun_gemm_f16x3_fused), zero where never written."""
+    if getattr(topo, "tail_s", None) is None:
+        rows_all = (topo.N + 127) // 128 * 128
+        topo.tail_s = torch.zeros(8 * rows_all * 32, dtype=torch.float32, device=topo.device)
+        topo.tail_v = torch.zeros(3 * 2 * rows_all * 32, dtype=torch.float32, device=topo.device)
+        topo.xs_op = topo.tail_s[4 * rows_all * 32:]
+
+
+def _fuse_gate_ok(topo: Topology, b: Dict, build_impl: str) -> bool:
+    """The contraction can apply the Gate and write the block-tail operands itself (jamun_gemm_f16x3_fused mode 1) when it
+    runs as one pass per row tile: fp16-split GEMM, tensor-core builder, hidden block, enough tiles that split-K is off."""
+    tiles = (min(topo.chunk_rows, topo.N) + 127) // 128
+    return (b.get("gemm_kind") == "f16" and build_impl == "tc" and b["v_in"] > 0 and tiles > 74
+            and os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) == "tc" and os.environ.get("JAMUN_B200_TAIL_FUSE", "1") == "1")
+
+
+def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const_key=None, defer_reduce: bool = False,
+            fuse_gate: bool = False) -> None:
     """Conv.forward on the tensor cores: per-node transform Y = x_s.W of the 0e(x)1e->1e path (tcgen05 GEMM,
     17 column blocks) -> aggregate A of the other paths (jamun_conv_build_tc: per-node tcgen05 products; or the FP32-pipe
     jamun_conv_build_a) -> contraction jamun_gemm_tf32x3.  With the tensor-core builder the gather of Y (jamun_conv_p2) runs
@@ -319,7 +339,7 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
     rows_all = (N + 127) // 128 * 128
     if topo.a_ws is None:
         topo.a_ws = torch.empty(65 * (5 + 3 * 2) * rp * 32, dtype=torch.float32, device=topo.device)
-        topo.xs_op = torch.zeros(4 * rows_all * 32, dtype=torch.float32, device=topo.device)
+        _ensure_tail_operands(topo)
         topo.y = torch.empty(N, Y_LD, dtype=torch.float32, device=topo.device)
         topo.p2 = torch.empty(N, 96, dtype=torch.float32, device=topo.device)
         topo.t_edge = torch.empty(topo.cap, 32, dtype=torch.float32, device=topo.device)
@@ -355,7 +375,9 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
         topo.ev_fork.record(main)
         with torch.cuda.stream(side):
             side.wait_event(topo.ev_fork)
-            if defer_reduce:  # only T_e; the receiver-side sum is taken by jamun_tail_pack (block_tail)
+            if fuse_gate:  # raw receiver-side sums -> the contraction's addend (its epilogue gates conv + p2 together)
+                ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, topo.p2.data_ptr(), 96, 0.0)
+            elif defer_reduce:  # only T_e; the receiver-side sum is taken by jamun_tail_pack (block_tail)
                 ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, None, 0, 0.0)
             elif v_in:
                 ops.conv_p2(topo.rowptr, topo.src_rowptr, topo.src_eid, topo.h, topo.rhat, y_buf, topo.t_edge, topo.p2.data_ptr(), 96,
@@ -365,7 +387,8 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
                             out.data_ptr() + 4 * 152, ops.GATE_IN, b["alpha1"])
             topo.ev_join.record(side)
         topo.p2_pending = True
-        topo.p2_deferred = bool(defer_reduce)
+        topo.p2_deferred = bool(defer_reduce) and not fuse_gate
+        topo.gate_fused = bool(fuse_gate)
     for row0 in range(0, N, rp):
         nrows = min(rp, N - row0)
         if build_impl == "tc":
@@ -378,6 +401,17 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
             a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
             b_ptrs = [b["b0_img"].data_ptr()] + [b["b1_img"].data_ptr()] * 3
             p2 = topo.p2.data_ptr() + 4 * row0 * 96
+            if fuse_gate:
+                if topo.p2_pending:  # the receiver-side sums must be complete before the contraction's epilogue adds them
+                    torch.cuda.current_stream().wait_event(topo.ev_join)
+                    topo.p2_pending = False
+                epi = dict(mode=1, op_s=topo.tail_s.data_ptr() + 4 * row0 * 32, op_v=topo.tail_v.data_ptr() + 4 * row0 * 32,
+                           op_v_comp_stride=2 * rows_all * 32, op_rows_pad=rows_all, c_act=b["c_act"], c_gate=b["c_gate"])
+                ops.gemm_f16x3_fused(a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
+                                     [b["alpha0"] / sc[0]] + [b["alpha1"] / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr() + 4 * row0, epi,
+                                     addend_ptrs=[None, p2, p2 + 4 * 32, p2 + 4 * 64], addend_ld=[0, 96, 96, 96],
+                                     addend_scale=[sc[0]] + [sc[1]] * 3, status=topo.gemm_status, a_tile_major=tiled)
+                continue
             addend = None if build_impl == "tc" else [None, p2, p2 + 4 * 32, p2 + 4 * 64]
             _contract(topo, a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
                       [b["alpha0"] / sc[0]] + [b["alpha1"] / sc[1]] * 3, nrows, rp, topo.inv_deg.data_ptr() + 4 * row0,
@@ -392,6 +426,9 @@ def conv_tc(topo: Topology, b: Dict, x: torch.Tensor, out: torch.Tensor, y_const
 
 def conv_tc_join(topo: Topology, b: Dict) -> Optional[torch.Tensor]:
     """Join the side-stream gather started by conv_tc; returns the [N, 96] addend for block_tail (hidden blocks) or None."""
+    if getattr(topo, "gate_fused", False):
+        topo.gate_fused = False
+        return "fused"  # Gate applied and operands written by the contraction's epilogue
     if not getattr(topo, "p2_pending", False):
         return None
     torch.cuda.current_stream().wait_event(topo.ev_join)
@@ -406,8 +443,9 @@ TAIL_IMPL = os.environ.get("JAMUN_B200_TAIL", "tc")  # "tc": pack -> tcgen05 GEM
 
 def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_scaled, vadd) -> None:
     """Gate + self-interaction + skip Linear + noise-conditional skip/scale (ConvBlock.forward after the conv)."""
-    deferred = isinstance(vadd, str)
-    if deferred:
+    fused = vadd == "fused" if isinstance(vadd, str) else False
+    deferred = isinstance(vadd, str) and not fused
+    if isinstance(vadd, str):
         vadd = None
     if os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) != "tc" or topo.a_ws is None:
         assert not deferred, "the deferred path-2 sum needs the tensor-core block tail"
@@ -422,16 +460,36 @@ def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_sc
     assert need <= topo.a_ws.numel(), "operand workspace too small for the block tail"
     if getattr(topo, "ytail", None) is None:
         topo.ytail = torch.empty(N, ops.HID, dtype=torch.float32, device=topo.device)
-    base = topo.a_ws.data_ptr()  # the conv operand is dead once the contraction has run
-    a_v = base + 4 * st_s * rows_all * 32
-    comp = st_v * rows_all * 32
-    if deferred:
+    kind, sc = b.get("gemm_kind", "tf32"), b.get("f16_scales", (1.0, 1.0, 1.0, 1.0))
+    if fused:  # operands already in tail_s / tail_v (stages: 4 activated + 4 input scalar stages, gated + input vectors)
+        base, a_v, comp = topo.tail_s.data_ptr(), topo.tail_v.data_ptr(), 2 * rows_all * 32
+        st_s, st_v = 8, 2
+    else:
+        base = topo.a_ws.data_ptr()  # the conv operand is dead once the contraction has run
+        a_v = base + 4 * st_s * rows_all * 32
+        comp = st_v * rows_all * 32
+    if fused:
+        pass
+    elif deferred:
         ops.tail_pack(topo.conv, None, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp,
                       rowptr=topo.rowptr, rhat=topo.rhat, t_edge=topo.t_edge, p2_scale=b["alpha1"], conv_has_v=bool(b["v_in"]))
     else:
         ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
-    sc = b.get("f16_scales", (1.0, 1.0, 1.0, 1.0))
-    _gemm(topo, b.get("gemm_kind", "tf32"), [base] + [a_v + 4 * c * comp for c in range(3)],
+    if kind == "f16" and os.environ.get("JAMUN_B200_TAIL_FUSE", "1") == "1":
+        # skip-mix + next-block scaling + operand packing in the GEMM's epilogue (mode 2): no tail_mix launch, no y round trip
+        _ensure_tail_operands(topo)
+        pack = x_scaled is not None
+        epi = dict(mode=2, op_s=topo.tail_s.data_ptr() if pack else None, op_v=topo.tail_v.data_ptr() if pack else None,
+                   op_v_comp_stride=2 * rows_all * 32, op_rows_pad=rows_all, x_res=None if skip_w is None else x_res.data_ptr(),
+                   skip_w=None if skip_w is None else skip_w.data_ptr(), s_next=None if s_next is None else s_next.data_ptr(),
+                   x_new=x_new.data_ptr(), x_scaled=x_scaled.data_ptr() if pack else None)
+        ops.gemm_f16x3_fused([base] + [a_v + 4 * c * comp for c in range(3)],
+                             [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3, [st_s, st_v, st_v, st_v],
+                             [128, 32, 32, 32], [120, 32, 32, 32], [0, 120, 152, 184], [1.0 / sc[2]] + [1.0 / sc[3]] * 3, N, rows_all, None,
+                             epi, status=topo.gemm_status)
+        topo.xs_op_of = x_scaled if pack else None
+        return
+    _gemm(topo, kind, [base] + [a_v + 4 * c * comp for c in range(3)],
           [b["tail_bs_img"].data_ptr()] + [b["tail_bv_img"].data_ptr()] * 3, [st_s, st_v, st_v, st_v], [128, 32, 32, 32],
           [120, 32, 32, 32], [0, 120, 152, 184], [1.0 / sc[2]] + [1.0 / sc[3]] * 3, N, rows_all, None, topo.ytail.data_ptr(), ops.HID)
     pack = x_scaled is not None and getattr(topo, "xs_op", None) is not None
@@ -466,7 +524,9 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
                          b["alpha0"], b["alpha1"], topo.conv)
         else:
             tail_tc = os.environ.get("JAMUN_B200_TAIL", TAIL_IMPL) == "tc" and os.environ.get("JAMUN_B200_BUILD", BUILD_IMPL) == "tc"
-            conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None, defer_reduce=tail_tc)
+            conv_tc(topo, b, x_in, topo.conv, y_const_key=key if l == 0 else None, defer_reduce=tail_tc,
+                    fuse_gate=tail_tc and l > 0 and topo.xs_op_of is x_in  # x_in's packed halves were written by the last tail
+                    and _fuse_gate_ok(topo, b, os.environ.get("JAMUN_B200_BUILD", BUILD_IMPL)))
             vadd = conv_tc_join(topo, b)
         x_new, x_scaled = topo.xa[l & 1], topo.xs[l & 1]
         skip_w = plan.skips[l - 1] if l > 0 else None

@@ -314,6 +314,23 @@ def gemm_f16x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: i
     _count(2 if k_splits > 1 else 1)
 
 
+def gemm_f16x3_fused(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr, epi: dict,
+                     addend_ptrs=None, addend_ld=None, addend_scale=None, status=None, a_tile_major: bool = False):
+    """gemm_f16x3 with a fused ConvBlock epilogue (jamun_gemm_epilogue): epi = dict(mode=1|2, op_s=ptr, op_v=ptr,
+    op_v_comp_stride=floats, op_rows_pad=rows, c_act=, c_gate= | x_res=ptr, skip_w=ptr, s_next=ptr, x_new=ptr, x_scaled=ptr)."""
+    n = len(a_ptrs)
+    VP, IA, FA = C.c_void_p * n, C.c_int * n, C.c_float * n
+    ad = VP(*addend_ptrs) if addend_ptrs is not None else None
+    adl = IA(*addend_ld) if addend_ld is not None else None
+    ads = FA(*addend_scale) if addend_scale is not None else None
+    e = _lib.GemmEpilogue(**{k: (v if v is not None else None) for k, v in epi.items()})
+    rc = _lib.lib().jamun_gemm_f16x3_fused(n, VP(*a_ptrs), VP(*b_ptrs), IA(*n_stages), IA(*n_pad), IA(*n_valid), IA(*out_col),
+                                           FA(*alpha), ad, adl, ads, rows, rows_pad, row_scale_ptr, _ptr(status, torch.int32),
+                                           int(a_tile_major), C.byref(e), _stream())
+    _lib.check(rc, "jamun_gemm_f16x3_fused")
+    _count()
+
+
 def gemm_tf32x3(a_ptrs, b_ptrs, n_stages, n_pad, n_valid, out_col, alpha, rows: int, rows_pad: int, row_scale_ptr,
                 out_ptr, out_ld: int, addend_ptrs=None, addend_ld=None, col_blocks: int = 1, b_block_floats: int = 0):
     """Raw-pointer front end (segments are slices of larger workspaces).  All lists have one entry per segment."""

@@ -49,9 +49,15 @@ def test_walk_params_struct_matches_header():
     from jamun_b200 import _lib
 
     header = open(os.path.join(ROOT, "include", "jamun_b200.h")).read()
-    body = header[header.index("typedef struct {"):header.index("} jamun_walk_params;")]
+    end = header.index("} jamun_walk_params;")
+    body = header[header.rindex("typedef struct {", 0, end):end]
     names = re.findall(r"\b([a-z_0-9]+)\s*[,;]", body)
     assert names == [f[0] for f in _lib.WalkParams._fields_]
+    # the fused-epilogue descriptor of jamun_gemm_f16x3_fused
+    end = header.index("} jamun_gemm_epilogue;")
+    body = re.sub(r"/\*.*?\*/", "", header[header.rindex("typedef struct {", 0, end):end], flags=re.S)
+    names = re.findall(r"\b([a-z_0-9]+)\s*[,;]", body)
+    assert names == [f[0] for f in _lib.GemmEpilogue._fields_]
 
 
 def test_no_cpu_fallback_and_error_conventions():

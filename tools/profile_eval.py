@@ -32,7 +32,7 @@ kw = dict(delta=0.04, friction=1.0, M=1.0, inverse_temperature=1.0, score_fn_cli
 fused_baoab(model, wrapped.topology, y, 0.04, steps=3, v_init="gaussian", use_cuda_graph=False, **kw)  # warm-up
 
 records = collections.defaultdict(list)
-names = ["center_scale", "radius_csr", "csr_by_source", "edge_geom", "edge_radial_hidden", "edge_radial_hidden_all", "pack_rows", "gemm_tf32x3", "gemm_f16x3", "conv_build_a", "conv_build_tc", "conv_p2", "block_tail", "tail_pack", "tail_mix",
+names = ["center_scale", "radius_csr", "csr_by_source", "edge_geom", "edge_radial_hidden", "edge_radial_hidden_all", "pack_rows", "gemm_tf32x3", "gemm_f16x3", "gemm_f16x3_fused", "conv_build_a", "conv_build_tc", "conv_p2", "block_tail", "tail_pack", "tail_mix",
          "head", "walk_step", "gaussian_axpy"]
 orig = {n: getattr(ops, n) for n in names}
 
@@ -44,6 +44,8 @@ def wrap(n):
         r = orig[n](*a, **k)
         e1.record()
         tag = n
+        if n == "gemm_f16x3_fused":
+            tag = "gemm_f16x3_fused (contraction + gate)" if a[10]["mode"] == 1 else "gemm_f16x3_fused (block tail + mix)"
         if n in ("gemm_tf32x3", "gemm_f16x3"):
             tag = (f"{n} (transform Y)" if k.get("col_blocks", 1) > 1 else
                    f"{n} (block tail)" if a[3][0] == 128 else f"{n} (contraction)")
