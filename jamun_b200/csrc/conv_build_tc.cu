@@ -33,7 +33,11 @@ constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr int YLD = 17 * 128;
 constexpr int kSlots = 2;        // operand slots
 constexpr int kAccCols = 80;     // accumulator width: 65 channels padded to a legal N
-constexpr int kProducerWarps = 8;
+#ifndef JAMUN_BUILD_PRODUCERS
+#define JAMUN_BUILD_PRODUCERS 8
+#endif
+constexpr int kProducerWarps = JAMUN_BUILD_PRODUCERS;  // 8; 11 (= 5 warps per scheduler at 96 registers) measured: 2AA +9 %, 4AA -1 %, protein1000 -5 %
+__host__ __device__ constexpr int pmod(int x) { return ((x % kProducerWarps) + kProducerWarps) % kProducerWarps; }
 constexpr int kEpiWarps = 8;     // two sets of four (TMEM lane quarter = warp % 4)
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kThreads = 32 * (kEpiWarps + 1 + kProducerWarps);
@@ -171,7 +175,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             for (int q = 0; q < 4; ++q) jc[q] = jn[q];
             e0_n = e0_nn, deg_n = deg_nn;
             if (r + r_step < r_end) {
-                const int kn = (w - tb - tasks_of(deg)) & 7;  // this warp's K-quad in the next node's first chunk
+                const int kn = pmod(w - tb - tasks_of(deg));  // this warp's K-quad in the next node's first chunk
 #pragma unroll
                 for (int q = 0; q < 4; ++q) jn[q] = 4 * kn + q < deg_n ? col[e0_n + 4 * kn + q] : 0;
             }
@@ -185,8 +189,8 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                 const int n = min(32, deg - 32 * c);
                 const int ksteps = n > 8 ? (n + 7) >> 3 : 1;
                 const int ntasks = 2 * ksteps;
-                const int g = (w - tb) & 7;  // K-quad owned by this warp (none if g >= ntasks)
-                tb = (tb + ntasks) & 7;
+                const int g = pmod(w - tb);  // K-quad owned by this warp (none if g >= ntasks)
+                tb = pmod(tb + ntasks);
                 const uint32_t off = off_lane + (uint32_t)((g ^ (lane & 7)) << 4);
                 if (g == 0) TC_TRACE(it, 0);
                 const int s = it % kSlots;
