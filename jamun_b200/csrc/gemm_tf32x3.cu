@@ -136,50 +136,56 @@ __device__ __forceinline__ void epi_gate(const Params& P, int s, int c0, const u
 // input scaling x_scaled = x_new * s_next (model/noise_conditioning.py:50-73, arch/e3conv.py:131-133), written row-major for
 // the gathers of the next aggregate and, packed, as the x_in halves of the next block-tail operands (scalars: stages 4-7 of
 // op_s, which are also the per-node transform's operand; vectors: stage 1 of op_v).  Weights are per irrep: [120 | 32].
-__device__ __forceinline__ void epi_mix(const Params& P, int s, int c0, const uint32_t (&v)[32], int row) {
+// The warp's 32 x 32 accumulator block (thread = row) is transposed through shared memory first, so that every global access
+// below is a float4 with eight lanes covering one 128-byte piece of a row: 4 rows per instruction instead of 32 scattered
+// 16-byte pieces.  Called by all 32 lanes (rows beyond the batch only skip the memory accesses).
+__device__ __forceinline__ void epi_mix(const Params& P, int s, int c0, const uint32_t (&v)[32], int warp_row0, int lane, float* stg) {
     const jamun_gemm_epilogue& E = P.epi;
     const Seg& sg = P.seg[s];
     const int nval = sg.n_valid - c0 < 32 ? sg.n_valid - c0 : 32;  // 24 in the last scalar chunk
     if (nval <= 0) return;
-    const int j0 = sg.out_col + c0;                        // column of the [216]-wide node row
-    const int w0 = s == 0 ? c0 : JAMUN_S;                  // first per-irrep weight of this chunk
-    const float* xr = E.skip_w ? E.x_res + (size_t)row * JAMUN_HID + j0 : nullptr;
-    float xn[32], xs[32];
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xr && 4 * q4 < nval) r4 = *reinterpret_cast<const float4*>(xr + 4 * q4);
-        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(v[4 * q]) * sg.alpha, __uint_as_float(v[4 * q + 1]) * sg.alpha,
+                        __uint_as_float(v[4 * q + 2]) * sg.alpha, __uint_as_float(v[4 * q + 3]) * sg.alpha);
+    __syncwarp();
+    const int ch = lane & 7;                               // 16-byte piece of the 32-column chunk
+    const int j0 = sg.out_col + c0 + 4 * ch;               // column of the [216]-wide node row
+    const int w0 = (s == 0 ? c0 : JAMUN_S) + 4 * ch;       // per-irrep weight index
+    const bool cols_live = 4 * ch < nval;
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (cols_live) {
+        if (E.skip_w) w4 = *reinterpret_cast<const float4*>(E.skip_w + w0);
+        if (E.s_next) s4 = *reinterpret_cast<const float4*>(E.s_next + w0);
+    }
+    const bool pack = E.x_scaled && E.op_s;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int q = 4 * q4 + t;
-            float y = __uint_as_float(v[q]) * sg.alpha;
-            if (q < nval) {
-                if (E.skip_w) {
-                    const float w = E.skip_w[w0 + q];
-                    y = rr[t] * w + y * (1.0f - w);
-                }
-                xn[q] = y;
-                xs[q] = E.s_next ? y * E.s_next[w0 + q] : y;
-            } else {
-                xn[q] = 0.f;
-                xs[q] = 0.f;
+    for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3);
+        const int row = warp_row0 + rl;
+        if (row >= P.rows) continue;
+        float4 y = *reinterpret_cast<const float4*>(stg + rl * 32 + ((ch ^ (rl & 7)) << 2));
+        float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cols_live) {
+            if (E.skip_w) {
+                const float4 r4 = *reinterpret_cast<const float4*>(E.x_res + (size_t)row * JAMUN_HID + j0);
+                y.x = r4.x * w4.x + y.x * (1.0f - w4.x);
+                y.y = r4.y * w4.y + y.y * (1.0f - w4.y);
+                y.z = r4.z * w4.z + y.z * (1.0f - w4.z);
+                y.w = r4.w * w4.w + y.w * (1.0f - w4.w);
             }
+            *reinterpret_cast<float4*>(E.x_new + (size_t)row * JAMUN_HID + j0) = y;
+            xs = make_float4(y.x * s4.x, y.y * s4.y, y.z * s4.z, y.w * s4.w);
+            if (E.x_scaled) *reinterpret_cast<float4*>(E.x_scaled + (size_t)row * JAMUN_HID + j0) = xs;
+        }
+        if (pack) {
+            float* dst = s == 0 ? E.op_s + ((size_t)(4 + (c0 >> 5)) * E.op_rows_pad + row) * 32
+                                : E.op_v + (size_t)(s - 1) * E.op_v_comp_stride + ((size_t)E.op_rows_pad + row) * 32;
+            *reinterpret_cast<float4*>(dst + ((ch ^ (row & 7)) << 2)) = xs;  // columns beyond the segment: zeros
         }
     }
-    float* on = E.x_new + (size_t)row * JAMUN_HID + j0;
-    float* os = E.x_scaled ? E.x_scaled + (size_t)row * JAMUN_HID + j0 : nullptr;
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4)
-        if (4 * q4 < nval) {
-            *reinterpret_cast<float4*>(on + 4 * q4) = make_float4(xn[4 * q4], xn[4 * q4 + 1], xn[4 * q4 + 2], xn[4 * q4 + 3]);
-            if (os) *reinterpret_cast<float4*>(os + 4 * q4) = make_float4(xs[4 * q4], xs[4 * q4 + 1], xs[4 * q4 + 2], xs[4 * q4 + 3]);
-        }
-    if (E.x_scaled && E.op_s) {
-        const int sw = row & 7;
-        if (s == 0) store_op_row(E.op_s + ((size_t)(4 + (c0 >> 5)) * E.op_rows_pad + row) * 32, sw, xs);
-        else store_op_row(E.op_v + (size_t)(s - 1) * E.op_v_comp_stride + ((size_t)E.op_rows_pad + row) * 32, sw, xs);
-    }
+    __syncwarp();
 }
 
 // COALESCE: epilogue variant for wide outputs in stationary mode (kept out of the contraction instantiation: +40 registers)
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params P
                     // (epi_gate reads TMEM with a warp-collective tcgen05.ld: every thread calls it, rows beyond the batch only
                     // skip the memory accesses)
                     if (P.epi.mode == 1) epi_gate(P, s, c0, v, row, row < P.rows, rs_own, tmem + lane_base);
-                    else if (row < P.rows) epi_mix(P, s, c0, v, row);
+                    else epi_mix(P, s, c0, v, tile_row0 + (warp & 3) * 32, threadIdx.x & 31, reinterpret_cast<float*>(S.a[4]) + warp * 1024);
                     continue;
                 }
                 if (row < P.rows) {

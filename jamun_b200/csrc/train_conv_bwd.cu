@@ -207,10 +207,8 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             for (int k = 0; k < 65; ++k) {
                 const float a = A[k * lda];
                 const float4 hk = sh[k];
-                acc.x = fmaf(hk.x, a, acc.x);
-                acc.y = fmaf(hk.y, a, acc.y);
-                acc.z = fmaf(hk.z, a, acc.z);
-                acc.w = fmaf(hk.w, a, acc.w);
+                jb::ffma2(acc.x, acc.y, a, hk.x, hk.y);  // packed FP32 FMA: two edges per issue slot
+                jb::ffma2(acc.z, acc.w, a, hk.z, hk.w);
             }
             sdf[tid] = acc;
         }
@@ -220,7 +218,8 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             for (int u = lane; u < W0; u += 32) {
                 const float a = sA0[k * W0 + u];
                 const float4 f = sf[u];
-                acc.x = fmaf(f.x, a, acc.x), acc.y = fmaf(f.y, a, acc.y), acc.z = fmaf(f.z, a, acc.z), acc.w = fmaf(f.w, a, acc.w);
+                jb::ffma2(acc.x, acc.y, a, f.x, f.y);
+                jb::ffma2(acc.z, acc.w, a, f.z, f.w);
             }
             if (V_IN > 0)
 #pragma unroll
@@ -230,7 +229,8 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                     for (int hv = 0; hv < 2; ++hv) {
                         const float a = A[32 * hv + lane];
                         const float4 f = sf[W0 + c * 64 + 32 * hv + lane];
-                        acc.x = fmaf(f.x, a, acc.x), acc.y = fmaf(f.y, a, acc.y), acc.z = fmaf(f.z, a, acc.z), acc.w = fmaf(f.w, a, acc.w);
+                        jb::ffma2(acc.x, acc.y, a, f.x, f.y);
+                        jb::ffma2(acc.z, acc.w, a, f.z, f.w);
                     }
                 }
             acc.x = warp_sum(acc.x), acc.y = warp_sum(acc.y), acc.z = warp_sum(acc.z), acc.w = warp_sum(acc.w);

@@ -133,21 +133,37 @@ __global__ void radial_bwd_kernel(const float* __restrict__ rb, const unsigned c
 }
 
 // ---- atom embedding backward (model/atom_embedding.py:58-76 fused with the initial noise scaling) ------------------------------
-// x0[i, col_k + c] = tab_k[idx_k[i]][c] * scale[col_k + c].  One warp per (table, row): lanes stride the atoms in order.
+// x0[i, col_k + c] = tab_k[idx_k[i]][c] * scale[col_k + c].  One CTA per (table, row r): its 8 warps take contiguous eighths of
+// the atoms, read 32 indices per step (coalesced), and for every atom of the step whose index is r (ballot, ascending order)
+// add that atom's gradient row (lanes = the table's columns, dim <= 32); the eight partial rows are summed in warp order.
+// Fixed order everywhere: bit-reproducible.
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const int* __restrict__ idx, const float* __restrict__ scale, const float* __restrict__ dx0, int ld, int col0, int dim,
                  int n_rows, int N, float* __restrict__ dtab) {
-    const int lane = threadIdx.x & 31;
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x;
     if (r >= n_rows) return;
-    for (int c = 0; c < dim; ++c) {
-        float acc = 0.f;
-        for (int i = lane; i < N; i += 32) {
-            const int id = idx ? idx[i] : 0;
-            if (id == r) acc += dx0[(size_t)i * ld + col0 + c];
+    const int per = (((N + 7) / 8) + 31) & ~31;  // atoms per warp, a multiple of 32
+    const int i0 = warp * per, i1 = min(N, i0 + per);
+    float acc = 0.f;
+    for (int base = i0; base < i1; base += 32) {
+        const int i = base + lane;
+        const int id = i < i1 ? (idx ? idx[i] : 0) : -1;
+        unsigned m = __ballot_sync(0xffffffffu, id == r);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            if (lane < dim) acc += dx0[(size_t)(base + j) * ld + col0 + lane];
         }
-        acc = warp_sum(acc);
-        if (lane == 0) dtab[(size_t)r * dim + c] = acc * (scale ? scale[col0 + c] : 1.f);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && lane < dim) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        dtab[(size_t)r * dim + lane] = t * (scale ? scale[col0 + lane] : 1.f);
     }
 }
 
@@ -485,6 +501,7 @@ extern "C" int jamun_embed_bwd(const int* idx0, const int* idx1, const int* idx2
                                float* dtab0, float* dtab1, float* dtab2, float* dtab3, float* prod, jamun_stream_t stream) {
     JB_CHECK_ARG(idx0 && idx1 && idx2 && tab0 && tab1 && tab2 && tab3 && dx0 && dtab0 && dtab1 && dtab2 && dtab3 && prod,
                  "null argument");
+    JB_CHECK_ARG(dim0 <= 32 && dim1 <= 32 && dim2 <= 32 && dim3 <= 32, "embedding tables wider than 32 columns");
     cudaStream_t s = jb::as_stream(stream);
     const int D = dim0 + dim1 + dim2 + dim3;
     const int* idx[4] = {idx0, idx1, idx2, idx3};
@@ -492,7 +509,7 @@ extern "C" int jamun_embed_bwd(const int* idx0, const int* idx1, const int* idx2
     const int dims[4] = {dim0, dim1, dim2, dim3}, rows[4] = {rows0, rows1, rows2, rows3};
     int col0 = 0;
     for (int k = 0; k < 4; ++k) {
-        embed_bwd_kernel<<<(rows[k] * 32 + 255) / 256, 256, 0, s>>>(idx[k], scale, dx0, D, col0, dims[k], rows[k], N, dt[k]);
+        if (rows[k] > 0) embed_bwd_kernel<<<rows[k], 256, 0, s>>>(idx[k], scale, dx0, D, col0, dims[k], rows[k], N, dt[k]);
         col0 += dims[k];
     }
     if (N > 0)
