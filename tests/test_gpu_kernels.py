@@ -474,6 +474,25 @@ def test_full_size_properties(models, monkeypatch):
     monkeypatch.setattr(engine, "CONV_IMPL", "tc")
     monkeypatch.delenv("JAMUN_B200_TAIL")
     assert torch.allclose(x, x_simt, rtol=1e-4, atol=1e-5), (x - x_simt).abs().max()
+    # (1b) the tf32-split GEMMs with the unfused block tail (round-1 pipeline) agree with the fp16-split, fused-epilogue default
+    monkeypatch.setenv("JAMUN_B200_GEMM", "tf32")
+    x_tf32 = run(y)
+    monkeypatch.delenv("JAMUN_B200_GEMM")
+    assert torch.allclose(x, x_tf32, rtol=1e-4, atol=1e-5), (x - x_tf32).abs().max()
+    monkeypatch.setenv("JAMUN_B200_TAIL_FUSE", "0")
+    x_unfused = run(y)
+    monkeypatch.delenv("JAMUN_B200_TAIL_FUSE")
+    assert torch.allclose(x, x_unfused, rtol=1e-5, atol=1e-6), (x - x_unfused).abs().max()
+    # (1c) the operand workspace capped so that the batch is processed in two row chunks (as BASELINE config 4 is at 512 k
+    # atoms): fused epilogues address the block-tail operands and the path-2 addend by chunk offset -- same bits
+    monkeypatch.setattr(engine.Topology, "WORKSPACE_BYTES", 9600 * 65 * 11 * 32 * 4)
+    batch_c = data.Batch.from_tensors(t).to("cuda")
+    yb = batch_c.clone("pos")
+    yb.pos = y.cuda().contiguous()
+    x_chunked = prod.xhat(yb, SIGMA).pos.cpu()
+    assert prod.topology_for(yb).chunk_rows == 9600
+    monkeypatch.undo()
+    assert torch.equal(x_chunked, x), (x_chunked - x).abs().max()
     # (2) the last 12 chains alone, against the oracle
     k = 12
     n_tail = sum(sizes[-k:])
