@@ -21,6 +21,7 @@
 // Two operand slots and two sets of three 80-column accumulators keep the roles overlapped; the kernel is persistent
 // with one CTA per SM (222 KB of shared memory) and is bound by the HBM write of A (91.5 KB per node).
 // The path 0e(x)1e->1e gather (p2) is conv_p2_kernel below.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -31,7 +32,6 @@ using namespace jb;
 constexpr float kInvSqrt3 = 0.57735026918962576451f;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr int YLD = 17 * 128;
-constexpr int kSlots = 2;        // operand slots
 constexpr int kAccCols = 80;     // accumulator width: 65 channels padded to a legal N
 #ifndef JAMUN_BUILD_PRODUCERS
 #define JAMUN_BUILD_PRODUCERS 8
@@ -43,7 +43,11 @@ constexpr int kMmaWarp = kEpiWarps;
 constexpr int kThreads = 32 * (kEpiWarps + 1 + kProducerWarps);
 constexpr int kHBytes = kAccCols * 128;  // H tile: channel rows 0..64 (rows 65..79 are never written nor used)
 
-template <int S_IN, int V_IN>
+// F16: operands split in fp16 and interleaved along K -- a 16-byte chunk of a tile row = [hi(e0..e3) | lo(e0..e3)] halves, so
+// one kind::f16 instruction (K = 16) covers 8 edges and  F.H1 + F.H2  with H1 = [hh | hh], H2 = [hl | 0] gives
+// fh.hh + fl.hh + fh.hl: 2 MMAs per 8-edge step instead of 3, one F tile instead of two (half the shared-memory stores), and
+// three operand slots instead of two in the same shared memory.  (tf32: F16 = false, the round-1 form.)
+template <int S_IN, int V_IN, bool F16 = false>
 struct Shape {
     static constexpr int D_IN = S_IN + 3 * V_IN;
     static constexpr int NS = (S_IN + 31) / 32;
@@ -51,7 +55,8 @@ struct Shape {
     static constexpr int NCOL = NS + (V_IN > 0 ? 7 : 0);  // 32-column groups of F
     static constexpr int F_BYTES = NCOL * 32 * 128;
     static constexpr int NT = V_IN > 0 ? 3 : 1;           // M tiles (accumulators) per node
-    static constexpr int SLOT_BYTES = 2 * kHBytes + 2 * F_BYTES;
+    static constexpr int kSlots = F16 ? 3 : 2;  // operand slots
+    static constexpr int SLOT_BYTES = 2 * kHBytes + (F16 ? 1 : 2) * F_BYTES;
     // barriers | slots | tail the last M tile's 128-row read may run into
     static constexpr int SMEM_BYTES = 1024 /*alignment*/ + 1024 /*barriers*/ + kSlots * SLOT_BYTES + 8192;
     __host__ __device__ static constexpr int tgroups(int t) { return t == 0 ? NS : t == 1 ? 4 : 3; }  // live 32-column groups
@@ -71,14 +76,31 @@ __device__ __forceinline__ void store_split(unsigned char* hi_tile, unsigned cha
     *reinterpret_cast<float4*>(lo_tile + off) = make_float4(a - ah, b - bh, c - ch, d - dh);
 }
 
-template <int S_IN, int V_IN, bool TRACE = false>
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// fp16 split of a K-quad: hi = rn16(v), lo = rn16(v - hi) as packed half2 words (hi01, hi23, lo01, lo23)
+__device__ __forceinline__ uint4 split_f16(float a, float b, float c, float d) {
+    const __half2 h01 = __floats2half2_rn(a, b), h23 = __floats2half2_rn(c, d);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    return make_uint4(h2u(h01), h2u(h23), h2u(__floats2half2_rn(a - f01.x, b - f01.y)), h2u(__floats2half2_rn(c - f23.x, d - f23.y)));
+}
+// F operand chunk: [hi | lo];  H operand chunks: H1 = [hi | hi], H2 = [lo | 0]
+__device__ __forceinline__ void store_f_f16(unsigned char* tile, uint32_t off, float a, float b, float c, float d) {
+    *reinterpret_cast<uint4*>(tile + off) = split_f16(a, b, c, d);
+}
+__device__ __forceinline__ void store_h_f16(unsigned char* h1, unsigned char* h2, uint32_t off, float a, float b, float c, float d) {
+    const uint4 s = split_f16(a, b, c, d);
+    *reinterpret_cast<uint4*>(h1 + off) = make_uint4(s.x, s.y, s.x, s.y);
+    *reinterpret_cast<uint4*>(h2 + off) = make_uint4(s.z, s.w, 0u, 0u);
+}
+
+template <int S_IN, int V_IN, bool TRACE = false, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                      const float* __restrict__ h, const float* __restrict__ rhat, int row0, int nrows, int rows_pad,
                      float* __restrict__ a0, float* __restrict__ a1, size_t a1_comp_stride, float* __restrict__ inv_deg,
                      int tile_major, int pf_dist) {
-    using SH = Shape<S_IN, V_IN>;
-    constexpr int NS = SH::NS, NCOL = SH::NCOL, NT = SH::NT;
+    using SH = Shape<S_IN, V_IN, F16>;
+    constexpr int NS = SH::NS, NCOL = SH::NCOL, NT = SH::NT, kSlots = SH::kSlots;
     constexpr int kBufs = 2 * NT;
     extern __shared__ unsigned char dsm_raw[];
     unsigned char* dsm = reinterpret_cast<unsigned char*>(((uintptr_t)dsm_raw + 1023) & ~(uintptr_t)1023);
@@ -248,6 +270,18 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                     if (g == 0) TC_TRACE(it, 1);
                     umma::mbar_wait(&empty[s], empty_parity);  // gathers above overlap the MMAs still reading this slot
                     if (g == 0) TC_TRACE(it, 2);
+                    if constexpr (F16) {  // Hhi / Hlo hold H1 = [hi | hi] / H2 = [lo | 0]; Fhi is the one F tile
+#pragma unroll
+                        for (int sl = 0; sl < NCOL; ++sl) store_f_f16(Fhi, off + sl * 4096, f[sl][0], f[sl][1], f[sl][2], f[sl][3]);
+                        store_h_f16(Hhi, Hlo, off, hh[0][0], hh[0][1], hh[0][2], hh[0][3]);
+                        store_h_f16(Hhi, Hlo, off + 4096, hh[1][0], hh[1][1], hh[1][2], hh[1][3]);
+                        if (lane == 0) {  // row 64: the bias channel h' = 1 (row % 8 == 0: chunk g is not permuted)
+                            const uint32_t o64 = 8 * 1024 + (uint32_t)(g << 4);
+                            const uint32_t w01 = 0x3C00u | (nv > 1 ? 0x3C000000u : 0u), w23 = (nv > 2 ? 0x3C00u : 0u) | (nv > 3 ? 0x3C000000u : 0u);
+                            *reinterpret_cast<uint4*>(Hhi + o64) = make_uint4(w01, w23, w01, w23);
+                            *reinterpret_cast<uint4*>(Hlo + o64) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    } else {
 #pragma unroll
                     for (int sl = 0; sl < NCOL; ++sl) store_split(Fhi, Flo, off + sl * 4096, f[sl][0], f[sl][1], f[sl][2], f[sl][3]);
                     store_split(Hhi, Hlo, off, hh[0][0], hh[0][1], hh[0][2], hh[0][3]);
@@ -258,13 +292,14 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                             make_float4(1.f, nv > 1 ? 1.f : 0.f, nv > 2 ? 1.f : 0.f, nv > 3 ? 1.f : 0.f);
                         *reinterpret_cast<float4*>(Hlo + o64) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    }
                 } else if (g < 2 * ksteps) {  // zero K-quad completing the last 8-edge step (or an isolated node)
                     umma::mbar_wait(&empty[s], empty_parity);
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int sl = 0; sl < NCOL; ++sl) {
                         *reinterpret_cast<float4*>(Fhi + off + sl * 4096) = z;
-                        *reinterpret_cast<float4*>(Flo + off + sl * 4096) = z;
+                        if constexpr (!F16) *reinterpret_cast<float4*>(Flo + off + sl * 4096) = z;
                     }
                     *reinterpret_cast<float4*>(Hhi + off) = z;
                     *reinterpret_cast<float4*>(Hlo + off) = z;
@@ -288,7 +323,7 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma::make_idesc_tf32(128, kAccCols);
+        constexpr uint32_t idesc = F16 ? umma::make_idesc_f16(128, kAccCols) : umma::make_idesc_tf32(128, kAccCols);
         int it = 0;
         uint32_t na = 0;  // node counter of this CTA: accumulator set = na & 1
         for (int r = r_begin; r < r_end; r += r_step, ++na) {
@@ -319,6 +354,13 @@ conv_build_tc_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
                         const uint32_t flo = umma::desc_lo_kmajor_sw128(slot + 2 * kHBytes + SH::F_BYTES + SH::trow0(t) * 128);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t k2 = 2u * ks;  // 32 bytes per K step, in 16-byte descriptor units
+                            if constexpr (F16) {  // F.[hh | hh] + F.[hl | 0]  (hhi / hlo address the H1 / H2 tiles)
+                                umma::mma_f16_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
+                                                 umma::make_desc(hhi + k2, umma::kDescHiKmajorSw128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                                umma::mma_f16_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
+                                                 umma::make_desc(hlo + k2, umma::kDescHiKmajorSw128), idesc, 1u);
+                                continue;
+                            }
                             umma::mma_tf32_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
                                               umma::make_desc(hhi + k2, umma::kDescHiKmajorSw128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
                             umma::mma_tf32_ss(d, umma::make_desc(fhi + k2, umma::kDescHiKmajorSw128),
@@ -484,13 +526,14 @@ conv_p2_reduce_kernel(const int* __restrict__ rowptr, const float* __restrict__ 
     out[2 * JAMUN_V] = pz * sc;
 }
 
-template <int S_IN, int V_IN, bool TRACE>
-int launch_tc(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
-              int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, int tile_major, cudaStream_t s) {
-    using SH = Shape<S_IN, V_IN>;
+template <int S_IN, int V_IN, bool TRACE, bool F16>
+int launch_tc_t(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
+                int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, int tile_major, cudaStream_t s) {
+    using SH = Shape<S_IN, V_IN, F16>;
+    static_assert(SH::SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_build_tc_kernel<S_IN, V_IN, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_build_tc_kernel<S_IN, V_IN, TRACE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SH::SMEM_BYTES);
         if (e != cudaSuccess) {
             jb::set_error("jamun_conv_build_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -504,10 +547,25 @@ int launch_tc(const float* x, const int* rowptr, const int* col, const float* h,
         const char* e = getenv("JAMUN_BUILD_PF");
         pf_dist = e ? atoi(e) : 4;
     }
-    conv_build_tc_kernel<S_IN, V_IN, TRACE><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows,
-                                                                                     rows_pad, a0, a1, comp, inv_deg, tile_major,
-                                                                                     pf_dist);
+    conv_build_tc_kernel<S_IN, V_IN, TRACE, F16><<<blocks, kThreads, SH::SMEM_BYTES, s>>>(x, rowptr, col, h, rhat, row0, nrows,
+                                                                                          rows_pad, a0, a1, comp, inv_deg, tile_major,
+                                                                                          pf_dist);
     return JAMUN_OK;
+}
+
+template <int S_IN, int V_IN, bool TRACE>
+int launch_tc(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, int row0, int nrows,
+              int rows_pad, float* a0, float* a1, size_t comp, float* inv_deg, int tile_major, cudaStream_t s) {
+    // operand split of the per-node products: tf32 (default) or fp16-interleaved (JAMUN_B200_BUILD_SPLIT=f16).  The fp16 form issues
+    // 2/3 of the MMAs and half the shared-memory stores, but measured no faster (2AA 1.89 vs 1.73 ms per six launches, 4AA 3.72 vs
+    // 3.65, protein1000 8.0 vs 8.2): the per-item time is not set by the MMA count
+    static int f16 = -1;
+    if (f16 < 0) {
+        const char* e = getenv("JAMUN_B200_BUILD_SPLIT");
+        f16 = (e && e[0] == 'f') ? 1 : 0;
+    }
+    return f16 ? launch_tc_t<S_IN, V_IN, TRACE, true>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, comp, inv_deg, tile_major, s)
+               : launch_tc_t<S_IN, V_IN, TRACE, false>(x, rowptr, col, h, rhat, row0, nrows, rows_pad, a0, a1, comp, inv_deg, tile_major, s);
 }
 
 }  // namespace
