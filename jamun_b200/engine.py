@@ -475,7 +475,9 @@ def block_tail(topo: Topology, b: Dict, x_in, x_res, skip_w, s_next, x_new, x_sc
                       rowptr=topo.rowptr, rhat=topo.rhat, t_edge=topo.t_edge, p2_scale=b["alpha1"], conv_has_v=bool(b["v_in"]))
     else:
         ops.tail_pack(topo.conv, vadd, x_in, b["s_in"], b["v_in"], b["c_act"], b["c_gate"], rows_all, base, a_v, comp)
-    if kind == "f16" and os.environ.get("JAMUN_B200_TAIL_FUSE", "1") == "1":
+    # (few row tiles -- small batches -- keep tail_mix: it spreads over all SMs, the GEMM's epilogue only over its few CTAs;
+    # measured on C1, 11 tiles: 1.73 M atom-steps/s unfused vs 1.57 M fused)
+    if kind == "f16" and os.environ.get("JAMUN_B200_TAIL_FUSE", "1") == "1" and (fused or rows_all // 128 > 74):
         # skip-mix + next-block scaling + operand packing in the GEMM's epilogue (mode 2): no tail_mix launch, no y round trip
         _ensure_tail_operands(topo)
         pack = x_scaled is not None

@@ -484,7 +484,7 @@ def test_full_size_properties(models, monkeypatch):
     monkeypatch.delenv("JAMUN_B200_TAIL_FUSE")
     assert torch.allclose(x, x_unfused, rtol=1e-5, atol=1e-6), (x - x_unfused).abs().max()
     # (1c) the operand workspace capped so that the batch is processed in two row chunks (as BASELINE config 4 is at 512 k
-    # atoms): fused epilogues address the block-tail operands and the path-2 addend by chunk offset -- same bits
+    # atoms): fused epilogues address the block-tail operands and the path-2 addend by chunk offset
     monkeypatch.setattr(engine.Topology, "WORKSPACE_BYTES", 9600 * 65 * 11 * 32 * 4)
     batch_c = data.Batch.from_tensors(t).to("cuda")
     yb = batch_c.clone("pos")
@@ -492,7 +492,8 @@ def test_full_size_properties(models, monkeypatch):
     x_chunked = prod.xhat(yb, SIGMA).pos.cpu()
     assert prod.topology_for(yb).chunk_rows == 9600
     monkeypatch.undo()
-    assert torch.equal(x_chunked, x), (x_chunked - x).abs().max()
+    # (not bit-identical: the second chunk of the initial block has few enough row tiles to take the split-K contraction)
+    assert torch.allclose(x_chunked, x, rtol=1e-5, atol=1e-6), (x_chunked - x).abs().max()
     # (2) the last 12 chains alone, against the oracle
     k = 12
     n_tail = sum(sizes[-k:])
