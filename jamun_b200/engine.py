@@ -28,6 +28,17 @@ BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
 # instructions of the tf32 form at the same 11-bit significands; weights pre-scaled into the fp16 range when the plan is built,
 # operand overflow reported through Topology.gemm_status); "tf32" = jamun_gemm_tf32x3.  Read when a plan is built.
 GEMM_KIND = os.environ.get("JAMUN_B200_GEMM", "f16")
+
+
+def fall_back_to_tf32(what: str) -> None:
+    """An activation left the fp16 range in the fp16-split GEMMs: switch this process to the tf32-split kernels (fp32 range,
+    same accuracy, ~1.4x slower contraction) so the caller can redo the call.  Still this library's tensor-core kernels --
+    not a CPU or library fallback."""
+    import warnings
+
+    warnings.warn(f"jamun_b200: an activation exceeded the fp16 range (65504) during {what}; switching to the tf32-split "
+                  "tensor-core GEMMs (JAMUN_B200_GEMM=tf32) and repeating the call", RuntimeWarning, stacklevel=3)
+    os.environ["JAMUN_B200_GEMM"] = "tf32"
 # layout of the conv operand between the tensor-core builder and the fp16-split contraction: "tile" = [row/128][stage][128][32]
 # (a tile's stages contiguous), "stage" = [stage][rows_pad][32] (the layout of every other user of the GEMM).  Read at call time.
 A_LAYOUT = os.environ.get("JAMUN_B200_A_LAYOUT", "tile")
@@ -125,6 +136,13 @@ class Topology:
             self.gemm_status.zero_()
             raise FloatingPointError("jamun_b200: an activation exceeded the fp16 range (65504) in the fp16-split tensor-core GEMM; "
                                      "results of this call are invalid -- set JAMUN_B200_GEMM=tf32 and rebuild the plan")
+
+    def overflowed(self) -> bool:
+        """Host sync: True (and the flag is cleared) if an fp16-split GEMM reported an operand outside the fp16 range."""
+        if int(self.gemm_status.item()) == 0:
+            return False
+        self.gemm_status.zero_()
+        return True
 
     def build_csr(self, pos: torch.Tensor, r_cut: float):
         """K1 on (mean-centred, unscaled) positions; r2 = float(double(r)*double(r)) as torch_cluster does."""

@@ -77,7 +77,9 @@ class E3Conv(torch.nn.Module):
         plan = self.plan(float(torch.as_tensor(c_noise).reshape(-1)[0]), pos.device)
         g = torch.empty_like(pos)
         engine.e3conv_forward(plan, topo, pos.contiguous(), float(effective_radial_cutoff), g)
-        if plan.gemm_kind == "f16" and not torch.cuda.is_current_stream_capturing():
-            topo.check_status()
+        if plan.gemm_kind == "f16" and not torch.cuda.is_current_stream_capturing() and topo.overflowed():
+            engine.fall_back_to_tf32("E3Conv.forward")
+            plan = self.plan(float(torch.as_tensor(c_noise).reshape(-1)[0]), pos.device)
+            engine.e3conv_forward(plan, topo, pos.contiguous(), float(effective_radial_cutoff), g)
         data["pos"] = g
         return data

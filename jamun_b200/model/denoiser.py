@@ -159,8 +159,9 @@ class Denoiser(_Base):
                               seed=0, step=0)
         v_dummy = torch.zeros_like(y)
         ops.walk_step(y, v_dummy, ybar, p, g, topo.chain_ptr, prm, None, xhat, score)
-        if plan.gemm_kind == "f16" and not torch.cuda.is_current_stream_capturing():
-            topo.check_status()
+        if plan.gemm_kind == "f16" and not torch.cuda.is_current_stream_capturing() and topo.overflowed():
+            engine.fall_back_to_tf32("a denoiser evaluation")
+            return self.denoise_positions(y, topo, sigma, want_score)
         return xhat, score
 
     # ------------------------------------------------------------------ reference API

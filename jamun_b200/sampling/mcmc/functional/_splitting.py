@@ -246,8 +246,12 @@ def fused_baoab(model, topo: "engine.Topology", y: torch.Tensor, sigma: float, s
                 ops._count(ws.graph_launches[(gkey, i in slot)])
         if steps > 1:
             eager_step(steps - 1)
-    if plan.gemm_kind == "f16":
-        topo.check_status()  # 4-byte read-back: the fp16-split GEMMs report operands outside the fp16 range here
+    if plan.gemm_kind == "f16" and topo.overflowed():  # 4-byte read-back of the fp16-split GEMMs' range flag
+        engine.fall_back_to_tf32("the walk")
+        return fused_baoab(model, topo, y, sigma, steps, v_init=v_init, save_trajectory=save_trajectory,
+                           save_every_n_steps=save_every_n_steps, burn_in_steps=burn_in_steps, verbose=verbose, cpu_offload=cpu_offload,
+                           delta=delta, friction=friction, M=M, inverse_temperature=inverse_temperature, score_fn_clip=score_fn_clip,
+                           noise=noise, use_cuda_graph=use_cuda_graph)
     out_y, out_v, out_x = ws.y.clone(), ws.v.clone(), ws.xhat.clone()
     y_traj = ws.y_traj.clone() if ws.y_traj is not None else None
     xhat_traj = ws.xhat_traj.clone() if ws.xhat_traj is not None else None

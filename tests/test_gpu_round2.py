@@ -175,3 +175,43 @@ def test_sampling_launchers_are_torch_library_operators(models):
         w = torch.empty(9, 64, device="cuda")
         out = T.linear_act(torch.empty(5, 64, device="cuda"), w, torch.empty(9, device="cuda"), 1)
         assert out.shape == (5, 9)
+
+
+def test_fp16_range_overflow_falls_back_to_tf32_kernels(monkeypatch):
+    """Activations beyond the fp16 range (here: an atom embedding scaled by 3e5) raise the fp16-split GEMMs' status bit; the
+    call is repeated on the tf32-split kernels with a warning, and equals a run that used them from the start."""
+    import copy
+    import warnings
+
+    import jamun_b200 as J
+    from jamun_b200 import data, synthetic
+
+    monkeypatch.setenv("JAMUN_B200_GEMM", "f16")  # restored on teardown (the fallback rewrites the variable)
+    torch.manual_seed(3)
+    m = J.default_denoiser()
+    with torch.no_grad():
+        m.arch_module.output_gain.fill_(1.0)
+        for p in m.arch_module.atom_embedder.parameters():
+            p.mul_(3.0e5)
+    m = m.cuda().eval()
+    t = synthetic.make_tensors([22, 15, 9, 30])
+    gen = torch.Generator().manual_seed(2)
+    y = (t["pos"] + 0.04 * torch.randn(t["pos"].shape, generator=gen)).cuda()
+
+    def run():
+        yb = data.Batch.from_tensors(t).to("cuda")
+        yb.pos = y.clone()
+        return m.xhat(yb, 0.04).pos.cpu()
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        x = run()
+    assert any("fp16 range" in str(i.message) for i in w), [str(i.message) for i in w]
+    import os
+    assert os.environ["JAMUN_B200_GEMM"] == "tf32"
+    assert torch.isfinite(x).all()
+    with warnings.catch_warnings(record=True) as w2:
+        warnings.simplefilter("always")
+        x_tf32 = run()
+    assert not any("fp16 range" in str(i.message) for i in w2)
+    assert torch.equal(x, x_tf32)
