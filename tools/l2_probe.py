@@ -54,9 +54,12 @@ def probe(rows):
     part = torch.empty(ks * rows * 248, device=dev)
     a_ptrs = [base] + [base + 4 * (a1_off + c * comp) for c in range(3)]
     b_ptrs = [blk["b0_img"].data_ptr()] + [blk["b1_img"].data_ptr()] * 3
-    args = (a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216], [1.0] * 4, rows, rp,
-            inv.data_ptr(), out.data_ptr(), 248)
-    if ks > 1:
+    kind, sc = blk["gemm_kind"], blk["f16_scales"]
+    args = (a_ptrs, b_ptrs, [st0, st1, st1, st1], [160, 32, 32, 32], [152, 32, 32, 32], [0, 152, 184, 216],
+            [1.0 / sc[0]] + [1.0 / sc[1]] * 3, rows, rp, inv.data_ptr(), out.data_ptr(), 248)
+    if kind == "f16":
+        tg = timeit(lambda: ops.gemm_f16x3(*args, k_splits=ks, partial=part if ks > 1 else None))
+    elif ks > 1:
         tg = timeit(lambda: ops.gemm_tf32x3_splitk(*args, ks, part))
     else:
         tg = timeit(lambda: ops.gemm_tf32x3(*args))
