@@ -553,9 +553,8 @@ extern "C" int jamun_gemm_f16x3_fused(int nseg, const float* const* a, const flo
                      "mode 2: block-tail segments");
     }
     JB_CHECK_ARG(epi->op_rows_pad % 8 == 0 && (((size_t)epi->op_s | (size_t)epi->op_v) & 127) == 0, "operand buffers must be 128-byte aligned");
-    float dummy;
     return gemm_launch(true, nseg, a, b, n_stages, n_pad, n_valid, out_col, alpha, addend, addend_ld, 1, 0, rows, rows_pad, row_scale,
-                       &dummy, 0, 1, nullptr, status, addend_scale, a_tile_major, epi, stream);
+                       nullptr, 0, 1, nullptr, status, addend_scale, a_tile_major, epi, stream);
 }
 
 template <bool F16>
@@ -601,7 +600,8 @@ static int gemm_launch(bool f16, int nseg, const float* const* a, const float* c
                        const int* addend_ld, int col_blocks, long long b_block_floats, int rows, int rows_pad,
                        const float* row_scale, float* out, int out_ld, int k_splits, float* partial, int* status,
                        const float* addend_scale, int a_tile_major, const jamun_gemm_epilogue* epi, jamun_stream_t stream) {
-    JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && out, "bad argument");
+    JB_CHECK_ARG(nseg >= 1 && nseg <= 4 && a && b && n_stages && n_pad && n_valid && out_col && alpha && (out || (epi && epi->mode != 0)),
+                 "bad argument");
     JB_CHECK_ARG(rows_pad % 128 == 0 && rows <= rows_pad, "rows_pad must be a multiple of 128");
     if (rows == 0) return JAMUN_OK;
     Params P{};
