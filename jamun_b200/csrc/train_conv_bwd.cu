@@ -212,29 +212,41 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
             }
             sdf[tid] = acc;
         }
-        // dh: warp per channel, four edges at once
-        for (int k = warp; k < 64; k += 12) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int u = lane; u < W0; u += 32) {
-                const float a = sA0[k * W0 + u];
-                const float4 f = sf[u];
-                jb::ffma2(acc.x, acc.y, a, f.x, f.y);
-                jb::ffma2(acc.z, acc.w, a, f.z, f.w);
-            }
-            if (V_IN > 0)
+        // dh: a warp takes eight channels at a time, four edges at once -- the edge features (float4 per lane: four shared-memory
+        // wavefronts per load) are read once per eight channels instead of once per channel
+        if (warp < 8) {
+            const int k0 = warp * 8;
+            float4 acc[8];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float* A = sA1 + (c * 65 + k) * W1;
+            for (int c = 0; c < 8; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = lane; u < W0; u += 32) {
+                const float4 f = sf[u];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float a = sA0[(k0 + c) * W0 + u];
+                    jb::ffma2(acc[c].x, acc[c].y, a, f.x, f.y);
+                    jb::ffma2(acc[c].z, acc[c].w, a, f.z, f.w);
+                }
+            }
+            if (V_IN > 0) {
+#pragma unroll
+                for (int c3 = 0; c3 < 3; ++c3)
 #pragma unroll
                     for (int hv = 0; hv < 2; ++hv) {
-                        const float a = A[32 * hv + lane];
-                        const float4 f = sf[W0 + c * 64 + 32 * hv + lane];
-                        jb::ffma2(acc.x, acc.y, a, f.x, f.y);
-                        jb::ffma2(acc.z, acc.w, a, f.z, f.w);
+                        const float4 f = sf[W0 + c3 * 64 + 32 * hv + lane];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float a = sA1[(c3 * 65 + k0 + c) * W1 + 32 * hv + lane];
+                            jb::ffma2(acc[c].x, acc[c].y, a, f.x, f.y);
+                            jb::ffma2(acc[c].z, acc[c].w, a, f.z, f.w);
+                        }
                     }
-                }
-            acc.x = warp_sum(acc.x), acc.y = warp_sum(acc.y), acc.z = warp_sum(acc.z), acc.w = warp_sum(acc.w);
-            if (lane < nb) dh[(size_t)(eb + lane) * JAMUN_EDGE_HID + k] = lane == 0 ? acc.x : lane == 1 ? acc.y : lane == 2 ? acc.z : acc.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float sx = warp_sum(acc[c].x), sy = warp_sum(acc[c].y), sz = warp_sum(acc[c].z), sw = warp_sum(acc[c].w);
+                if (lane < nb) dh[(size_t)(eb + lane) * JAMUN_EDGE_HID + k0 + c] = lane == 0 ? sx : lane == 1 ? sy : lane == 2 ? sz : sw;
+            }
         }
         __syncthreads();
         // dxe = J^T df
