@@ -8,15 +8,22 @@ scatter-mean, brute-force capped radius graph, Python Langevin loop).  Only
 ``--impl reference`` legs may import it.  The product (``jamun_b200``) never
 does; it fails loudly when its CUDA library is missing.
 
-PARITY STATUS: **parity unpinned**.  The reference (prescient-design/jamun)
-ships no tests, golden vectors or fixtures for this path, and it cannot be
-imported here: its arithmetic lives in un-vendored third-party packages that
-are not installed and not installable offline --
-e3nn==0.5.4, torch-cluster==1.6.3, torch-scatter==2.1.2, torch-geometric==2.6.1,
-lightning==2.4.0 (pins: /root/reference/env/requirements.txt, pyproject.toml).
-Their published algorithms are restated below and anchored on the reference's
-call sites; analytic known-answer tests and fp64 self-consistency/equivariance
-properties (tests/test_oracle.py) are the substitute pin.
+PARITY STATUS: **pinned to executed reference code around the network; parity unpinned inside it**.
+The reference (prescient-design/jamun) ships no tests, golden vectors or fixtures for this path, and
+it cannot be imported as a package here: its arithmetic lives in un-vendored third-party packages
+that are not installed and not installable offline -- e3nn==0.5.4, torch-cluster==1.6.3,
+torch-scatter==2.1.2, torch-geometric==2.6.1, lightning==2.4.0 (pins:
+/root/reference/env/requirements.txt, pyproject.toml).
+ * Pinned: every function below that restates a plain-torch reference file (Denoiser wrapper,
+   normalisation, centring, baoab / aboba, walk_jump, Kabsch, loss, noise MLPs, atom embedding) is
+   checked against tests/golden/reference_exec.npz, which tests/golden/make_reference_golden.py
+   produced by loading those reference files from /root/reference and running them
+   (tests/test_reference_pins.py).
+ * Unpinned: the e3nn arithmetic (wigner_3j, FullyConnectedTensorProduct, o3.Linear, Gate,
+   spherical harmonics, radial basis) and torch_cluster's radius graph.  Their published algorithms
+   are restated below and anchored on the reference's call sites; analytic known-answer tests, a
+   sympy replay of e3nn's wigner_3j recipe and fp64 equivariance properties (tests/test_oracle.py)
+   are the substitute pin.
 
 Reference call sites followed (paths relative to /root/reference/src/jamun):
   model/denoiser.py:111-217        score, normalization_factors, add_edges, xhat
