@@ -11,7 +11,11 @@
 //             dx_j   = sum_{e from j} J_e^T df_e  (+ dx_s)  -- source-major, out-edge lists sorted: deterministic
 //                                                                                  jamun_conv_bwd_gather
 // Every reduction has a fixed order; no atomics.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace {
 using namespace jb;
@@ -272,6 +276,256 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
     }
 }
 
+// ---- the same per-edge backward on the warp-level tensor cores (default) ---------------------------------------------------------
+// Per receiver both products are small dense GEMMs over the staged dA_i [65][NFC] (NFC = compact feature columns: scalars, v.rhat,
+// then per component v/sqrt3 and the cross product):
+//   product 1   dF^T [NFC x edges]  = dA_i^T [NFC x 64] . H^T [64 x edges]   (+ the bias row dA_i[64][:])
+//   product 2   dH^T [64 x edges]   = dA_i   [64 x NFC] . F^T [NFC x edges]
+// with the edges as the N dimension of mma.sync.m16n8k8 (tf32 operands, fp32 accumulate), so in-degrees are padded to a multiple
+// of 8 only.  fp32 accuracy comes from the same three-product split as the forward kernels (hi = rna_tf32(v), lo = rna_tf32(v-hi);
+// lo.hi + hi.lo + hi.hi), done in registers as the fragments are loaded.  tcgen05 is the wrong tool here: its M is 64/128 rows, a
+// receiver has <= 35 edges, and 2 x 91 KB of pre-split dA_i would not fit next to the operands -- measured on the aggregate
+// builder, small SS-mode tcgen05 products retire at ~300 clk each, more than a warp-level m16n8k8 triple per tile costs here.
+// One persistent CTA per SM (16 warps); per batch of <= 32 in-edges the 16 + ceil(NFC/16) tile tasks are dealt round-robin to the
+// warps (product 2 split in four K slices whose partial tiles are summed in slice order: deterministic).  Shared-memory strides
+// are chosen so that every fragment load but the product-2 A load (2-way) is conflict-free: LDA = NFC (24 mod 32), LDF = NFC + 4
+// (28 mod 32), LDH = 68.
+// hi = the tf32 the tensor core reads anyway (it ignores the low 13 mantissa bits), lo = the exact remainder (its own low bits are
+// ignored in turn: 2^-20 relative).  cvt.rna.tf32 would cost four instructions per value on this architecture; this is two.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int S_IN, int V_IN>
+struct EdgeMmaCfg {
+    static constexpr int D_IN = S_IN + 3 * V_IN;
+    static constexpr int NS32 = ((S_IN + 31) / 32) * 32;
+    static constexpr int W0 = NS32 + (V_IN > 0 ? 32 : 0);   // row length of dA0 in global memory (padded scalars + v.rhat)
+    static constexpr int NFC = S_IN + V_IN + 6 * V_IN;      // compact feature columns
+    static constexpr int LDA = NFC, LDF = NFC + 4, LDH = 68;
+    static constexpr int NB = 32;                           // in-edges per batch (four n-tiles)
+    static constexpr int LDP = NB + 1;                      // partial-tile rows (odd: the channel-major read-back is conflict-free)
+    static constexpr int MT1 = (NFC + 15) / 16;             // product 1: m-tiles over the features
+    static constexpr int KS2 = NFC / 8;                     // product 2: k-steps over the features
+    static constexpr int NSL = 4;                           // ... in four slices
+    static constexpr int kThreads = 512;
+    static constexpr size_t kSmemFloats = (size_t)65 * LDA + 8 + 2 * NB * LDF + NB * LDH + NSL * 64 * LDP + 4 * NB + 4;  // + mbarrier
+    static_assert(S_IN % 4 == 0 && V_IN % 4 == 0 && NFC % 8 == 0, "16-byte staging chunks / whole k-steps");
+    static_assert(LDA % 32 == 24 || LDA % 32 == 8, "conflict-free product-1 A fragments");
+    static_assert(LDF % 32 == 28 || LDF % 32 == 4, "conflict-free B fragments");
+    static_assert((65 * LDA + 8 + 2 * NB * LDF + NB * LDH + NSL * 64 * LDP) % 4 == 0, "float4 alignment of the rhat slots");
+};
+
+// The tile tasks of one batch with NTILES n-tiles of 8 edges: 0..15 = product 2 (m-tile, K slice), 16.. = product 1 m-tiles.
+template <int S_IN, int V_IN, int NTILES>
+__device__ __forceinline__ void edge_mma_tasks(const float* __restrict__ sA, const float* __restrict__ sF, const float* __restrict__ sH,
+                                               float* __restrict__ sDF, float* __restrict__ sP, int warp, int g, int tig) {
+    using C = EdgeMmaCfg<S_IN, V_IN>;
+    constexpr int NFC = C::NFC, LDA = C::LDA, LDF = C::LDF, LDH = C::LDH, LDP = C::LDP;
+    for (int task = warp; task < 16 + C::MT1; task += C::kThreads / 32) {
+        float acc[NTILES][4];
+#pragma unroll
+        for (int nt = 0; nt < NTILES; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
+        if (task < 16) {
+            const int mt = task & 3, sl = task >> 2;
+            const int ks0 = sl * C::KS2 / C::NSL, ks1 = (sl + 1) * C::KS2 / C::NSL;
+            const float* Ar = sA + (16 * mt + g) * LDA + tig;
+            const float* Br = sF + g * LDF + tig;
+#pragma unroll 2
+            for (int ks = ks0; ks < ks1; ++ks) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(Ar[8 * ks], ahi[0], alo[0]);
+                split_tf32(Ar[8 * ks + 8 * LDA], ahi[1], alo[1]);
+                split_tf32(Ar[8 * ks + 4], ahi[2], alo[2]);
+                split_tf32(Ar[8 * ks + 8 * LDA + 4], ahi[3], alo[3]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(Br[8 * nt * LDF + 8 * ks], bh0, bl0);
+                    split_tf32(Br[8 * nt * LDF + 8 * ks + 4], bh1, bl1);
+                    mma_tf32(acc[nt], alo, bh0, bh1);
+                    mma_tf32(acc[nt], ahi, bl0, bl1);
+                    mma_tf32(acc[nt], ahi, bh0, bh1);
+                }
+            }
+            float* P = sP + (sl * 64 + 16 * mt + g) * LDP + 2 * tig;
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt) {
+                P[8 * nt] = acc[nt][0], P[8 * nt + 1] = acc[nt][1];
+                P[8 * LDP + 8 * nt] = acc[nt][2], P[8 * LDP + 8 * nt + 1] = acc[nt][3];
+            }
+        } else {
+            const int f0 = 16 * (task - 16);
+            const float* Ar = sA + tig * LDA + f0 + g;  // A[row = feature][col = channel] = dA[channel][feature]
+            const float* Br = sH + g * LDH + tig;
+#pragma unroll 2
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(Ar[8 * ks * LDA], ahi[0], alo[0]);
+                split_tf32(Ar[8 * ks * LDA + 8], ahi[1], alo[1]);
+                split_tf32(Ar[(8 * ks + 4) * LDA], ahi[2], alo[2]);
+                split_tf32(Ar[(8 * ks + 4) * LDA + 8], ahi[3], alo[3]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) {
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(Br[8 * nt * LDH + 8 * ks], bh0, bl0);
+                    split_tf32(Br[8 * nt * LDH + 8 * ks + 4], bh1, bl1);
+                    mma_tf32(acc[nt], alo, bh0, bh1);
+                    mma_tf32(acc[nt], ahi, bl0, bl1);
+                    mma_tf32(acc[nt], ahi, bh0, bh1);
+                }
+            }
+            // + bias channel (h' = 1), transposed into sDF[edge][feature]
+            const int fa = f0 + g, fb = f0 + g + 8;
+            const float ba = fa < NFC ? sA[64 * LDA + fa] : 0.f, bb = fb < NFC ? sA[64 * LDA + fb] : 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt) {
+                float* D = sDF + (8 * nt + 2 * tig) * LDF;
+                if (fa < NFC) D[fa] = acc[nt][0] + ba, D[LDF + fa] = acc[nt][1] + ba;
+                if (fb < NFC) D[fb] = acc[nt][2] + bb, D[LDF + fb] = acc[nt][3] + bb;
+            }
+        }
+    }
+}
+
+template <int S_IN, int V_IN>
+__global__ void __launch_bounds__(512, 1)
+conv_bwd_edge_mma_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
+                         const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ dA0, int ld0,
+                         const float* __restrict__ dA1, int ld1, long long dA1_comp_stride, int N, float* __restrict__ dh,
+                         float* __restrict__ dxe) {
+    using C = EdgeMmaCfg<S_IN, V_IN>;
+    constexpr int D_IN = C::D_IN, NFC = C::NFC, LDA = C::LDA, LDF = C::LDF, LDH = C::LDH, LDP = C::LDP, NB = C::NB, NW = C::kThreads / 32;
+    constexpr int B1 = S_IN + V_IN;  // first per-component column
+    extern __shared__ __align__(16) float sm[];
+    float* sA = sm;                       // [65][LDA] (+8 floats: the last partial m-tile reads past row 64's end)
+    float* sF = sA + 65 * LDA + 8;        // [NB][LDF] edge features
+    float* sDF = sF + NB * LDF;           // [NB][LDF] their gradients
+    float* sH = sDF + NB * LDF;           // [NB][LDH] radial hidden channels
+    float* sP = sH + NB * LDH;            // [NSL][64][LDP] product-2 partial tiles
+    float4* srh = reinterpret_cast<float4*>(sP + C::NSL * 64 * LDP);  // [NB]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(srh + NB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
+    static_assert(NB == 2 * NW, "the gather takes two edges per warp");
+    if (tid == 0) {
+        umma::mbar_init(bar, 1);
+        umma::fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (int i = blockIdx.x; i < N; i += gridDim.x) {
+        const int e0 = rowptr[i], e1 = rowptr[i + 1];
+        if (e0 == e1) continue;
+        // stage dA_i (compacted) with 1-D bulk async copies, one contiguous piece per thread: per channel row the scalars, the
+        // v.rhat columns and the three components (the previous receiver's last barrier ordered all reads of sA before this)
+        {
+            constexpr int PIECES = V_IN > 0 ? 5 : 1;
+            if (tid == 0) umma::mbar_arrive_expect_tx(bar, 65 * NFC * (uint32_t)sizeof(float));
+            if (tid < 65 * PIECES) {
+                const int k = tid / PIECES, pc = tid - k * PIECES;
+                const float* a0 = dA0 + (size_t)i * ld0 + k * C::W0;
+                float* dst = sA + k * LDA;
+                if (pc == 0) umma::bulk_g2s(dst, a0, S_IN * sizeof(float), bar);
+                else if (pc == 1) umma::bulk_g2s(dst + S_IN, a0 + C::NS32, V_IN * sizeof(float), bar);
+                else
+                    umma::bulk_g2s(dst + B1 + (pc - 2) * 2 * V_IN, dA1 + (size_t)(pc - 2) * dA1_comp_stride + (size_t)i * ld1 + k * 2 * V_IN,
+                                   2 * V_IN * sizeof(float), bar);
+            }
+        }
+        for (int eb = e0; eb < e1; eb += NB) {
+            const int nb = e1 - eb < NB ? e1 - eb : NB;
+            const int ntiles = (nb + 7) >> 3, npad = ntiles * 8;
+            // ---- features, hidden channels, rhat of the batch: a warp per edge, two edges per warp with all their loads issued
+            //      before the first use (rows nb..npad-1 zero)
+            {
+                constexpr int NSC = (S_IN + 31) / 32;
+                float xs[2][NSC], xv[2][3], hh[2][2];
+                float4 rh[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = warp + NW * u;
+                    const bool on = q < nb;
+                    const float* xr = x + (size_t)(on ? col[eb + q] : 0) * D_IN;
+#pragma unroll
+                    for (int m = 0; m < NSC; ++m) xs[u][m] = (on && 32 * m + lane < S_IN) ? xr[32 * m + lane] : 0.f;
+                    if (V_IN > 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) xv[u][c] = on ? xr[S_IN + c * V_IN + lane] : 0.f;
+                        rh[u] = on ? *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(eb + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    hh[u][0] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + lane] : 0.f;
+                    hh[u][1] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + 32 + lane] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = warp + NW * u;
+                    if (q >= npad) break;
+                    float* f = sF + q * LDF;
+#pragma unroll
+                    for (int m = 0; m < NSC; ++m)
+                        if (32 * m + lane < S_IN) f[32 * m + lane] = xs[u][m];
+                    sH[q * LDH + lane] = hh[u][0], sH[q * LDH + 32 + lane] = hh[u][1];
+                    if (V_IN > 0) {
+                        const int w = lane;
+                        const float vx = xv[u][0], vy = xv[u][1], vz = xv[u][2];
+                        const float4 r = rh[u];
+                        f[S_IN + w] = vx * r.x + vy * r.y + vz * r.z;
+                        f[B1 + 0 * 2 * V_IN + w] = vx * kInvSqrt3;
+                        f[B1 + 1 * 2 * V_IN + w] = vy * kInvSqrt3;
+                        f[B1 + 2 * 2 * V_IN + w] = vz * kInvSqrt3;
+                        f[B1 + 0 * 2 * V_IN + V_IN + w] = (vy * r.z - vz * r.y) * kInvSqrt2;
+                        f[B1 + 1 * 2 * V_IN + V_IN + w] = (vz * r.x - vx * r.z) * kInvSqrt2;
+                        f[B1 + 2 * 2 * V_IN + V_IN + w] = (vx * r.y - vy * r.x) * kInvSqrt2;
+                        if (w == 0) srh[q] = r;
+                    }
+                }
+            }
+            if (eb == e0) umma::mbar_wait(bar, phase);
+            __syncthreads();
+            switch (ntiles) {
+                case 1: edge_mma_tasks<S_IN, V_IN, 1>(sA, sF, sH, sDF, sP, warp, g, tig); break;
+                case 2: edge_mma_tasks<S_IN, V_IN, 2>(sA, sF, sH, sDF, sP, warp, g, tig); break;
+                case 3: edge_mma_tasks<S_IN, V_IN, 3>(sA, sF, sH, sDF, sP, warp, g, tig); break;
+                default: edge_mma_tasks<S_IN, V_IN, 4>(sA, sF, sH, sDF, sP, warp, g, tig); break;
+            }
+            __syncthreads();
+            // ---- dh = sum of the four K slices (ascending), dxe = J^T df: a warp per edge
+            for (int q = warp; q < nb; q += NW) {
+                const float* d = sDF + q * LDF;
+                float* o = dxe + (size_t)(eb + q) * D_IN;
+#pragma unroll
+                for (int hv = 0; hv < 2; ++hv) {
+                    const float* P = sP + (32 * hv + lane) * LDP + q;
+                    dh[(size_t)(eb + q) * JAMUN_EDGE_HID + 32 * hv + lane] = ((P[0] + P[64 * LDP]) + P[2 * 64 * LDP]) + P[3 * 64 * LDP];
+                }
+                for (int c = lane; c < S_IN; c += 32) o[c] = d[c];
+                if (V_IN > 0) {
+                    const int w = lane;
+                    const float4 rh = srh[q];
+                    const float dd = d[S_IN + w];
+                    const float cx = d[B1 + 0 * 2 * V_IN + V_IN + w], cy = d[B1 + 1 * 2 * V_IN + V_IN + w],
+                                cz = d[B1 + 2 * 2 * V_IN + V_IN + w];
+                    // cross = x_v x rhat  =>  d x_v = rhat x d cross
+                    o[S_IN + w] = dd * rh.x + d[B1 + 0 * 2 * V_IN + w] * kInvSqrt3 + (rh.y * cz - rh.z * cy) * kInvSqrt2;
+                    o[S_IN + V_IN + w] = dd * rh.y + d[B1 + 1 * 2 * V_IN + w] * kInvSqrt3 + (rh.z * cx - rh.x * cz) * kInvSqrt2;
+                    o[S_IN + 2 * V_IN + w] = dd * rh.z + d[B1 + 2 * 2 * V_IN + w] * kInvSqrt3 + (rh.x * cy - rh.y * cx) * kInvSqrt2;
+                }
+            }
+            __syncthreads();  // sF / sH / sDF / sP (and, after the last batch, sA) are free again
+        }
+        phase ^= 1;
+    }
+}
+
 // ---- path 0e(x)1e->1e, source-major ---------------------------------------------------------------------------------------------
 // One warp per source j (lane = output channel w): Y_j [65][32] in registers; for every out-edge e (receiver i):
 //   dT[w] = sum_c rhat_e[c] G1_i[c][w];  dY[k'][w] += h'_e[k'] dT[w];  dh_e[k'] += sum_w Y[k'][w] dT[w]   (k' < 64)
@@ -362,6 +616,34 @@ int launch_edge(const float* x, const int* rowptr, const int* col, const float* 
     return JAMUN_OK;
 }
 
+template <int S_IN, int V_IN>
+int launch_edge_mma(const float* x, const int* rowptr, const int* col, const float* h, const float* rhat, const float* dA0, int ld0,
+                    const float* dA1, int ld1, long long comp, int N, float* dh, float* dxe, cudaStream_t s) {
+    using C = EdgeMmaCfg<S_IN, V_IN>;
+    constexpr size_t smem = C::kSmemFloats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_bwd_edge_mma_kernel<S_IN, V_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            jb::set_error("jamun_conv_bwd_edge: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return JAMUN_ECUDA;
+        }
+        attr_set = true;
+    }
+    const int grid = N < jb::kNumSMs ? N : jb::kNumSMs;
+    conv_bwd_edge_mma_kernel<S_IN, V_IN><<<grid, C::kThreads, smem, s>>>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, comp, N, dh, dxe);
+    return JAMUN_OK;
+}
+
+// JAMUN_B200_BWD_EDGE=simt selects the CUDA-core kernel (A/B reference); default: warp-level tensor cores
+bool edge_use_mma() {
+    static const bool v = [] {
+        const char* e = getenv("JAMUN_B200_BWD_EDGE");
+        return !(e && strcmp(e, "simt") == 0);
+    }();
+    return v;
+}
+
 }  // namespace
 
 extern "C" int jamun_conv_bwd_scale(const float* dout, const float* inv_deg, float alpha0, float alpha1, int N, float* g,
@@ -402,9 +684,13 @@ extern "C" int jamun_conv_bwd_edge(const float* x, int s_in, int v_in, const int
     int rc;
     if (s_in == JAMUN_S && v_in == JAMUN_V) {
         JB_CHECK_ARG(dA1, "dA1 required for vector inputs");
-        rc = launch_edge<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, dA1_comp_stride, N, dh, dxe, s);
+        JB_CHECK_ARG(ld0 % 4 == 0 && ld1 % 4 == 0 && dA1_comp_stride % 4 == 0, "dA rows must be 16-byte aligned");
+        rc = edge_use_mma() ? launch_edge_mma<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, dA1_comp_stride, N, dh, dxe, s)
+                            : launch_edge<JAMUN_S, JAMUN_V>(x, rowptr, col, h, rhat, dA0, ld0, dA1, ld1, dA1_comp_stride, N, dh, dxe, s);
     } else if (s_in == JAMUN_S0 && v_in == 0) {
-        rc = launch_edge<JAMUN_S0, 0>(x, rowptr, col, h, rhat, dA0, ld0, nullptr, 0, 0, N, dh, dxe, s);
+        JB_CHECK_ARG(ld0 % 4 == 0, "dA rows must be 16-byte aligned");
+        rc = edge_use_mma() ? launch_edge_mma<JAMUN_S0, 0>(x, rowptr, col, h, rhat, dA0, ld0, nullptr, 0, 0, N, dh, dxe, s)
+                            : launch_edge<JAMUN_S0, 0>(x, rowptr, col, h, rhat, dA0, ld0, nullptr, 0, 0, N, dh, dxe, s);
     } else {
         jb::set_error("jamun_conv_bwd_edge: unsupported input irreps %dx0e+%dx1e", s_in, v_in);
         return JAMUN_EINVAL;
