@@ -62,29 +62,55 @@ rowmat_mul_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
 }
 
 // ---- dW = X^T . dY over a chunk of rows -------------------------------------------------------------------------------------
-// grid (ceil(a/16), ceil(b/16), splits): thread (ty, tx) owns dW[k0+ty][j0+tx] for rows [chunk z); partial[z][a][b].
+// grid (splits): a CTA reduces its chunk of rows into the whole a x b product (a, b <= 128), 32 rows at a time through shared
+// memory; thread (ty, tx) of the 16 x 16 block owns the 8 x 8 register tile dW[ty + 16 i][tx + 16 j], so X and dY are read from
+// global memory exactly once and every pair of shared-memory loads feeds eight FMAs.  partial[z][a][b], summed in split order by
+// rowmat_dw_reduce_kernel (deterministic).  RI / RJ = register-tile extents actually needed (ceil(a/16), ceil(b/16)).
+template <int RI, int RJ>
 __global__ void __launch_bounds__(256)
 rowmat_dw_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, float* __restrict__ partial, int rows,
                  const int* __restrict__ rows_dev, int a, int b, int rows_per_split) {
-    __shared__ float Xs[64][17], Ys[64][17];
+    constexpr int RB = 32;
+    __shared__ float Xs[RB][16 * RI + 1], Ys[RB][16 * RJ + 1];
     if (rows_dev) rows = min(rows, *rows_dev);
-    const int k0 = blockIdx.x * 16, j0 = blockIdx.y * 16;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const int n_begin = blockIdx.z * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
-    float acc = 0.f;
-    for (int n0 = n_begin; n0 < n_end; n0 += 64) {
-        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
-            const int rr = t >> 4, cc = t & 15;
-            const bool ok = n0 + rr < n_end;
-            Xs[rr][cc] = (ok && k0 + cc < a) ? X[(size_t)(n0 + rr) * ldx + k0 + cc] : 0.f;
-            Ys[rr][cc] = (ok && j0 + cc < b) ? dY[(size_t)(n0 + rr) * ldy + j0 + cc] : 0.f;
+    const int n_begin = blockIdx.x * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
+    float acc[RI][RJ];
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < RJ; ++j) acc[i][j] = 0.f;
+    for (int n0 = n_begin; n0 < n_end; n0 += RB) {
+        for (int t = threadIdx.x; t < RB * 16 * RI; t += 256) {
+            const int rr = t / (16 * RI), cc = t - rr * (16 * RI);
+            Xs[rr][cc] = (n0 + rr < n_end && cc < a) ? X[(size_t)(n0 + rr) * ldx + cc] : 0.f;
+        }
+        for (int t = threadIdx.x; t < RB * 16 * RJ; t += 256) {
+            const int rr = t / (16 * RJ), cc = t - rr * (16 * RJ);
+            Ys[rr][cc] = (n0 + rr < n_end && cc < b) ? dY[(size_t)(n0 + rr) * ldy + cc] : 0.f;
         }
         __syncthreads();
-#pragma unroll 16
-        for (int rr = 0; rr < 64; ++rr) acc = fmaf(Xs[rr][ty], Ys[rr][tx], acc);
+#pragma unroll 4
+        for (int rr = 0; rr < RB; ++rr) {
+            float xv[RI], yv[RJ];
+#pragma unroll
+            for (int i = 0; i < RI; ++i) xv[i] = Xs[rr][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < RJ; ++j) yv[j] = Ys[rr][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < RI; ++i)
+#pragma unroll
+                for (int j = 0; j < RJ; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+        }
         __syncthreads();
     }
-    if (k0 + ty < a && j0 + tx < b) partial[((size_t)blockIdx.z * a + k0 + ty) * b + j0 + tx] = acc;
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < RJ; ++j) {
+            const int k = ty + 16 * i, c = tx + 16 * j;
+            if (k < a && c < b) partial[((size_t)blockIdx.x * a + k) * b + c] = acc[i][j];
+        }
 }
 
 __global__ void rowmat_dw_reduce_kernel(const float* __restrict__ partial, int splits, int a, int b, float* __restrict__ dW, int lddw,
@@ -157,18 +183,28 @@ extern "C" int jamun_rowmat_mul(const float* X, int ldx, const float* W, int ldw
 }
 
 // scratch: >= jamun_rowmat_dw_scratch(rows, a, b) floats
-extern "C" long long jamun_rowmat_dw_scratch(int rows, int a, int b) { return (long long)pick_splits(rows, 2048, 128) * a * b; }
+inline int dw_splits(int rows) { return pick_splits(rows, 256, 2 * jb::kNumSMs); }
+
+extern "C" long long jamun_rowmat_dw_scratch(int rows, int a, int b) { return (long long)dw_splits(rows) * a * b; }
 
 extern "C" int jamun_rowmat_dw(const float* X, int ldx, const float* dY, int ldy, float* dW, int lddw, int transW, int rows,
                                const int* rows_dev, int a, int b, int accumulate, float* scratch, jamun_stream_t stream) {
     JB_CHECK_ARG(X && dY && dW && scratch, "null argument");
-    JB_CHECK_ARG(a >= 1 && b >= 1, "bad shape");
+    JB_CHECK_ARG(a >= 1 && b >= 1 && a <= 128 && b <= 128, "shape must be within 128 x 128");
     cudaStream_t s = jb::as_stream(stream);
-    const int splits = pick_splits(rows, 2048, 128);
-    const int per = rows > 0 ? (rows + splits - 1) / splits : 1;
-    if (rows > 0)
-        rowmat_dw_kernel<<<dim3((a + 15) / 16, (b + 15) / 16, splits), 256, 0, s>>>(X, ldx, dY, ldy, scratch, rows, rows_dev, a, b,
-                                                                                    per);
+    const int splits = dw_splits(rows);
+    const int per = rows > 0 ? ((rows + splits - 1) / splits + 31) / 32 * 32 : 32;
+    if (rows > 0) {
+        const int ri = (a + 15) / 16, rj = (b + 15) / 16;
+#define JB_DW(RI, RJ) rowmat_dw_kernel<RI, RJ><<<splits, 256, 0, s>>>(X, ldx, dY, ldy, scratch, rows, rows_dev, a, b, per)
+        if (ri <= 2 && rj <= 2) JB_DW(2, 2);
+        else if (ri <= 2 && rj <= 4) JB_DW(2, 4);
+        else if (ri <= 4 && rj <= 4) JB_DW(4, 4);
+        else if (ri <= 2) JB_DW(2, 8);
+        else if (rj <= 2) JB_DW(8, 2);
+        else JB_DW(8, 8);
+#undef JB_DW
+    }
     rowmat_dw_reduce_kernel<<<(a * b + 255) / 256, 256, 0, s>>>(scratch, rows > 0 ? splits : 0, a, b, dW, lddw, transW, accumulate);
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
