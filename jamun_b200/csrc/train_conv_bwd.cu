@@ -346,15 +346,19 @@ __device__ __forceinline__ void edge_mma_tasks(const float* __restrict__ sA, con
                 split_tf32(Ar[8 * ks + 8 * LDA], ahi[1], alo[1]);
                 split_tf32(Ar[8 * ks + 4], ahi[2], alo[2]);
                 split_tf32(Ar[8 * ks + 8 * LDA + 4], ahi[3], alo[3]);
+                uint32_t bh[NTILES][2], bl[NTILES][2];
 #pragma unroll
                 for (int nt = 0; nt < NTILES; ++nt) {
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(Br[8 * nt * LDF + 8 * ks], bh0, bl0);
-                    split_tf32(Br[8 * nt * LDF + 8 * ks + 4], bh1, bl1);
-                    mma_tf32(acc[nt], alo, bh0, bh1);
-                    mma_tf32(acc[nt], ahi, bl0, bl1);
-                    mma_tf32(acc[nt], ahi, bh0, bh1);
+                    split_tf32(Br[8 * nt * LDF + 8 * ks], bh[nt][0], bl[nt][0]);
+                    split_tf32(Br[8 * nt * LDF + 8 * ks + 4], bh[nt][1], bl[nt][1]);
                 }
+                // term by term across the n-tiles: consecutive MMAs never wait on each other's accumulator
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], alo, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bl[nt][0], bl[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bh[nt][0], bh[nt][1]);
             }
             float* P = sP + (sl * 64 + 16 * mt + g) * LDP + 2 * tig;
 #pragma unroll
@@ -373,15 +377,19 @@ __device__ __forceinline__ void edge_mma_tasks(const float* __restrict__ sA, con
                 split_tf32(Ar[8 * ks * LDA + 8], ahi[1], alo[1]);
                 split_tf32(Ar[(8 * ks + 4) * LDA], ahi[2], alo[2]);
                 split_tf32(Ar[(8 * ks + 4) * LDA + 8], ahi[3], alo[3]);
+                uint32_t bh[NTILES][2], bl[NTILES][2];
 #pragma unroll
                 for (int nt = 0; nt < NTILES; ++nt) {
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(Br[8 * nt * LDH + 8 * ks], bh0, bl0);
-                    split_tf32(Br[8 * nt * LDH + 8 * ks + 4], bh1, bl1);
-                    mma_tf32(acc[nt], alo, bh0, bh1);
-                    mma_tf32(acc[nt], ahi, bl0, bl1);
-                    mma_tf32(acc[nt], ahi, bh0, bh1);
+                    split_tf32(Br[8 * nt * LDH + 8 * ks], bh[nt][0], bl[nt][0]);
+                    split_tf32(Br[8 * nt * LDH + 8 * ks + 4], bh[nt][1], bl[nt][1]);
                 }
+                // term by term across the n-tiles: consecutive MMAs never wait on each other's accumulator
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], alo, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bl[nt][0], bl[nt][1]);
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bh[nt][0], bh[nt][1]);
             }
             // + bias channel (h' = 1), transposed into sDF[edge][feature]
             const int fa = f0 + g, fb = f0 + g + 8;
@@ -422,9 +430,43 @@ conv_bwd_edge_mma_kernel(const float* __restrict__ x, const int* __restrict__ ro
     __syncthreads();
     uint32_t phase = 0;
 
+    // raw gathers of one batch (two edges per warp), held in registers: the first batch of the NEXT receiver is loaded before the
+    // tile tasks of the current receiver's last batch, so its latency is covered by the tensor-core phase
+    constexpr int NSC = (S_IN + 31) / 32;
+    float xs[2][NSC], xv[2][3], hh[2][2];
+    float4 rh[2];
+    auto gather = [&](int eb, int e1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int q = warp + NW * u;
+            const bool on = eb + q < e1;
+            const float* xr = x + (size_t)(on ? col[eb + q] : 0) * D_IN;
+#pragma unroll
+            for (int m = 0; m < NSC; ++m) xs[u][m] = (on && 32 * m + lane < S_IN) ? xr[32 * m + lane] : 0.f;
+            if (V_IN > 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) xv[u][c] = on ? xr[S_IN + c * V_IN + lane] : 0.f;
+                rh[u] = on ? *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(eb + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            hh[u][0] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + lane] : 0.f;
+            hh[u][1] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + 32 + lane] : 0.f;
+        }
+    };
+    int e0 = 0, e1 = 0;
+    if ((int)blockIdx.x < N) {
+        e0 = rowptr[blockIdx.x], e1 = rowptr[blockIdx.x + 1];
+        gather(e0, e1);
+    }
     for (int i = blockIdx.x; i < N; i += gridDim.x) {
-        const int e0 = rowptr[i], e1 = rowptr[i + 1];
-        if (e0 == e1) continue;
+        // the next receiver's row extent (its gather is issued below); `continue` for an isolated node still advances to it
+        const int i_next = i + gridDim.x;
+        int e0n = 0, e1n = 0;
+        if (i_next < N) e0n = rowptr[i_next], e1n = rowptr[i_next + 1];
+        if (e0 == e1) {
+            e0 = e0n, e1 = e1n;
+            gather(e0, e1);
+            continue;
+        }
         // stage dA_i (compacted) with 1-D bulk async copies, one contiguous piece per thread: per channel row the scalars, the
         // v.rhat columns and the three components (the previous receiver's last barrier ordered all reads of sA before this)
         {
@@ -444,27 +486,9 @@ conv_bwd_edge_mma_kernel(const float* __restrict__ x, const int* __restrict__ ro
         for (int eb = e0; eb < e1; eb += NB) {
             const int nb = e1 - eb < NB ? e1 - eb : NB;
             const int ntiles = (nb + 7) >> 3, npad = ntiles * 8;
-            // ---- features, hidden channels, rhat of the batch: a warp per edge, two edges per warp with all their loads issued
-            //      before the first use (rows nb..npad-1 zero)
+            // ---- features, hidden channels, rhat of the batch from the gathered registers (rows nb..npad-1 zero)
+            if (eb != e0) gather(eb, e1);  // later batches of a high-degree receiver: loaded here
             {
-                constexpr int NSC = (S_IN + 31) / 32;
-                float xs[2][NSC], xv[2][3], hh[2][2];
-                float4 rh[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int q = warp + NW * u;
-                    const bool on = q < nb;
-                    const float* xr = x + (size_t)(on ? col[eb + q] : 0) * D_IN;
-#pragma unroll
-                    for (int m = 0; m < NSC; ++m) xs[u][m] = (on && 32 * m + lane < S_IN) ? xr[32 * m + lane] : 0.f;
-                    if (V_IN > 0) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) xv[u][c] = on ? xr[S_IN + c * V_IN + lane] : 0.f;
-                        rh[u] = on ? *reinterpret_cast<const float4*>(rhat + 4 * (size_t)(eb + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    hh[u][0] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + lane] : 0.f;
-                    hh[u][1] = on ? h[(size_t)(eb + q) * JAMUN_EDGE_HID + 32 + lane] : 0.f;
-                }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int q = warp + NW * u;
@@ -491,6 +515,7 @@ conv_bwd_edge_mma_kernel(const float* __restrict__ x, const int* __restrict__ ro
             }
             if (eb == e0) umma::mbar_wait(bar, phase);
             __syncthreads();
+            if (eb + NB >= e1) gather(e0n, e1n);  // registers are free again: the next receiver's first batch flies under the MMAs
             switch (ntiles) {
                 case 1: edge_mma_tasks<S_IN, V_IN, 1>(sA, sF, sH, sDF, sP, warp, g, tig); break;
                 case 2: edge_mma_tasks<S_IN, V_IN, 2>(sA, sF, sH, sDF, sP, warp, g, tig); break;
@@ -523,6 +548,7 @@ conv_bwd_edge_mma_kernel(const float* __restrict__ x, const int* __restrict__ ro
             __syncthreads();  // sF / sH / sDF / sP (and, after the last batch, sA) are free again
         }
         phase ^= 1;
+        e0 = e0n, e1 = e1n;
     }
 }
 
