@@ -139,13 +139,15 @@ __global__ void radial_bwd_kernel(const float* __restrict__ rb, const unsigned c
 // Fixed order everywhere: bit-reproducible.
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const int* __restrict__ idx, const float* __restrict__ scale, const float* __restrict__ dx0, int ld, int col0, int dim,
-                 int n_rows, int N, float* __restrict__ dtab) {
+                 int n_rows, int N, int per_split, float* __restrict__ partial, float* __restrict__ dtab) {
     __shared__ float part[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x;
     if (r >= n_rows) return;
-    const int per = (((N + 7) / 8) + 31) & ~31;  // atoms per warp, a multiple of 32
-    const int i0 = warp * per, i1 = min(N, i0 + per);
+    // grid.y splits the atoms (per_split a multiple of 256); within a split the 8 warps take contiguous eighths
+    const int s0 = blockIdx.y * per_split, s1 = min(N, s0 + per_split);
+    const int per = per_split / 8;
+    const int i0 = s0 + warp * per, i1 = min(s1, i0 + per);
     float acc = 0.f;
     for (int base = i0; base < i1; base += 32) {
         const int i = base + lane;
@@ -163,8 +165,19 @@ embed_bwd_kernel(const int* __restrict__ idx, const float* __restrict__ scale, c
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += part[w][lane];
-        dtab[(size_t)r * dim + lane] = t * (scale ? scale[col0 + lane] : 1.f);
+        if (partial) partial[((size_t)blockIdx.y * n_rows + r) * 32 + lane] = t;
+        else dtab[(size_t)r * dim + lane] = t * (scale ? scale[col0 + lane] : 1.f);
     }
+}
+
+// dtab[r] = scale * sum over the splits (ascending) of partial[split][r]
+__global__ void embed_bwd_reduce_kernel(const float* __restrict__ partial, int splits, int n_rows, const float* __restrict__ scale,
+                                        int col0, int dim, float* __restrict__ dtab) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    if (lane >= dim) return;
+    float t = 0.f;
+    for (int z = 0; z < splits; ++z) t += partial[((size_t)z * n_rows + r) * 32 + lane];
+    dtab[(size_t)r * dim + lane] = t * (scale ? scale[col0 + lane] : 1.f);
 }
 
 // prod[i, c] = dx0[i, c] * emb[i, c] (unscaled embedding) -> colsum gives dscale
@@ -508,8 +521,20 @@ extern "C" int jamun_embed_bwd(const int* idx0, const int* idx1, const int* idx2
     float* dt[4] = {dtab0, dtab1, dtab2, dtab3};
     const int dims[4] = {dim0, dim1, dim2, dim3}, rows[4] = {rows0, rows1, rows2, rows3};
     int col0 = 0;
+    // the atoms are split over grid.y when there are enough of them; the per-split partial rows live in `prod` (free until
+    // embed_prod_kernel below overwrites it; the stream orders the two)
+    int splits = (N + 1023) / 1024;
+    if (splits > 64) splits = 64;
+    int max_rows = 1;
+    for (int k = 0; k < 4; ++k) max_rows = rows[k] > max_rows ? rows[k] : max_rows;
+    if (splits > 1 && (size_t)splits * max_rows * 32 > (size_t)N * D) splits = 1;
+    const int per_split = splits > 1 ? ((N + splits - 1) / splits + 255) / 256 * 256 : ((N + 255) / 256 * 256 > 0 ? (N + 255) / 256 * 256 : 256);
     for (int k = 0; k < 4; ++k) {
-        if (rows[k] > 0) embed_bwd_kernel<<<rows[k], 256, 0, s>>>(idx[k], scale, dx0, D, col0, dims[k], rows[k], N, dt[k]);
+        if (rows[k] > 0) {
+            embed_bwd_kernel<<<::dim3(rows[k], splits), 256, 0, s>>>(idx[k], scale, dx0, D, col0, dims[k], rows[k], N, per_split,
+                                                                  splits > 1 ? prod : nullptr, dt[k]);
+            if (splits > 1) embed_bwd_reduce_kernel<<<rows[k], 32, 0, s>>>(prod, splits, rows[k], scale, col0, dims[k], dt[k]);
+        }
         col0 += dims[k];
     }
     if (N > 0)
