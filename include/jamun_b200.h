@@ -100,6 +100,12 @@ int jamun_edge_radial_hidden(const float* rb, const unsigned char* ebond, const 
 int jamun_edge_radial_hidden_all(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
                                  const float* w0r_all, const float* b0eff_all, int layers, float* h_all,
                                  jamun_stream_t stream);
+/* The same on the warp-level tensor cores (mma.sync tf32, three-product split = fp32 accuracy).  jamun_radial_pack_frag turns
+ * w0r_all [layers, 32, 64] into pre-split, fragment-ordered weight images img [layers * 4096] floats (once per plan);
+ * jamun_edge_radial_hidden_mma evaluates all layers from them. */
+int jamun_radial_pack_frag(const float* w0r_all, int layers, float* img, jamun_stream_t stream);
+int jamun_edge_radial_hidden_mma(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                                 const float* img, const float* b0eff_all, int layers, float* h_all, jamun_stream_t stream);
 
 /* Conv.forward (e3tools/nn/_conv.py:96-119): gather, per-edge-weighted FullyConnectedTensorProduct,
  * scatter-mean -- evaluated in the aggregate-then-transform form: per receiver

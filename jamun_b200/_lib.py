@@ -40,6 +40,8 @@ _PROTOS = {
     "jamun_edge_geom": ([c_f, c_f, c_f, c_f, I, I, c_f, F, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden": ([c_f, c_f, c_f, I, I, c_f, c_f, c_f, c_f], I),
     "jamun_edge_radial_hidden_all": ([c_f, c_f, c_f, I, I, c_f, c_f, I, c_f, c_f], I),
+    "jamun_radial_pack_frag": ([c_f, I, c_f, c_f], I),
+    "jamun_edge_radial_hidden_mma": ([c_f, c_f, c_f, I, I, c_f, c_f, I, c_f, c_f], I),
     "jamun_conv_fwd": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, c_f, F, F, I, c_f, c_f], I),
     "jamun_conv_build_a": ([c_f, I, I, c_f, c_f, c_f, c_f, c_f, I, I, I, I, c_f, c_f, C.c_longlong, c_f, I, F, c_f, c_f], I),
     "jamun_conv_build_tc": ([c_f, I, I, c_f, c_f, c_f, c_f, I, I, I, c_f, c_f, C.c_longlong, c_f, c_f], I),

@@ -676,6 +676,120 @@ extern "C" int jamun_edge_radial_hidden_all(const float* rb, const unsigned char
     return JAMUN_OK;
 }
 
+// ---- K2b on the warp-level tensor cores ---------------------------------------------------------------------------------------
+// The same [E x 32] . [32 x 64] product per layer as mma.sync.m16n8k8 (tf32 operands, fp32 accumulate) with the three-product
+// split for fp32 accuracy (hi = v & 0xFFFFE000, lo = v - hi; lo.hi + hi.lo + hi.hi).  A warp owns 16 edges: their radial basis is
+// loaded and split once (32 registers) and reused by every layer; the weights arrive as pre-split, fragment-ordered images
+// ([layer][k-step][n-tile][lane] x {b0.hi, b1.hi, b0.lo, b1.lo}, built once per plan by radial_pack_frag_kernel; 96 KB for six
+// layers, L1-resident) so that a B fragment pair is one coalesced 16-byte load per lane.  Bias + SiLU in the epilogue; every store
+// instruction writes eight full 32-byte sectors.  Per 16 edges and layer: 96 HMMA + 32 loads, against 2048 FFMA2 before.
+__global__ void radial_pack_frag_kernel(const float* __restrict__ w0r_all, int layers, uint4* __restrict__ img) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= layers * 4 * 8 * 32) return;
+    const int lane = t & 31, nt = (t >> 5) & 7, ks = (t >> 8) & 3, l = t >> 10;
+    const int g = lane >> 2, tig = lane & 3;
+    const float* w = w0r_all + (size_t)l * JAMUN_NBASIS * JAMUN_EDGE_HID;
+    const float b0 = w[(8 * ks + tig) * JAMUN_EDGE_HID + 8 * nt + g], b1 = w[(8 * ks + tig + 4) * JAMUN_EDGE_HID + 8 * nt + g];
+    uint4 o;
+    o.x = __float_as_uint(b0) & 0xFFFFE000u, o.y = __float_as_uint(b1) & 0xFFFFE000u;
+    o.z = __float_as_uint(b0 - __uint_as_float(o.x)), o.w = __float_as_uint(b1 - __uint_as_float(o.y));
+    img[t] = o;
+}
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) edge_radial_hidden_mma_kernel(const float* __restrict__ rb, const unsigned char* __restrict__ ebond,
+                                                                     const int* __restrict__ rowptr, int N,
+                                                                     const uint4* __restrict__ img, const float* __restrict__ b0eff,
+                                                                     float* __restrict__ h, int L, size_t h_stride) {
+    const int E = rowptr[N];
+    const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int e_base = 16 * (blockIdx.x * 4 + (threadIdx.x >> 5));
+    if (e_base >= E) return;
+    const int r0 = e_base + g, r1 = r0 + 8;
+    const bool on0 = r0 < E, on1 = r1 < E;
+    uint32_t ahi[4][4], alo[4][4];
+    {
+        float a[4][4];
+        const float* p0 = rb + (size_t)r0 * JAMUN_NBASIS + tig;
+        const float* p1 = rb + (size_t)r1 * JAMUN_NBASIS + tig;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            a[ks][0] = on0 ? p0[8 * ks] : 0.f;
+            a[ks][1] = on1 ? p1[8 * ks] : 0.f;
+            a[ks][2] = on0 ? p0[8 * ks + 4] : 0.f;
+            a[ks][3] = on1 ? p1[8 * ks + 4] : 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ahi[ks][q] = __float_as_uint(a[ks][q]) & 0xFFFFE000u;
+                alo[ks][q] = __float_as_uint(a[ks][q] - __uint_as_float(ahi[ks][q]));
+            }
+    }
+    const int f0 = on0 && ebond[r0] ? JAMUN_EDGE_HID : 0, f1 = on1 && ebond[r1] ? JAMUN_EDGE_HID : 0;
+    for (int l = 0; l < L; ++l) {
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        const uint4* im = img + (size_t)l * 4 * 8 * 32 + lane;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint4 b[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) b[nt] = im[(ks * 8 + nt) * 32];
+            // term by term across the n-tiles: consecutive MMAs never wait on each other's accumulator
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], alo[ks], b[nt].x, b[nt].y);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ahi[ks], b[nt].z, b[nt].w);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], ahi[ks], b[nt].x, b[nt].y);
+        }
+        const float* bias = b0eff + (size_t)l * 2 * JAMUN_EDGE_HID + 2 * tig;
+        float* hl = h + (size_t)l * h_stride + 2 * tig;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (on0) {
+                const float2 bb = *reinterpret_cast<const float2*>(bias + f0 + 8 * nt);
+                *reinterpret_cast<float2*>(hl + (size_t)r0 * JAMUN_EDGE_HID + 8 * nt) =
+                    make_float2(jb::siluf_fast(acc[nt][0] + bb.x), jb::siluf_fast(acc[nt][1] + bb.y));
+            }
+            if (on1) {
+                const float2 bb = *reinterpret_cast<const float2*>(bias + f1 + 8 * nt);
+                *reinterpret_cast<float2*>(hl + (size_t)r1 * JAMUN_EDGE_HID + 8 * nt) =
+                    make_float2(jb::siluf_fast(acc[nt][2] + bb.x), jb::siluf_fast(acc[nt][3] + bb.y));
+            }
+        }
+    }
+}
+
+extern "C" int jamun_radial_pack_frag(const float* w0r_all, int layers, float* img, jamun_stream_t stream) {
+    JB_CHECK_ARG(w0r_all && img && layers >= 1, "bad argument");
+    const int total = layers * 4 * 8 * 32;
+    radial_pack_frag_kernel<<<(total + 255) / 256, 256, 0, jb::as_stream(stream)>>>(w0r_all, layers, reinterpret_cast<uint4*>(img));
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
+extern "C" int jamun_edge_radial_hidden_mma(const float* rb, const unsigned char* ebond, const int* rowptr, int N, int cap,
+                                            const float* img, const float* b0eff_all, int layers, float* h_all,
+                                            jamun_stream_t stream) {
+    JB_CHECK_ARG(rb && ebond && rowptr && img && b0eff_all && h_all && layers >= 1, "bad argument");
+    if (N == 0 || cap == 0) return JAMUN_OK;
+    // one warp per 16-edge tile of the capacity; the live edge count is device-side (rowptr[N]), surplus warps exit
+    const int blocks = (cap + 63) / 64;
+    edge_radial_hidden_mma_kernel<<<blocks, 128, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, reinterpret_cast<const uint4*>(img),
+                                                                             b0eff_all, h_all, layers, (size_t)cap * JAMUN_EDGE_HID);
+    JB_CHECK_LAUNCH();
+    return JAMUN_OK;
+}
+
 extern "C" int jamun_layout_to_soa(const float* in, int s, int v, int N, float* out, jamun_stream_t stream) {
     JB_CHECK_ARG(in && out && s >= 0 && v >= 0, "bad argument");
     if (N == 0) return JAMUN_OK;

@@ -24,6 +24,9 @@ CONV_IMPL = os.environ.get("JAMUN_B200_CONV", "tc")
 # aggregate builder of the tensor-core path: "tc" = tcgen05 per-node products (jamun_conv_build_tc) with the 0e(x)1e->1e
 # gather (jamun_conv_p2) on a side stream; "ffma" = the FP32-pipe builder jamun_conv_build_a (exact fp32 aggregate)
 BUILD_IMPL = os.environ.get("JAMUN_B200_BUILD", "tc")
+# radial MLP hidden layer: "ffma" = packed-FP32 CUDA-core kernel (0.186 ms at the 2AA bench size); "mma" = warp-level tensor cores
+# (tf32 three-product split, 34 % fewer instructions but 0.207 ms: latency-bound on its weight-fragment loads -- DESIGN.md 5)
+RADIAL_IMPL = os.environ.get("JAMUN_B200_RADIAL_HIDDEN", "ffma")
 # tensor-core split of the sampling path's GEMMs: "f16" = fp16 hi/lo split, tcgen05 kind::f16 (jamun_gemm_f16x3: half the MMA
 # instructions of the tf32 form at the same 11-bit significands; weights pre-scaled into the fp16 range when the plan is built,
 # operand overflow reported through Topology.gemm_status); "tf32" = jamun_gemm_tf32x3.  Read when a plan is built.
@@ -257,6 +260,7 @@ class E3ConvPlan:
                 self.blocks.append(blk)
             self.w0r_all = up(torch.stack([b.pack(emb)["w0r"] for b in [gc.initial_projector, *gc.layers]]))      # [L, 32, 64]
             self.b0eff_all = up(torch.stack([b.pack(emb)["b0eff"] for b in [gc.initial_projector, *gc.layers]]))  # [L, 2, 64]
+            self.w0r_frag = ops.radial_pack_frag(self.w0r_all) if RADIAL_IMPL == "mma" else None  # tensor-core weight images
             f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
             self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
             self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
@@ -535,7 +539,10 @@ def e3conv_forward(plan: E3ConvPlan, topo: Topology, p: torch.Tensor, r_cut: flo
     # radial hidden of every layer in one pass over the edges (h_all: [L, cap, 64])
     if getattr(topo, "h_all", None) is None or topo.h_all.shape[0] != nb:
         topo.h_all = torch.zeros(nb, topo.cap, ops.EDGE_HID, dtype=torch.float32, device=topo.device)
-    ops.edge_radial_hidden_all(topo.rb, topo.ebond, topo.rowptr, plan.w0r_all, plan.b0eff_all, topo.h_all)
+    if plan.w0r_frag is not None:
+        ops.edge_radial_hidden_mma(topo.rb, topo.ebond, topo.rowptr, plan.w0r_frag, plan.b0eff_all, topo.h_all)
+    else:
+        ops.edge_radial_hidden_all(topo.rb, topo.ebond, topo.rowptr, plan.w0r_all, plan.b0eff_all, topo.h_all)
     for l, b in enumerate(plan.blocks):
         vadd = None
         topo.h = topo.h_all[l]

@@ -181,6 +181,30 @@ def edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all):
     _T.edge_radial_hidden_all(rb, ebond, rowptr, w0r_all, b0eff_all, h_all)
 
 
+def radial_pack_frag(w0r_all: Tensor) -> Tensor:
+    """Pre-split, fragment-ordered weight images of the tensor-core radial hidden kernel ([layers * 4096] floats; plan build)."""
+    layers = w0r_all.shape[0]
+    img = torch.empty(layers * 4096, dtype=torch.float32, device=w0r_all.device)
+    rc = _lib.lib().jamun_radial_pack_frag(_ptr(w0r_all), layers, _ptr(img), _stream())
+    _lib.check(rc, "jamun_radial_pack_frag")
+    _count()
+    return img
+
+
+@_op("edge_radial_hidden_mma", mutates=("h_all",))
+def _edge_radial_hidden_mma(rb: Tensor, ebond: Tensor, rowptr: Tensor, img: Tensor, b0eff_all: Tensor, h_all: Tensor) -> None:
+    N, cap, layers = rowptr.numel() - 1, ebond.numel(), b0eff_all.shape[0]
+    assert h_all.shape[0] == layers and h_all.shape[1] == cap and img.numel() == layers * 4096
+    rc = _lib.lib().jamun_edge_radial_hidden_mma(_ptr(rb), _ptr(ebond, torch.uint8), _ptr(rowptr, torch.int32), N, cap, _ptr(img),
+                                                 _ptr(b0eff_all), layers, _ptr(h_all), _stream())
+    _lib.check(rc, "jamun_edge_radial_hidden_mma")
+    _count()
+
+
+def edge_radial_hidden_mma(rb, ebond, rowptr, img, b0eff_all, h_all):
+    _T.edge_radial_hidden_mma(rb, ebond, rowptr, img, b0eff_all, h_all)
+
+
 @_op("conv_fwd_simt", mutates=("out",))
 def _conv_fwd(x: Tensor, s_in: int, v_in: int, rowptr: Tensor, col: Tensor, h: Tensor, rhat: Tensor, m0: Tensor, m1: Tensor,
               alpha0: float, alpha1: float, out: Tensor) -> None:

@@ -215,3 +215,29 @@ def test_fp16_range_overflow_falls_back_to_tf32_kernels(monkeypatch):
         x_tf32 = run()
     assert not any("fp16 range" in str(i.message) for i in w2)
     assert torch.equal(x, x_tf32)
+
+
+def test_radial_hidden_tensor_core_kernel_matches_fp64_and_cuda_core_kernel():
+    """jamun_edge_radial_hidden_mma (mma.sync tf32, three-product split) against fp64 torch and the packed-FP32 kernel: all layers,
+    ragged edge count (not a multiple of 16), capacity rows beyond the live edges untouched."""
+    from jamun_b200 import ops
+
+    gen = torch.Generator().manual_seed(3)
+    E, cap, L = 1000 + 7, 1100, 6
+    rb = torch.rand(cap, 32, generator=gen) * 0.9
+    w = torch.randn(L, 32, 64, generator=gen) / 32 ** 0.5
+    b = torch.randn(L, 2, 64, generator=gen) * 0.3
+    flag = (torch.rand(cap, generator=gen) < 0.2).to(torch.uint8)
+    rowptr = torch.tensor([0, 400, E], dtype=torch.int32)
+    z = torch.einsum("ek,lko->leo", rb[:E].double(), w.double()) + b.double()[:, flag[:E].long()].reshape(L, E, 64)
+    want = (z * torch.sigmoid(z)).float()
+    dev = "cuda"
+    h_mma = torch.full((L, cap, 64), -7.0, device=dev)
+    h_ffma = torch.full((L, cap, 64), -7.0, device=dev)
+    img = ops.radial_pack_frag(w.to(dev))
+    ops.edge_radial_hidden_mma(rb.to(dev), flag.to(dev), rowptr.to(dev), img, b.to(dev).contiguous(), h_mma)
+    ops.edge_radial_hidden_all(rb.to(dev), flag.to(dev), rowptr.to(dev), w.to(dev).contiguous(), b.to(dev).contiguous(), h_ffma)
+    for got in (h_mma, h_ffma):
+        assert torch.allclose(got[:, :E].cpu(), want, rtol=2e-6, atol=2e-6), (got[:, :E].cpu() - want).abs().max()
+        assert torch.all(got[:, E:] == -7.0)
+    assert (h_mma[:, :E] - h_ffma[:, :E]).abs().max().item() < 4e-6
