@@ -338,10 +338,9 @@ def measure_training(cx: Ctx, chains: int, steps: int, warmup: int):
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     batch = data.Batch.from_tensors(t).to(cx.dev)
     torch.manual_seed(77 + cx.rank)
-    fwd_ms = bwd_ms = 0.0
+    marks = []  # per-step (start, after forward, after backward) events, read after the timed region: no per-step host sync
 
     def step(timed: bool):
-        nonlocal fwd_ms, bwd_ms
         reducer.reset()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
@@ -352,9 +351,7 @@ def measure_training(cx: Ctx, chains: int, steps: int, warmup: int):
         e[2].record()
         opt.step()
         if timed:
-            torch.cuda.synchronize()
-            fwd_ms += e[0].elapsed_time(e[1])
-            bwd_ms += e[1].elapsed_time(e[2])
+            marks.append(e)
         return out["loss"]
 
     for _ in range(warmup):
@@ -368,6 +365,8 @@ def measure_training(cx: Ctx, chains: int, steps: int, warmup: int):
     ev1.record()
     cx.barrier()
     ms, total_atoms = cx.max_ms_sum_atoms(ev0.elapsed_time(ev1), atoms)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in marks)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in marks)
     return {"metric": "train_atoms_per_s", "value": total_atoms * steps / (ms * 1e-3), "unit": "atoms/s (fwd+bwd+allreduce+Adam)",
             "ms_per_step": ms / steps, "fwd_ms": fwd_ms / steps, "bwd_allreduce_ms": bwd_ms / steps, "atoms_per_gpu": atoms,
             "graphs_per_gpu": len(sizes), "allreduce_bytes_per_step": reducer.gradient_bytes if cx.world > 1 else 0,

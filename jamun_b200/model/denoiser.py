@@ -166,7 +166,10 @@ class Denoiser(_Base):
 
     # ------------------------------------------------------------------ reference API
     def add_noise(self, x, sigma: Union[float, torch.Tensor]):
-        sigma = unsqueeze_trailing(torch.as_tensor(sigma).to(x.pos), x.pos.ndim)
+        if isinstance(sigma, torch.Tensor) and sigma.is_cuda:
+            sigma = unsqueeze_trailing(sigma.to(x.pos), x.pos.ndim)
+        else:  # host value: used as a Python scalar (a host-to-device copy of it would drain the stream)
+            sigma = float(torch.as_tensor(sigma))
         y = x.clone("pos")
         if self.add_fixed_ones:
             noise = torch.ones_like(x.pos)
@@ -250,8 +253,7 @@ class Denoiser(_Base):
         with torch.no_grad():
             if self.mean_center:
                 x = mean_center(x)
-            sigma = torch.as_tensor(sigma).to(x.pos)
-            y = self.add_noise(x, sigma)
+            y = self.add_noise(x, sigma)  # `sigma` stays where it is (host in training_step: no read-back, no copy)
             if self.mean_center:
                 y = mean_center(y)
             if align_noisy_input:
@@ -288,10 +290,20 @@ class Denoiser(_Base):
         xhat, _ = self.noise_and_denoise(x, sigma, align_noisy_input=align_noisy_input)
         return self.compute_loss(x, xhat, sigma)
 
+    def _to_device_scalar(self, t: torch.Tensor) -> torch.Tensor:
+        """`t.to(self.device)` for a 0-dim host tensor as a fill kernel: a pageable host-to-device copy would wait for the stream."""
+        if t.is_cuda or t.ndim != 0 or torch.device(self.device).type != "cuda":
+            return t.to(self.device)
+        return torch.full((), float(t), dtype=t.dtype, device=self.device)
+
     def training_step(self, batch, batch_idx: int):
         """denoiser.py:299-319.  Forward and backward run on this library's kernels (jamun_b200/training.py)."""
-        sigma = self.sigma_distribution.sample().to(self.device)
-        loss, aux = self.noise_and_compute_loss(batch, sigma, align_noisy_input=self.align_noisy_input_during_training)
+        sigma_host = self.sigma_distribution.sample()  # the distributions live on the host: the noise level is known there ...
+        sigma = self._to_device_scalar(sigma_host)
+        # ... so the per-sigma scalars (c_in, c_skip, c_out, cut-off, loss weight) are taken from the host copy -- reading them
+        # back from `sigma` would drain the stream at the start of every step and stop the host from running ahead
+        loss, aux = self.noise_and_compute_loss(batch, sigma if sigma_host.is_cuda else sigma_host,
+                                                align_noisy_input=self.align_noisy_input_during_training)
         aux["loss"] = loss
         for key in aux:
             aux[key] = aux[key].mean()
@@ -299,8 +311,10 @@ class Denoiser(_Base):
         return {"sigma": sigma, **aux}
 
     def validation_step(self, batch, batch_idx: int):
-        sigma = self.sigma_distribution.sample().to(self.device)
-        loss, aux = self.noise_and_compute_loss(batch, sigma, align_noisy_input=self.align_noisy_input_during_training)
+        sigma_host = self.sigma_distribution.sample()
+        sigma = self._to_device_scalar(sigma_host)
+        loss, aux = self.noise_and_compute_loss(batch, sigma if sigma_host.is_cuda else sigma_host,
+                                                align_noisy_input=self.align_noisy_input_during_training)
         aux["loss"] = loss
         for key in aux:
             aux[key] = aux[key].mean()

@@ -20,13 +20,25 @@ from . import engine, ops
 T = torch.ops.jamun_b200
 
 
+_grids = {}  # (r_cut, device) -> (centres on the device, spacing): uploaded once (a per-step upload would drain the stream)
+
+
+def _radial_grid(r_cut: float, device):
+    key = (r_cut, str(device))
+    if key not in _grids:
+        if len(_grids) > 64:
+            _grids.clear()
+        values = torch.linspace(0.0, r_cut, ops.NBASIS + 2, dtype=torch.float32)
+        _grids[key] = (values[1:-1].to(device).contiguous(), float(values[1] - values[0]))
+    return _grids[key]
+
+
 def network_output(arch, topo: engine.Topology, p: torch.Tensor, c_noise: float, r_cut: float) -> torch.Tensor:
     """g = E3Conv(p) [N, 3] on topo's current CSR, differentiable w.r.t. arch's parameters."""
     if not p.is_cuda:
         raise RuntimeError("jamun_b200.training runs on CUDA tensors only (no CPU fallback)")
     with torch.no_grad():  # geometry carries no gradient (positions are inputs)
-        values = torch.linspace(0.0, float(r_cut), ops.NBASIS + 2, dtype=torch.float32)
-        mu, step = values[1:-1].to(p.device).contiguous(), float(values[1] - values[0])
+        mu, step = _radial_grid(float(r_cut), p.device)
         ops.edge_geom(p.contiguous(), topo.rowptr, topo.col, topo.edst, mu, step, topo.rhat, topo.rb)
     csr = (topo.rhat, topo.rowptr, topo.col, topo.edst, topo.src_rowptr, topo.src_eid)
     emb = arch.embed_bondedness.weight

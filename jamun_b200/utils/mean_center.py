@@ -7,8 +7,9 @@ from .. import engine, ops
 def mean_center(x):
     """Per-graph centroid subtraction; returns a shallow clone with new `pos`."""
     out = x.clone("pos")
-    topo = x["_topology"] if "_topology" in x else engine.Topology(x, x.pos.device)
-    out["_topology"] = topo
+    if "_topology" not in x:
+        x["_topology"] = engine.Topology(x, x.pos.device)  # cached on the input too: later calls on the same batch reuse it
+    topo = out["_topology"] = x["_topology"]
     ybar, _ = ops.center_scale(x.pos.contiguous(), topo.chain_ptr, 1.0)
     out.pos = ybar
     return out
