@@ -10,6 +10,7 @@ MLP), model/atom_embedding.py:58-76, model/noise_conditioning.py:27-73, model/de
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -79,17 +80,15 @@ def _build_aggregate(x, s_in, v_in, rowptr, col, h, rhat, rows_pad):
 # =====================================================================================================================
 # conv
 # =====================================================================================================================
-@torch.library.custom_op(f"{NS_LIB}::conv", mutates_args=())
-def conv(x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, src_rowptr: Tensor, src_eid: Tensor,
-         m0: Tensor, m1: Tensor, s_in: int, v_in: int, alpha0: float, alpha1: float) -> Tensor:
-    """Conv.forward: x [N, s_in+3 v_in] (SoA) -> [N, 248]; h [cap, 64] radial hidden, CSR by receiver and by source."""
+def _conv_forward(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1):
+    """-> (out, a_ws, inv_deg, y): the conv output and the operands its backward can reuse."""
     from . import engine
 
     x, h, m0, m1 = x.contiguous(), h.contiguous(), m0.contiguous(), m1.contiguous()
     N = x.shape[0]
     out = _empty(N, GIN, like=x)
     if N == 0:
-        return out
+        return out, None, None, None
     rows_pad = _rows_pad(N)
     _, nsl0, nsl1 = _shape(s_in, v_in)
     st0, st1 = 65 * nsl0, 65 * nsl1
@@ -111,7 +110,16 @@ def conv(x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, col: Tensor, edst: 
         engine._contract(sc, [base], [b0.data_ptr()], [st0], [160], [152], [0], [alpha0], N, rows_pad, inv_deg.data_ptr(),
                          out.data_ptr())
         ops.conv_p2(rowptr, src_rowptr, src_eid, h, rhat, y, t_edge, out.data_ptr() + 4 * SO, GIN, alpha1)
-    return out
+    return out, a_ws, inv_deg, y
+
+
+
+
+@torch.library.custom_op(f"{NS_LIB}::conv", mutates_args=())
+def conv(x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, src_rowptr: Tensor, src_eid: Tensor,
+         m0: Tensor, m1: Tensor, s_in: int, v_in: int, alpha0: float, alpha1: float) -> Tensor:
+    """Conv.forward: x [N, s_in+3 v_in] (SoA) -> [N, 248]; h [cap, 64] radial hidden, CSR by receiver and by source."""
+    return _conv_forward(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1)[0]
 
 
 @conv.register_fake
@@ -121,9 +129,11 @@ def _(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, al
 
 @torch.library.custom_op(f"{NS_LIB}::conv_bwd", mutates_args=())
 def conv_bwd(dout: Tensor, x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, src_rowptr: Tensor,
-             src_eid: Tensor, m0: Tensor, m1: Tensor, s_in: int, v_in: int, alpha0: float, alpha1: float
+             src_eid: Tensor, m0: Tensor, m1: Tensor, s_in: int, v_in: int, alpha0: float, alpha1: float,
+             a_saved: Optional[Tensor] = None, inv_deg_saved: Optional[Tensor] = None, y_saved: Optional[Tensor] = None
              ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """-> (dx [N, D_in], dh [cap, 64], dm0, dm1); scheme in csrc/train_conv_bwd.cu."""
+    """-> (dx [N, D_in], dh [cap, 64], dm0, dm1); scheme in csrc/train_conv_bwd.cu.  a_saved / inv_deg_saved / y_saved: the
+    forward's aggregate operand, 1/deg and per-node transform when conv_keep kept them (otherwise recomputed here)."""
     dout, x, h, m0, m1 = dout.contiguous(), x.contiguous(), h.contiguous(), m0.contiguous(), m1.contiguous()
     N, D_in, cap = x.shape[0], x.shape[1], col.numel()
     ns, nsl0, nsl1 = _shape(s_in, v_in)
@@ -134,11 +144,18 @@ def conv_bwd(dout: Tensor, x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, c
     if N == 0:
         return dx, dh, dm0.zero_(), dm1.zero_()
     rows_pad = _rows_pad(N)
-    # recompute the forward operands: Y (per-node transform) and the aggregate A
-    wy = ops.pack_b(m1.reshape(65 * u1, 32), n_stages=ns, n_pad=128, k_src=s_in, n_valid=65 * 32, n_inner=32, outer_rows=u1,
-                    col_blocks=17)
-    y = _node_transform(x, wy, s_in, rows_pad)
-    a_ws, a1_off, comp, inv_deg = _build_aggregate(x, s_in, v_in, rowptr, col, h, rhat, rows_pad)
+    # the forward operands Y (per-node transform) and A (aggregate): kept by conv_keep, or recomputed
+    if y_saved is not None and y_saved.numel():
+        y = y_saved
+    else:
+        wy = ops.pack_b(m1.reshape(65 * u1, 32), n_stages=ns, n_pad=128, k_src=s_in, n_valid=65 * 32, n_inner=32, outer_rows=u1,
+                        col_blocks=17)
+        y = _node_transform(x, wy, s_in, rows_pad)
+    if a_saved is not None and a_saved.numel():
+        a_ws, inv_deg = a_saved, inv_deg_saved
+        a1_off, comp = 65 * nsl0 * rows_pad * 32, 65 * nsl1 * rows_pad * 32
+    else:
+        a_ws, a1_off, comp, inv_deg = _build_aggregate(x, s_in, v_in, rowptr, col, h, rhat, rows_pad)
     base = a_ws.data_ptr()
     g = _empty(N, GIN, like=x)
     ops.conv_bwd_scale(dout, inv_deg, alpha0, alpha1, g)
@@ -189,7 +206,8 @@ def conv_bwd(dout: Tensor, x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, c
 
 
 @conv_bwd.register_fake
-def _(dout, x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1):
+def _(dout, x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1, a_saved=None, inv_deg_saved=None,
+      y_saved=None):
     return torch.empty_like(x), h.new_empty(col.numel(), 64), torch.empty_like(m0), torch.empty_like(m1)
 
 
@@ -206,6 +224,53 @@ def _conv_backward(ctx, dout):
 
 
 conv.register_autograd(_conv_backward, setup_context=_conv_setup)
+
+
+# ---- conv_keep: the same forward, keeping the aggregate operand A (3.2 GB per hidden layer at 35 k atoms), 1/deg and the per-node
+# transform Y for the backward instead of rebuilding them there (builder + transform recompute: ~5 ms of a 79 ms step).  A layer
+# whose operand exceeds JAMUN_B200_TRAIN_KEEP_A_GB (default 4 GB, i.e. <= 24 GB over the six layers) is recomputed as before.
+def _keep_limit_bytes() -> float:
+    return float(os.environ.get("JAMUN_B200_TRAIN_KEEP_A_GB", "4")) * 2 ** 30
+
+
+def _a_floats(N: int, s_in: int, v_in: int) -> int:
+    _, nsl0, nsl1 = _shape(s_in, v_in)
+    return (65 * nsl0 + 3 * 65 * nsl1) * _rows_pad(N) * 32
+
+
+@torch.library.custom_op(f"{NS_LIB}::conv_keep", mutates_args=())
+def conv_keep(x: Tensor, h: Tensor, rhat: Tensor, rowptr: Tensor, col: Tensor, edst: Tensor, src_rowptr: Tensor, src_eid: Tensor,
+              m0: Tensor, m1: Tensor, s_in: int, v_in: int, alpha0: float, alpha1: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (out [N, 248], a_ws, inv_deg, y); the last three are empty when the operand is too large to keep."""
+    out, a_ws, inv_deg, y = _conv_forward(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1)
+    if a_ws is None or 4 * a_ws.numel() > _keep_limit_bytes():
+        return out, _empty(0, like=out), _empty(0, like=out), _empty(0, like=out)
+    return out, a_ws, inv_deg, y
+
+
+@conv_keep.register_fake
+def _(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1):
+    N = x.shape[0]
+    if N == 0 or 4 * _a_floats(N, s_in, v_in) > _keep_limit_bytes():
+        return x.new_empty(N, GIN), x.new_empty(0), x.new_empty(0), x.new_empty(0)
+    return x.new_empty(N, GIN), x.new_empty(_a_floats(N, s_in, v_in)), x.new_empty(N), x.new_empty(N, Y_LD)
+
+
+def _conv_keep_setup(ctx, inputs, output):
+    x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, s_in, v_in, alpha0, alpha1 = inputs
+    _, a_ws, inv_deg, y = output
+    ctx.save_for_backward(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, a_ws, inv_deg, y)
+    ctx.consts = (s_in, v_in, alpha0, alpha1)
+
+
+def _conv_keep_backward(ctx, dout, da, dinv, dy):
+    x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, a_ws, inv_deg, y = ctx.saved_tensors
+    dx, dh, dm0, dm1 = torch.ops.jamun_b200.conv_bwd(dout, x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, *ctx.consts,
+                                                     a_ws, inv_deg, y)
+    return dx, dh, None, None, None, None, None, None, dm0, dm1, None, None, None, None
+
+
+conv_keep.register_autograd(_conv_keep_backward, setup_context=_conv_keep_setup)
 
 
 # =====================================================================================================================

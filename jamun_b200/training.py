@@ -53,7 +53,7 @@ def network_output(arch, topo: engine.Topology, p: torch.Tensor, c_noise: float,
     for l, blk in enumerate(blocks):
         pk = blk.pack(emb)
         h = T.radial_hidden(topo.rb, topo.ebond, topo.rowptr, pk["w0r"], pk["b0eff"])
-        conv_out = T.conv(x_in, h, *csr, pk["m0"], pk["m1"], pk["s_in"], pk["v_in"], pk["alpha0"], pk["alpha1"])
+        conv_out = T.conv_keep(x_in, h, *csr, pk["m0"], pk["m1"], pk["s_in"], pk["v_in"], pk["alpha0"], pk["alpha1"])[0]
         skip_w = T.noise_mlp(*arch.skip_connections[l - 1].weights.mlp_operands(), c_noise, True) if l > 0 else None
         s_next = T.noise_mlp(*arch.noise_scalings[l].mlp_operands(), c_noise, False) if l < nb - 1 else None
         x_new, x_scaled = T.block_tail(conv_out, x_in, x_res, pk["wself_s"], pk["wself_v"], pk["wskip_s"], pk["wskip_v"], skip_w,

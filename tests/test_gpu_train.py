@@ -289,7 +289,7 @@ def test_training_gradients_match_oracle_autograd(models):
     print(f"worst relative gradient error vs oracle autograd: {worst:.2e}")
 
 
-def test_training_step_is_deterministic_and_reduces_loss(models):
+def test_training_step_is_deterministic_and_reduces_loss(models, monkeypatch):
     """A few SGD steps through Denoiser.training_step on one fixed noisy batch lower the loss; two identical runs give
     bit-identical losses and gradients (no atomics anywhere on the backward path)."""
     import jamun_b200 as J
@@ -319,6 +319,10 @@ def test_training_step_is_deterministic_and_reduces_loss(models):
     assert all(torch.isfinite(torch.tensor(l1)))
     assert l1[-1] < l1[0], l1
     assert l1 == l2 and all(torch.equal(a, b) for a, b in zip(g1, g2))
+    # operands kept from the forward (conv_keep, the default) vs rebuilt in the backward: the same bits
+    monkeypatch.setenv("JAMUN_B200_TRAIN_KEEP_A_GB", "0")
+    l3, g3 = run()
+    assert l1 == l3 and all(torch.equal(a, b) for a, b in zip(g1, g3))
 
 
 def test_operator_registrations_pass_opcheck(models):
@@ -340,6 +344,7 @@ def test_operator_registrations_pass_opcheck(models):
     args = (x, h, topo.rhat, topo.rowptr, topo.col, topo.edst, topo.src_rowptr, topo.src_eid, pk["m0"].detach().requires_grad_(True),
             pk["m1"].detach().requires_grad_(True), 120, 32, pk["alpha0"], pk["alpha1"])
     torch.library.opcheck(torch.ops.jamun_b200.conv.default, args, test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    torch.library.opcheck(torch.ops.jamun_b200.conv_keep.default, args, test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
 
 
 @pytest.mark.parametrize("rows,n_stages,nslots,ncomp,W,mode", [(300, 10, 5, 1, 152, 0), (1000, 6, 2, 3, 32, 0), (77, 65, 1, 1, 120, 1),
