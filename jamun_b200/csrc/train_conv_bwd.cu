@@ -606,6 +606,141 @@ conv_bwd_p2_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ s
     for (int k = 0; k < 65; ++k) dy_op[((size_t)k * rows_pad + j) * 32 + pos] = dy[k];
 }
 
+// ---- the same on the warp-level tensor cores (default) ---------------------------------------------------------------------------
+// Per source j with out-edges q = 0..n-1 (receiver i_q) both sums are small dense products over the source's out-edges:
+//   DH [n x 64]  = DT [n x 32] . Y_j^T [32 x 64]        (dh'_e += ...)         M = edges, N = channels, K = 32
+//   DY [64 x 32] = H^T [64 x n] . DT [n x 32]           (+ bias row: column sums of DT)   M = channels, N = 32, K = edges
+// as mma.sync.m16n8k8 (tf32, three-product split).  One warp per source; DT (<= 32 edges per chunk) and Y_j live in per-warp
+// shared memory, the H^T fragments are read straight from h (each element is used once).  Same fixed summation order for every
+// run: deterministic.
+constexpr int kP2mWarps = 4, kP2mLdY = 36, kP2mLdT = 40;
+__global__ void __launch_bounds__(32 * kP2mWarps, 3)
+conv_bwd_p2_mma_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ src_eid, const int* __restrict__ edst,
+                       const float* __restrict__ h, const float* __restrict__ rhat, const float* __restrict__ y, int y_ld,
+                       const float* __restrict__ gm, int N, int rows_pad, float* __restrict__ dh, float* __restrict__ dy_op) {
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    float* sY = sm + wib * (64 * kP2mLdY + 32 * kP2mLdT + 32);  // [64][36]
+    float* sT = sY + 64 * kP2mLdY;                              // [32][40]  DT, rows >= n zero
+    int* sE = reinterpret_cast<int*>(sT + 32 * kP2mLdT);        // [32]      edge ids of the chunk (-1 beyond n)
+    const int j = blockIdx.x * kP2mWarps + wib;
+    if (j >= N) return;
+    const int s0 = src_rowptr[j], s1 = src_rowptr[j + 1];
+    // Y_j (rows 0..63) -> shared memory
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) sY[k * kP2mLdY + lane] = y[(size_t)j * y_ld + k * JAMUN_V + lane];
+    float accB[4][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) accB[mt][nt][r] = 0.f;
+    float bsum = 0.f;
+    for (int c0 = s0; c0 < s1; c0 += 32) {
+        const int n = s1 - c0 < 32 ? s1 - c0 : 32;
+        __syncwarp();
+        const int e_mine = lane < n ? src_eid[c0 + lane] : -1;
+        sE[lane] = e_mine;
+        // DT rows: lane = w (rows n .. 8 ceil(n/8) - 1 zero; rows beyond hold stale finite values that only reach discarded outputs)
+        const int qpad = ((n + 7) >> 3) << 3;
+#pragma unroll 4
+        for (int q = 0; q < qpad; ++q) {
+            const int e = __shfl_sync(0xffffffffu, e_mine, q);
+            float dT = 0.f;
+            if (e >= 0) {
+                const float4 rh = *reinterpret_cast<const float4*>(rhat + 4 * (size_t)e);
+                const float* gi = gm + (size_t)edst[e] * JAMUN_GATE_IN + JAMUN_S + JAMUN_V;
+                dT = rh.x * gi[lane] + rh.y * gi[JAMUN_V + lane] + rh.z * gi[2 * JAMUN_V + lane];
+            }
+            sT[q * kP2mLdT + lane] = dT;
+            bsum += dT;
+        }
+        __syncwarp();
+        const int mtiles = (n + 15) >> 4, ksteps = (n + 7) >> 3;
+        // ---- DH = DT . Y^T, added to dh
+        for (int mt = 0; mt < mtiles; ++mt) {
+            float acc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+            const float* Ar = sT + (16 * mt + g) * kP2mLdT + tig;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(Ar[8 * ks], ahi[0], alo[0]);
+                split_tf32(Ar[8 * ks + 8 * kP2mLdT], ahi[1], alo[1]);
+                split_tf32(Ar[8 * ks + 4], ahi[2], alo[2]);
+                split_tf32(Ar[8 * ks + 8 * kP2mLdT + 4], ahi[3], alo[3]);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float* Br = sY + (8 * nt + g) * kP2mLdY + 8 * ks + tig;
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(Br[0], bh0, bl0);
+                    split_tf32(Br[4], bh1, bl1);
+                    mma_tf32(acc[nt], alo, bh0, bh1);
+                    mma_tf32(acc[nt], ahi, bl0, bl1);
+                    mma_tf32(acc[nt], ahi, bh0, bh1);
+                }
+            }
+            const int ea = sE[16 * mt + g], eb = sE[16 * mt + g + 8];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                if (ea >= 0) {
+                    float2* o = reinterpret_cast<float2*>(dh + (size_t)ea * JAMUN_EDGE_HID + 8 * nt + 2 * tig);
+                    float2 v = *o;
+                    v.x += acc[nt][0], v.y += acc[nt][1];
+                    *o = v;
+                }
+                if (eb >= 0) {
+                    float2* o = reinterpret_cast<float2*>(dh + (size_t)eb * JAMUN_EDGE_HID + 8 * nt + 2 * tig);
+                    float2 v = *o;
+                    v.x += acc[nt][2], v.y += acc[nt][3];
+                    *o = v;
+                }
+            }
+        }
+        // ---- DY += H^T . DT
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int qa = sE[8 * ks + tig], qb = sE[8 * ks + tig + 4];
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                split_tf32(sT[(8 * ks + tig) * kP2mLdT + 8 * nt + g], bh[nt][0], bl[nt][0]);
+                split_tf32(sT[(8 * ks + tig + 4) * kP2mLdT + 8 * nt + g], bh[nt][1], bl[nt][1]);
+            }
+            const float* ha = h + (size_t)(qa >= 0 ? qa : 0) * JAMUN_EDGE_HID + g;
+            const float* hb = h + (size_t)(qb >= 0 ? qb : 0) * JAMUN_EDGE_HID + g;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                // A[row = channel][col = edge] = h[edge][channel]
+                uint32_t ahi[4], alo[4];
+                split_tf32(qa >= 0 ? ha[16 * mt] : 0.f, ahi[0], alo[0]);
+                split_tf32(qa >= 0 ? ha[16 * mt + 8] : 0.f, ahi[1], alo[1]);
+                split_tf32(qb >= 0 ? hb[16 * mt] : 0.f, ahi[2], alo[2]);
+                split_tf32(qb >= 0 ? hb[16 * mt + 8] : 0.f, ahi[3], alo[3]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mma_tf32(accB[mt][nt], alo, bh[nt][0], bh[nt][1]);
+                    mma_tf32(accB[mt][nt], ahi, bl[nt][0], bl[nt][1]);
+                    mma_tf32(accB[mt][nt], ahi, bh[nt][0], bh[nt][1]);
+                }
+            }
+        }
+    }
+    // dY_j as a stage-major, chunk-swizzled GEMM operand ([65][rows_pad][32])
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int w = 8 * nt + 2 * tig;
+            const int pos = (((w >> 2) ^ (j & 7)) << 2) | (w & 3);
+            const int ka = 16 * mt + g, kb = ka + 8;
+            *reinterpret_cast<float2*>(dy_op + ((size_t)ka * rows_pad + j) * 32 + pos) = make_float2(accB[mt][nt][0], accB[mt][nt][1]);
+            *reinterpret_cast<float2*>(dy_op + ((size_t)kb * rows_pad + j) * 32 + pos) = make_float2(accB[mt][nt][2], accB[mt][nt][3]);
+        }
+    dy_op[((size_t)64 * rows_pad + j) * 32 + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3))] = bsum;
+}
+
 // ---- dx_j = sum over the out-edges of j (ascending edge id) of dxe[e]  (+ extra[j, :n_extra]) ----------------------------------
 __global__ void __launch_bounds__(256)
 conv_bwd_gather_kernel(const int* __restrict__ src_rowptr, const int* __restrict__ src_eid, const float* __restrict__ dxe, int D,
@@ -732,8 +867,27 @@ extern "C" int jamun_conv_bwd_p2(const int* src_rowptr, const int* src_eid, cons
     JB_CHECK_ARG(src_rowptr && src_eid && edst && h && rhat && y && g && dh && dy_op, "null argument");
     JB_CHECK_ARG(N <= rows_pad, "N exceeds rows_pad");
     if (N == 0) return JAMUN_OK;
-    conv_bwd_p2_kernel<<<(N + kP2Warps - 1) / kP2Warps, 32 * kP2Warps, 0, jb::as_stream(stream)>>>(src_rowptr, src_eid, edst, h, rhat, y,
-                                                                                                   y_ld, g, N, rows_pad, dh, dy_op);
+    static const bool use_mma = [] {
+        const char* e = getenv("JAMUN_B200_BWD_P2");  // "simt" selects the CUDA-core kernel (A/B reference)
+        return !(e && strcmp(e, "simt") == 0);
+    }();
+    if (use_mma) {
+        constexpr size_t smem = (size_t)kP2mWarps * (64 * kP2mLdY + 32 * kP2mLdT + 32) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(conv_bwd_p2_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                jb::set_error("jamun_conv_bwd_p2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return JAMUN_ECUDA;
+            }
+            attr_set = true;
+        }
+        conv_bwd_p2_mma_kernel<<<(N + kP2mWarps - 1) / kP2mWarps, 32 * kP2mWarps, smem, jb::as_stream(stream)>>>(
+            src_rowptr, src_eid, edst, h, rhat, y, y_ld, g, N, rows_pad, dh, dy_op);
+    } else {
+        conv_bwd_p2_kernel<<<(N + kP2Warps - 1) / kP2Warps, 32 * kP2Warps, 0, jb::as_stream(stream)>>>(src_rowptr, src_eid, edst, h, rhat,
+                                                                                                       y, y_ld, g, N, rows_pad, dh, dy_op);
+    }
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
