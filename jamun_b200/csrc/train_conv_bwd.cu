@@ -286,8 +286,8 @@ conv_bwd_edge_kernel(const float* __restrict__ x, const int* __restrict__ rowptr
 // lo.hi + hi.lo + hi.hi), done in registers as the fragments are loaded.  tcgen05 is the wrong tool here: its M is 64/128 rows, a
 // receiver has <= 35 edges, and 2 x 91 KB of pre-split dA_i would not fit next to the operands -- measured on the aggregate
 // builder, small SS-mode tcgen05 products retire at ~300 clk each, more than a warp-level m16n8k8 triple per tile costs here.
-// One persistent CTA per SM (16 warps); per batch of <= 32 in-edges the 16 + ceil(NFC/16) tile tasks are dealt round-robin to the
-// warps (product 2 split in four K slices whose partial tiles are summed in slice order: deterministic).  Shared-memory strides
+// One persistent CTA per SM (16 warps); per batch of <= 32 in-edges the tile tasks are dealt one per warp
+// (product 2 split in four K slices whose partial tiles are summed in slice order: deterministic).  Shared-memory strides
 // are chosen so that every fragment load but the product-2 A load (2-way) is conflict-free: LDA = NFC (24 mod 32), LDF = NFC + 4
 // (28 mod 32), LDH = 68.
 // hi = the tf32 the tensor core reads anyway (it ignores the low 13 mantissa bits), lo = the exact remainder (its own low bits are
@@ -322,85 +322,106 @@ struct EdgeMmaCfg {
     static_assert((65 * LDA + 8 + 2 * NB * LDF + NB * LDH + NSL * 64 * LDP) % 4 == 0, "float4 alignment of the rhat slots");
 };
 
-// The tile tasks of one batch with NTILES n-tiles of 8 edges: 0..15 = product 2 (m-tile, K slice), 16.. = product 1 m-tiles.
+// The tile tasks of one batch with NTILES n-tiles of 8 edges, one per warp: warps 0..7 = product 2 (a pair of m-tiles = 32
+// channels, one of four K slices), warps 8..15 = product 1 (ceil(MT1/8) m-tiles -- three = 48 feature columns for the hidden layers --, all eight k-steps).  A task splits
+// its B fragments once per k-step and reuses them for all of its m-tiles; 21.5 / 24 (m-tile, k-step) units per warp.
 template <int S_IN, int V_IN, int NTILES>
 __device__ __forceinline__ void edge_mma_tasks(const float* __restrict__ sA, const float* __restrict__ sF, const float* __restrict__ sH,
                                                float* __restrict__ sDF, float* __restrict__ sP, int warp, int g, int tig) {
     using C = EdgeMmaCfg<S_IN, V_IN>;
     constexpr int NFC = C::NFC, LDA = C::LDA, LDF = C::LDF, LDH = C::LDH, LDP = C::LDP;
-    for (int task = warp; task < 16 + C::MT1; task += C::kThreads / 32) {
-        float acc[NTILES][4];
+    static_assert(C::kThreads == 512 && C::NSL == 4, "one task per warp");
+    if (warp < 8) {
+        const int pair = warp & 1, sl = warp >> 1;
+        const int ks0 = sl * C::KS2 / C::NSL, ks1 = (sl + 1) * C::KS2 / C::NSL;
+        float acc[2][NTILES][4];
 #pragma unroll
-        for (int nt = 0; nt < NTILES; ++nt)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
-        if (task < 16) {
-            const int mt = task & 3, sl = task >> 2;
-            const int ks0 = sl * C::KS2 / C::NSL, ks1 = (sl + 1) * C::KS2 / C::NSL;
-            const float* Ar = sA + (16 * mt + g) * LDA + tig;
-            const float* Br = sF + g * LDF + tig;
-#pragma unroll 2
-            for (int ks = ks0; ks < ks1; ++ks) {
-                uint32_t ahi[4], alo[4];
-                split_tf32(Ar[8 * ks], ahi[0], alo[0]);
-                split_tf32(Ar[8 * ks + 8 * LDA], ahi[1], alo[1]);
-                split_tf32(Ar[8 * ks + 4], ahi[2], alo[2]);
-                split_tf32(Ar[8 * ks + 8 * LDA + 4], ahi[3], alo[3]);
-                uint32_t bh[NTILES][2], bl[NTILES][2];
-#pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) {
-                    split_tf32(Br[8 * nt * LDF + 8 * ks], bh[nt][0], bl[nt][0]);
-                    split_tf32(Br[8 * nt * LDF + 8 * ks + 4], bh[nt][1], bl[nt][1]);
-                }
-                // term by term across the n-tiles: consecutive MMAs never wait on each other's accumulator
-#pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], alo, bh[nt][0], bh[nt][1]);
-#pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bl[nt][0], bl[nt][1]);
-#pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bh[nt][0], bh[nt][1]);
-            }
-            float* P = sP + (sl * 64 + 16 * mt + g) * LDP + 2 * tig;
+            for (int nt = 0; nt < NTILES; ++nt) acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.f;
+        const float* Ar = sA + (32 * pair + g) * LDA + tig;
+        const float* Br = sF + g * LDF + tig;
+        for (int ks = ks0; ks < ks1; ++ks) {
+            uint32_t bh[NTILES][2], bl[NTILES][2];
 #pragma unroll
             for (int nt = 0; nt < NTILES; ++nt) {
-                P[8 * nt] = acc[nt][0], P[8 * nt + 1] = acc[nt][1];
-                P[8 * LDP + 8 * nt] = acc[nt][2], P[8 * LDP + 8 * nt + 1] = acc[nt][3];
+                split_tf32(Br[8 * nt * LDF + 8 * ks], bh[nt][0], bl[nt][0]);
+                split_tf32(Br[8 * nt * LDF + 8 * ks + 4], bh[nt][1], bl[nt][1]);
             }
-        } else {
-            const int f0 = 16 * (task - 16);
-            const float* Ar = sA + tig * LDA + f0 + g;  // A[row = feature][col = channel] = dA[channel][feature]
-            const float* Br = sH + g * LDH + tig;
-#pragma unroll 2
-            for (int ks = 0; ks < 8; ++ks) {
-                uint32_t ahi[4], alo[4];
-                split_tf32(Ar[8 * ks * LDA], ahi[0], alo[0]);
-                split_tf32(Ar[8 * ks * LDA + 8], ahi[1], alo[1]);
-                split_tf32(Ar[(8 * ks + 4) * LDA], ahi[2], alo[2]);
-                split_tf32(Ar[(8 * ks + 4) * LDA + 8], ahi[3], alo[3]);
-                uint32_t bh[NTILES][2], bl[NTILES][2];
 #pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) {
-                    split_tf32(Br[8 * nt * LDH + 8 * ks], bh[nt][0], bl[nt][0]);
-                    split_tf32(Br[8 * nt * LDH + 8 * ks + 4], bh[nt][1], bl[nt][1]);
-                }
+            for (int i = 0; i < 2; ++i) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(Ar[16 * i * LDA + 8 * ks], ahi[0], alo[0]);
+                split_tf32(Ar[(16 * i + 8) * LDA + 8 * ks], ahi[1], alo[1]);
+                split_tf32(Ar[16 * i * LDA + 8 * ks + 4], ahi[2], alo[2]);
+                split_tf32(Ar[(16 * i + 8) * LDA + 8 * ks + 4], ahi[3], alo[3]);
                 // term by term across the n-tiles: consecutive MMAs never wait on each other's accumulator
 #pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], alo, bh[nt][0], bh[nt][1]);
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], alo, bh[nt][0], bh[nt][1]);
 #pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bl[nt][0], bl[nt][1]);
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], ahi, bl[nt][0], bl[nt][1]);
 #pragma unroll
-                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[nt], ahi, bh[nt][0], bh[nt][1]);
-            }
-            // + bias channel (h' = 1), transposed into sDF[edge][feature]
-            const int fa = f0 + g, fb = f0 + g + 8;
-            const float ba = fa < NFC ? sA[64 * LDA + fa] : 0.f, bb = fb < NFC ? sA[64 * LDA + fb] : 0.f;
-#pragma unroll
-            for (int nt = 0; nt < NTILES; ++nt) {
-                float* D = sDF + (8 * nt + 2 * tig) * LDF;
-                if (fa < NFC) D[fa] = acc[nt][0] + ba, D[LDF + fa] = acc[nt][1] + ba;
-                if (fb < NFC) D[fb] = acc[nt][2] + bb, D[LDF + fb] = acc[nt][3] + bb;
+                for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], ahi, bh[nt][0], bh[nt][1]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float* P = sP + (sl * 64 + 32 * pair + 16 * i + g) * LDP + 2 * tig;
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt) {
+                P[8 * nt] = acc[i][nt][0], P[8 * nt + 1] = acc[i][nt][1];
+                P[8 * LDP + 8 * nt] = acc[i][nt][2], P[8 * LDP + 8 * nt + 1] = acc[i][nt][3];
+            }
+        }
+    } else {
+        constexpr int MG = (C::MT1 + 7) / 8;  // m-tiles per product-1 task
+        const int mt0 = MG * (warp - 8);
+        const int nmt = C::MT1 - mt0 < MG ? C::MT1 - mt0 : MG;
+        if (nmt <= 0) return;
+        float acc[MG][NTILES][4];
+#pragma unroll
+        for (int i = 0; i < MG; ++i)
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt) acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.f;
+        const float* Ar = sA + tig * LDA + 16 * mt0 + g;  // A[row = feature][col = channel] = dA[channel][feature]
+        const float* Br = sH + g * LDH + tig;
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t bh[NTILES][2], bl[NTILES][2];
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt) {
+                split_tf32(Br[8 * nt * LDH + 8 * ks], bh[nt][0], bl[nt][0]);
+                split_tf32(Br[8 * nt * LDH + 8 * ks + 4], bh[nt][1], bl[nt][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < MG; ++i)
+                if (i < nmt) {
+                    uint32_t ahi[4], alo[4];
+                    split_tf32(Ar[8 * ks * LDA + 16 * i], ahi[0], alo[0]);
+                    split_tf32(Ar[8 * ks * LDA + 16 * i + 8], ahi[1], alo[1]);
+                    split_tf32(Ar[(8 * ks + 4) * LDA + 16 * i], ahi[2], alo[2]);
+                    split_tf32(Ar[(8 * ks + 4) * LDA + 16 * i + 8], ahi[3], alo[3]);
+#pragma unroll
+                    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], alo, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], ahi, bl[nt][0], bl[nt][1]);
+#pragma unroll
+                    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(acc[i][nt], ahi, bh[nt][0], bh[nt][1]);
+                }
+        }
+        // + bias channel (h' = 1), transposed into sDF[edge][feature]
+#pragma unroll
+        for (int i = 0; i < MG; ++i)
+            if (i < nmt) {
+                const int fa = 16 * (mt0 + i) + g, fb = fa + 8;
+                const float ba = fa < NFC ? sA[64 * LDA + fa] : 0.f, bb = fb < NFC ? sA[64 * LDA + fb] : 0.f;
+#pragma unroll
+                for (int nt = 0; nt < NTILES; ++nt) {
+                    float* D = sDF + (8 * nt + 2 * tig) * LDF;
+                    if (fa < NFC) D[fa] = acc[i][nt][0] + ba, D[LDF + fa] = acc[i][nt][1] + ba;
+                    if (fb < NFC) D[fb] = acc[i][nt][2] + bb, D[LDF + fb] = acc[i][nt][3] + bb;
+                }
+            }
     }
 }
 
