@@ -113,6 +113,102 @@ rowmat_dw_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
         }
 }
 
+// The narrow shapes (a <= 32, b <= 64: the radial MLP's first layer over the ~20 edges per atom) on the warp-level tensor cores:
+// dW [32 x 64] = X^T [32 x rows] . dY [rows x 64] as mma.sync.m16n8k8 (tf32 operands, fp32 accumulate, three-product split
+// hi = v & 0xFFFFE000, lo = v - hi for fp32 accuracy) with the rows as the K dimension.  The fragments are read straight from
+// global memory (every element is used once; a load instruction covers four rows x 32 bytes).  A warp accumulates the whole
+// product over its k-steps (ascending), the eight warps of a CTA are summed in warp order: deterministic.
+__device__ __forceinline__ void dw_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void dw_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256)
+rowmat_dw_mma_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, float* __restrict__ partial, int rows,
+                     const int* __restrict__ rows_dev, int a, int b, int rows_per_split) {
+    __shared__ float red[4][32 * 64];  // warps 4..7 deposit first, warps 0..3 add theirs on top: fixed order
+    if (rows_dev) rows = min(rows, *rows_dev);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const int n_begin = blockIdx.x * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    for (int r0 = n_begin + 8 * warp; r0 < n_end; r0 += 64) {
+        const int ra = r0 + tig, rb = r0 + tig + 4;
+        const bool ona = ra < n_end, onb = rb < n_end;
+        const float* xa = X + (size_t)ra * ldx;
+        const float* xb = X + (size_t)rb * ldx;
+        const float* ya = dY + (size_t)ra * ldy;
+        const float* yb = dY + (size_t)rb * ldy;
+        // A[m = column of X][k = row]: a0 = (g, tig), a1 = (g + 8, tig), a2 = (g, tig + 4), a3 = (g + 8, tig + 4)
+        float av[2][4], bv[8][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int c0 = 16 * mt + g, c1 = c0 + 8;
+            av[mt][0] = (ona && c0 < a) ? xa[c0] : 0.f;
+            av[mt][1] = (ona && c1 < a) ? xa[c1] : 0.f;
+            av[mt][2] = (onb && c0 < a) ? xb[c0] : 0.f;
+            av[mt][3] = (onb && c1 < a) ? xb[c1] : 0.f;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = 8 * nt + g;
+            bv[nt][0] = (ona && c < b) ? ya[c] : 0.f;
+            bv[nt][1] = (onb && c < b) ? yb[c] : 0.f;
+        }
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dw_split(av[mt][q], ahi[mt][q], alo[mt][q]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            dw_split(bv[nt][0], bh0, bl0);
+            dw_split(bv[nt][1], bh1, bl1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                dw_mma(acc[mt][nt], alo[mt], bh0, bh1);
+                dw_mma(acc[mt][nt], ahi[mt], bl0, bl1);
+                dw_mma(acc[mt][nt], ahi[mt], bh0, bh1);
+            }
+        }
+    }
+    // D[m][n]: c0 = (g, 2 tig), c1 = (g, 2 tig + 1), c2 = (g + 8, 2 tig), c3 = (g + 8, 2 tig + 1)
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        if ((warp >> 2) == 1 - round) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float* r = red[warp & 3] + (16 * mt + g) * 64 + 8 * nt + 2 * tig;
+                    if (round == 0) {
+                        r[0] = acc[mt][nt][0], r[1] = acc[mt][nt][1];
+                        r[8 * 64] = acc[mt][nt][2], r[8 * 64 + 1] = acc[mt][nt][3];
+                    } else {
+                        r[0] += acc[mt][nt][0], r[1] += acc[mt][nt][1];
+                        r[8 * 64] += acc[mt][nt][2], r[8 * 64 + 1] += acc[mt][nt][3];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < a * b; t += 256) {
+        const int k = t / b, c = t - k * b;
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sum += red[w][k * 64 + c];
+        partial[(size_t)blockIdx.x * a * b + t] = sum;
+    }
+}
+
 __global__ void rowmat_dw_reduce_kernel(const float* __restrict__ partial, int splits, int a, int b, float* __restrict__ dW, int lddw,
                                         int transW, int accumulate) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,6 +294,8 @@ extern "C" int jamun_rowmat_dw(const float* X, int ldx, const float* dY, int ldy
         const int ri = (a + 15) / 16, rj = (b + 15) / 16;
 #define JB_DW(RI, RJ) rowmat_dw_kernel<RI, RJ><<<splits, 256, 0, s>>>(X, ldx, dY, ldy, scratch, rows, rows_dev, a, b, per)
         if (ri <= 2 && rj <= 2) JB_DW(2, 2);
+        else if (ri <= 2 && rj <= 4 && rows >= 65536)  // many rows (edges): tensor-core kernel
+            rowmat_dw_mma_kernel<<<splits, 256, 0, s>>>(X, ldx, dY, ldy, scratch, rows, rows_dev, a, b, per);
         else if (ri <= 2 && rj <= 4) JB_DW(2, 4);
         else if (ri <= 4 && rj <= 4) JB_DW(4, 4);
         else if (ri <= 2) JB_DW(2, 8);

@@ -393,3 +393,23 @@ def test_stage_atb_tensor_core_matches_simt_and_fp64(rows, n_stages, nslots, nco
     for impl in ("simt", "tc"):
         assert torch.isfinite(outs[impl]).all(), impl
         assert (outs[impl].double() - want).abs().max().item() <= 3e-5 * scale, impl
+
+
+@pytest.mark.parametrize("rows,a,b,live", [(70_001, 32, 64, 66_003), (200, 32, 64, 200), (3000, 120, 120, 2500), (70_000, 20, 40, 70_000)])
+def test_rowmat_dw_shapes_vs_fp64(rows, a, b, live):
+    """dW = X^T . dY: the register-tiled CUDA-core kernel and, for narrow shapes with many rows (the radial MLP over the edges),
+    the tensor-core kernel -- device-side row count, column offsets, ragged tails, bit-reproducible."""
+    from jamun_b200 import ops
+
+    gen = torch.Generator().manual_seed(rows + a)
+    X = torch.randn(rows, a + 5, generator=gen).cuda()
+    dY = torch.randn(rows, b + 3, generator=gen).cuda()
+    rows_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    dW = torch.empty(a, b, device="cuda")
+    ops.rowmat_dw(X, 2, dY, 1, dW, 0, a, b, rows=rows, rows_dev=rows_dev)
+    want = X[:live, 2:2 + a].double().T @ dY[:live, 1:1 + b].double()
+    scale = want.abs().max().item()
+    assert (dW.double() - want).abs().max().item() <= 2e-5 * scale
+    dW2 = torch.empty(a, b, device="cuda")
+    ops.rowmat_dw(X, 2, dY, 1, dW2, 0, a, b, rows=rows, rows_dev=rows_dev)
+    assert torch.equal(dW, dW2)
