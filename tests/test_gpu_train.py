@@ -52,12 +52,18 @@ def _close(got, want, tol, what):
     assert err <= tol * scale + 1e-9, f"{what}: err {err:.3e} scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("layer", [0, 1])
-def test_conv_operator_forward_and_backward_vs_torch(models, layer):
+@pytest.mark.parametrize("layer,sizes", [(0, [22, 15, 9, 30, 1, 2]), (1, [22, 15, 9, 30, 1, 2]), (1, [150, 40])])
+def test_conv_operator_forward_and_backward_vs_torch(models, layer, sizes):
+    """[150, 40]: a dense graph -- in-degrees beyond 32 (neighbour cap + bonded edges), so the per-edge backward takes a second
+    batch per receiver and sources have more than 32 out-edges."""
     import jamun_b200.autograd_ops  # noqa: F401
 
-    o32, prod, t, y, batch, yb = _setup(models, [22, 15, 9, 30, 1, 2])
+    o32, prod, t, y, batch, yb = _setup(models, sizes)
     topo, ctx, p = _graph(prod, yb)
+    if len(sizes) == 2:
+        deg = (topo.rowptr[1:] - topo.rowptr[:-1]).max().item()
+        outdeg = (topo.src_rowptr[1:] - topo.src_rowptr[:-1]).max().item()
+        assert deg > 32 and outdeg > 32, (deg, outdeg)
     g = prod.arch_module
     blk = [g.initial_projector, *g.layers][layer]
     pk = blk.pack(g.embed_bondedness.weight)
