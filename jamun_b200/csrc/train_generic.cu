@@ -7,6 +7,9 @@
 //   jamun_colsum      out[c] (+)= sum_n M[n, c]           (bias-like gradients, per-irrep scale gradients)
 // Reductions over rows run in a fixed order (row chunks -> partial sums -> ascending final sum): results are bit-reproducible.
 // `rows_dev` (optional) is a device-side row count (e.g. rowptr + N for the live edge count) clamped to `rows`.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -59,6 +62,101 @@ rowmat_mul_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
         for (int q = 0; q < kMaxB / 8; ++q)
             if (cg + 8 * q < b) y[cg + 8 * q] = accumulate ? y[cg + 8 * q] + acc[q] : acc[q];
     }
+}
+
+// ---- Y = X . W on the warp-level tensor cores ------------------------------------------------------------------------------------
+// mma.sync.m16n8k8 (tf32 operands, fp32 accumulate) with the three-product split (hi = v & 0xFFFFE000, lo = v - hi: fp32
+// accuracy).  One CTA = 128 rows (a warp per 16 rows, N tiles of 8 columns, NT = ceil(b/8) accumulators per warp).  W is staged
+// once per CTA into shared memory, K-major with a row stride of 8 mod 32 floats (conflict-free B fragments); the A fragments come
+// straight from X (a load instruction covers eight rows x 16 bytes, both halves of every 32-byte sector are used by the
+// instruction pair).  Used when there are enough rows to pay for staging W (rows >= 2048); a <= 160, b <= 160.
+__device__ __forceinline__ void mm_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mm_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int NT>
+__global__ void __launch_bounds__(256)
+rowmat_mul_mma_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, int transW, float* __restrict__ Y,
+                      int ldy, int rows, const int* __restrict__ rows_dev, int a, int b, int accumulate) {
+    constexpr int LDW = 8 * NT + (8 * NT % 32 == 8 ? 0 : (40 - 8 * NT % 32) % 32);  // >= 8 NT, == 8 (mod 32)
+    extern __shared__ __align__(16) float mm_sm[];  // [a_pad][LDW], rows a..a_pad-1 and columns b.. zero
+    if (rows_dev) rows = min(rows, *rows_dev);
+    const int row0 = blockIdx.x * 128;
+    if (row0 >= rows) return;
+    const int a_pad = (a + 7) & ~7;
+    for (int t = threadIdx.x; t < a_pad * LDW; t += 256) {
+        const int k = t / LDW, j = t - k * LDW;
+        float v = 0.f;
+        if (k < a && j < b) v = transW ? W[(size_t)j * ldw + k] : W[(size_t)k * ldw + j];
+        mm_sm[t] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const int ra = row0 + 16 * warp + g, rb = ra + 8;
+    if (row0 + 16 * warp >= rows) return;
+    const bool ona = ra < rows, onb = rb < rows;
+    const float* xa = X + (size_t)ra * ldx;
+    const float* xb = X + (size_t)rb * ldx;
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    for (int k0 = 0; k0 < a_pad; k0 += 8) {
+        const int ka = k0 + tig, kb = ka + 4;
+        uint32_t ahi[4], alo[4];
+        mm_split((ona && ka < a) ? xa[ka] : 0.f, ahi[0], alo[0]);
+        mm_split((onb && ka < a) ? xb[ka] : 0.f, ahi[1], alo[1]);
+        mm_split((ona && kb < a) ? xa[kb] : 0.f, ahi[2], alo[2]);
+        mm_split((onb && kb < a) ? xb[kb] : 0.f, ahi[3], alo[3]);
+        const float* Br = mm_sm + ka * LDW + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh0, bl0, bh1, bl1;
+            mm_split(Br[8 * nt], bh0, bl0);
+            mm_split(Br[4 * LDW + 8 * nt], bh1, bl1);
+            mm_mma(acc[nt], alo, bh0, bh1);
+            mm_mma(acc[nt], ahi, bl0, bl1);
+            mm_mma(acc[nt], ahi, bh0, bh1);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int c = 8 * nt + 2 * tig;
+        if (ona) {
+            float* y = Y + (size_t)ra * ldy + c;
+            if (c < b) y[0] = accumulate ? y[0] + acc[nt][0] : acc[nt][0];
+            if (c + 1 < b) y[1] = accumulate ? y[1] + acc[nt][1] : acc[nt][1];
+        }
+        if (onb) {
+            float* y = Y + (size_t)rb * ldy + c;
+            if (c < b) y[0] = accumulate ? y[0] + acc[nt][2] : acc[nt][2];
+            if (c + 1 < b) y[1] = accumulate ? y[1] + acc[nt][3] : acc[nt][3];
+        }
+    }
+}
+
+template <int NT>
+int launch_rowmat_mul_mma(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int rows, const int* rows_dev,
+                          int a, int b, int accumulate, cudaStream_t s) {
+    constexpr int LDW = 8 * NT + (8 * NT % 32 == 8 ? 0 : (40 - 8 * NT % 32) % 32);
+    static_assert(LDW % 32 == 8 && LDW >= 8 * NT, "row stride of the staged W");
+    constexpr size_t smem = (size_t)160 * LDW * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rowmat_mul_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            jb::set_error("jamun_rowmat_mul: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return JAMUN_ECUDA;
+        }
+        attr_set = true;
+    }
+    const size_t need = (size_t)((a + 7) & ~7) * LDW * sizeof(float);
+    rowmat_mul_mma_kernel<NT><<<(rows + 127) / 128, 256, need, s>>>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate);
+    return JAMUN_OK;
 }
 
 // ---- dW = X^T . dY over a chunk of rows -------------------------------------------------------------------------------------
@@ -272,8 +370,22 @@ extern "C" int jamun_rowmat_mul(const float* X, int ldx, const float* W, int ldw
     JB_CHECK_ARG(X && W && Y, "null argument");
     JB_CHECK_ARG(a >= 1 && b >= 1 && b <= kMaxB, "b must be in [1, 160]");
     if (rows == 0) return JAMUN_OK;
-    rowmat_mul_kernel<<<(rows + 31) / 32, 256, 0, jb::as_stream(stream)>>>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b,
-                                                                           accumulate);
+    cudaStream_t s = jb::as_stream(stream);
+    static const bool use_mma = [] {
+        const char* e = getenv("JAMUN_B200_ROWMAT");  // "simt" keeps the CUDA-core kernel for every size (A/B reference)
+        return !(e && strcmp(e, "simt") == 0);
+    }();
+    if (use_mma && rows >= 2048 && a <= 160) {
+        const int nt = (b + 7) / 8;
+        int rc;
+        if (nt <= 4) rc = launch_rowmat_mul_mma<4>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate, s);
+        else if (nt <= 8) rc = launch_rowmat_mul_mma<8>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate, s);
+        else if (nt <= 15) rc = launch_rowmat_mul_mma<15>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate, s);
+        else rc = launch_rowmat_mul_mma<20>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate, s);
+        if (rc != JAMUN_OK) return rc;
+    } else {
+        rowmat_mul_kernel<<<(rows + 31) / 32, 256, 0, s>>>(X, ldx, W, ldw, transW, Y, ldy, rows, rows_dev, a, b, accumulate);
+    }
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }

@@ -419,3 +419,25 @@ def test_rowmat_dw_shapes_vs_fp64(rows, a, b, live):
     dW2 = torch.empty(a, b, device="cuda")
     ops.rowmat_dw(X, 2, dY, 1, dW2, 0, a, b, rows=rows, rows_dev=rows_dev)
     assert torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("rows,a,b,trans,acc,live", [(5000, 120, 120, False, False, 5000), (4101, 56, 120, True, True, 3999),
+                                                      (2048, 32, 32, False, True, 2048), (9000, 152, 160, True, False, 9000),
+                                                      (300, 120, 120, False, False, 300), (70_000, 64, 64, False, False, 66_000)])
+def test_rowmat_mul_shapes_vs_fp64(rows, a, b, trans, acc, live):
+    """Y (+)= X . W: the tensor-core kernel (>= 2048 rows) and the CUDA-core kernel -- transposed weights, accumulation,
+    column offsets, ragged rows / columns, device-side row count; rows beyond the live count untouched."""
+    from jamun_b200 import ops
+
+    gen = torch.Generator().manual_seed(rows + a + b)
+    X = torch.randn(rows, a + 3, generator=gen).cuda()
+    W = (torch.randn(b, a + 2, generator=gen) if trans else torch.randn(a, b + 2, generator=gen)).cuda()
+    Y0 = torch.randn(rows, b + 4, generator=gen).cuda()
+    Y = Y0.clone()
+    rows_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    ops.rowmat_mul(X, 1, W, 2 if trans else 1, Y, 3, a, b, trans_w=trans, accumulate=acc, rows=rows, rows_dev=rows_dev)
+    Wm = W[:, 2:2 + a].T if trans else W[:, 1:1 + b]
+    want = X[:live, 1:1 + a].double() @ Wm.double() + (Y0[:live, 3:3 + b].double() if acc else 0.0)
+    scale = want.abs().max().item()
+    assert (Y[:live, 3:3 + b].double() - want).abs().max().item() <= 2e-5 * scale
+    assert torch.equal(Y[live:], Y0[live:]) and torch.equal(Y[:, :3], Y0[:, :3]) and torch.equal(Y[:, 3 + b:], Y0[:, 3 + b:])
