@@ -2,6 +2,9 @@
 // backward, noise-conditioning MLP backward, the denoising loss (forward + backward) and the batched Kabsch alignment.
 // Reference: /root/reference/src/jamun/model/denoiser.py:87-109,219-319 (noise, align, loss, training_step),
 // utils/align.py:9-56 (Kabsch), e3tools/nn/_gate.py:63, _interaction.py:26-30, model/noise_conditioning.py:27-73.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -129,6 +132,84 @@ __global__ void radial_bwd_kernel(const float* __restrict__ rb, const unsigned c
         for (int k = 0; k < JAMUN_NBASIS; ++k) z = fmaf(r[k], ws[k][o], z);
         const float sg = sigmoidf_acc(z);
         dz[t] = dh[t] * sg * (1.f + z * (1.f - sg));
+    }
+}
+
+// The same with z on the warp-level tensor cores: mma.sync.m16n8k8 (tf32 operands, fp32 accumulate, three-product split
+// hi = v & 0xFFFFE000, lo = v - hi for fp32 accuracy).  A warp owns 16 edges per pass (A fragments straight from rb), the weight
+// is staged once per CTA (row stride 72: conflict-free B fragments); the epilogue reads dh and writes dz as float2 pairs.
+__device__ __forceinline__ void rbw_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void rbw_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256)
+radial_bwd_mma_kernel(const float* __restrict__ rb, const unsigned char* __restrict__ ebond, const int* __restrict__ rowptr, int N,
+                      const float* __restrict__ w0r, const float* __restrict__ b0eff, const float* __restrict__ dh,
+                      float* __restrict__ dz) {
+    constexpr int LDW = JAMUN_EDGE_HID + 8;
+    __shared__ float ws[JAMUN_NBASIS * LDW];
+    __shared__ float bs[2 * JAMUN_EDGE_HID];
+    for (int t = threadIdx.x; t < JAMUN_NBASIS * JAMUN_EDGE_HID; t += 256) ws[(t / JAMUN_EDGE_HID) * LDW + t % JAMUN_EDGE_HID] = w0r[t];
+    for (int t = threadIdx.x; t < 2 * JAMUN_EDGE_HID; t += 256) bs[t] = b0eff[t];
+    __syncthreads();
+    const int E = rowptr[N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    for (int e0 = 16 * (blockIdx.x * 8 + warp); e0 < E; e0 += 16 * 8 * gridDim.x) {
+        const int ra = e0 + g, rbi = ra + 8;
+        const bool ona = ra < E, onb = rbi < E;
+        const float* pa = rb + (size_t)ra * JAMUN_NBASIS + tig;
+        const float* pb = rb + (size_t)rbi * JAMUN_NBASIS + tig;
+        float av[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            av[ks][0] = ona ? pa[8 * ks] : 0.f;
+            av[ks][1] = onb ? pb[8 * ks] : 0.f;
+            av[ks][2] = ona ? pa[8 * ks + 4] : 0.f;
+            av[ks][3] = onb ? pb[8 * ks + 4] : 0.f;
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rbw_split(av[ks][q], ahi[q], alo[q]);
+            const float* Br = ws + (8 * ks + tig) * LDW + g;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                uint32_t bh0, bl0, bh1, bl1;
+                rbw_split(Br[8 * nt], bh0, bl0);
+                rbw_split(Br[4 * LDW + 8 * nt], bh1, bl1);
+                rbw_mma(acc[nt], alo, bh0, bh1);
+                rbw_mma(acc[nt], ahi, bl0, bl1);
+                rbw_mma(acc[nt], ahi, bh0, bh1);
+            }
+        }
+        const float* ba = bs + ((ona && ebond[ra]) ? JAMUN_EDGE_HID : 0) + 2 * tig;
+        const float* bb = bs + ((onb && ebond[rbi]) ? JAMUN_EDGE_HID : 0) + 2 * tig;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (ona) {
+                const size_t o = (size_t)ra * JAMUN_EDGE_HID + 8 * nt + 2 * tig;
+                const float2 d = *reinterpret_cast<const float2*>(dh + o);
+                const float z0 = acc[nt][0] + ba[8 * nt], z1 = acc[nt][1] + ba[8 * nt + 1];
+                const float s0 = sigmoidf_acc(z0), s1 = sigmoidf_acc(z1);
+                *reinterpret_cast<float2*>(dz + o) = make_float2(d.x * s0 * (1.f + z0 * (1.f - s0)), d.y * s1 * (1.f + z1 * (1.f - s1)));
+            }
+            if (onb) {
+                const size_t o = (size_t)rbi * JAMUN_EDGE_HID + 8 * nt + 2 * tig;
+                const float2 d = *reinterpret_cast<const float2*>(dh + o);
+                const float z0 = acc[nt][2] + bb[8 * nt], z1 = acc[nt][3] + bb[8 * nt + 1];
+                const float s0 = sigmoidf_acc(z0), s1 = sigmoidf_acc(z1);
+                *reinterpret_cast<float2*>(dz + o) = make_float2(d.x * s0 * (1.f + z0 * (1.f - s0)), d.y * s1 * (1.f + z1 * (1.f - s1)));
+            }
+        }
     }
 }
 
@@ -502,8 +583,18 @@ extern "C" int jamun_radial_bwd(const float* rb, const unsigned char* ebond, con
                                 const float* b0eff, const float* dh, float* dz, jamun_stream_t stream) {
     JB_CHECK_ARG(rb && ebond && rowptr && w0r && b0eff && dh && dz, "null argument");
     if (N == 0 || cap == 0) return JAMUN_OK;
-    radial_bwd_kernel<<<ew_blocks((size_t)cap * JAMUN_EDGE_HID), 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, dh,
-                                                                                                  dz);
+    static const bool use_mma = [] {
+        const char* e = getenv("JAMUN_B200_RADIAL_BWD");  // "simt" selects the CUDA-core kernel (A/B reference)
+        return !(e && strcmp(e, "simt") == 0);
+    }();
+    if (use_mma) {
+        int blocks = (cap + 127) / 128;
+        if (blocks > jb::kNumSMs * 8) blocks = jb::kNumSMs * 8;
+        radial_bwd_mma_kernel<<<blocks, 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, dh, dz);
+    } else {
+        radial_bwd_kernel<<<ew_blocks((size_t)cap * JAMUN_EDGE_HID), 256, 0, jb::as_stream(stream)>>>(rb, ebond, rowptr, N, w0r, b0eff, dh,
+                                                                                                      dz);
+    }
     JB_CHECK_LAUNCH();
     return JAMUN_OK;
 }
