@@ -261,10 +261,13 @@ def _conv_keep_setup(ctx, inputs, output):
     _, a_ws, inv_deg, y = output
     ctx.save_for_backward(x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, a_ws, inv_deg, y)
     ctx.consts = (s_in, v_in, alpha0, alpha1)
+    ctx.set_materialize_grads(False)  # no zero-filled 3.2 GB "gradients" for the kept operands, which nothing differentiates
 
 
 def _conv_keep_backward(ctx, dout, da, dinv, dy):
     x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, a_ws, inv_deg, y = ctx.saved_tensors
+    if dout is None:
+        dout = torch.zeros(x.shape[0], GIN, dtype=x.dtype, device=x.device)
     dx, dh, dm0, dm1 = torch.ops.jamun_b200.conv_bwd(dout, x, h, rhat, rowptr, col, edst, src_rowptr, src_eid, m0, m1, *ctx.consts,
                                                      a_ws, inv_deg, y)
     return dx, dh, None, None, None, None, None, None, dm0, dm1, None, None, None, None
