@@ -51,3 +51,7 @@ def convert_to_one_letter_code(aa: str) -> str:
     if len(aa) == 3 and aa in ResidueMetadata.AA_1CODES:
         return ResidueMetadata.AA_1CODES[aa]
     raise ValueError(f"Invalid amino acid code: {aa}")
+
+
+def convert_to_one_letter_codes(peptide: str) -> str:
+    return peptide if "_" not in peptide else "".join(convert_to_one_letter_code(aa) for aa in peptide.split("_"))

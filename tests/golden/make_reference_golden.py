@@ -16,6 +16,8 @@ What runs here is the unmodified code under /root/reference/src/jamun, loaded fi
                                          noise_and_compute_loss
     model/noise_conditioning.py          NoiseConditionalScaling.scale_predictor, NoiseConditionalSkipConnection weights
     model/atom_embedding.py              AtomEmbeddingWithResidueInformation.forward
+    utils/residue_metadata.py            vocabulary tables, encode_* and convert_* helpers (the embedding-row order of checkpoints)
+    utils/average_squared_distance.py    compute_distance_matrix, compute_average_squared_distance (numpy)
 
 The reference's third-party dependencies are absent here (e3nn, torch_geometric, torch_scatter, torch_cluster, lightning),
 so the interpreter gets *stand-ins for the containers and primitives only* (listed in `install_stand_ins`): a Data/Batch
@@ -166,8 +168,10 @@ def install_stand_ins():
     _module("torch_scatter", scatter_mean=scatter_mean, scatter_sum=scatter_sum)
     o3 = _module("e3nn.o3", Irreps=Irreps, ElementwiseTensorProduct=_NotExecuted)
     _module("e3nn", o3=o3)
-    plm = _module("lightning.pytorch", LightningModule=LightningModule)
+    plu = _module("lightning.pytorch.utilities", rank_zero_only=lambda f: f)
+    plm = _module("lightning.pytorch", LightningModule=LightningModule, LightningDataModule=object, Trainer=object, utilities=plu)
     _module("lightning", pytorch=plm)
+    _module("hydra")
 
 
 def load_reference():
@@ -203,6 +207,8 @@ def load_reference():
         denoiser=load("jamun.model.denoiser", "model/denoiser.py"),
         noise=load("jamun.model.noise_conditioning", "model/noise_conditioning.py"),
         embed=load("jamun.model.atom_embedding", "model/atom_embedding.py"),
+        meta=load("jamun.utils.residue_metadata", "utils/residue_metadata.py"),
+        asd=load("jamun.utils.average_squared_distance", "utils/average_squared_distance.py"),
     )
     return ref
 
@@ -363,6 +369,28 @@ def main():
         out[f"embed_sd.{k}"] = v.numpy()
     for k, v in idx.items():
         out[f"embed_idx.{k}"] = v.numpy()
+
+    # ---- 7. vocabulary (utils/residue_metadata.py): the order of these lists is the embedding-row order of released checkpoints
+    M = ref.meta.ResidueMetadata
+    out["meta_atom_types"], out["meta_atom_codes"], out["meta_residue_codes"] = (np.array(v) for v in (M.ATOM_TYPES, M.ATOM_CODES, M.RESIDUE_CODES))
+    out["meta_aa3_keys"], out["meta_aa3_values"] = np.array(list(M.AA_3CODES.keys())), np.array(list(M.AA_3CODES.values()))
+    probes = ["C", "O", "N", "F", "S", "H", "CA", "CB", "CG", "OXT", "ALA", "NME", "ACE", "HOH", "XYZ", ""]
+    out["meta_probes"] = np.array(probes)
+    out["meta_enc_type"] = np.array([ref.meta.encode_atom_type(p) for p in probes])
+    out["meta_enc_code"] = np.array([ref.meta.encode_atom_code(p) for p in probes])
+    out["meta_enc_res"] = np.array([ref.meta.encode_residue(p) for p in probes])
+    peptides = ["AKT", "ala_LYS_thr", "W", "GLY", "ACDEFGHIKLMNPQRSTVWY"]
+    out["meta_peptides"] = np.array(peptides)
+    out["meta_three"] = np.array([ref.meta.convert_to_three_letter_codes(p) for p in peptides])
+    out["meta_one"] = np.array([ref.meta.convert_to_one_letter_codes(p) for p in peptides])
+
+    # ---- 8. average squared distance (utils/average_squared_distance.py:153-178), per chain, with and without a cut-off
+    xs = x.numpy().astype(np.float64)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    cuts = [None, 0.4, 1.0]
+    out["asd_cutoffs"] = np.array([-1.0 if c is None else c for c in cuts])
+    out["asd_values"] = np.array([[ref.asd.compute_average_squared_distance(xs[offs[c]:offs[c + 1]], cutoff=cut) if sizes[c] > 1 else np.nan
+                                   for c in range(len(sizes))] for cut in cuts])
 
     path = os.path.join(HERE, "reference_exec.npz")
     np.savez_compressed(path, **out)

@@ -187,3 +187,25 @@ def test_noise_mlp_and_embedding_kernels_equal_reference(gold):
     idx = {k: v.cuda() for k, v in sd("embed_idx.").items()}
     got = emb(data.Data(**idx))
     _close(got, gold["embed_out"], 0, 0, "embedding")
+
+
+def test_average_squared_distance_kernel_equals_reference(gold):
+    """jamun_avg_sq_dist against utils/average_squared_distance.py (numpy, executed from the reference): per chain, with and
+    without a cut-off, and the batched mean over graphs."""
+    from jamun_b200.utils import compute_average_squared_distance
+
+    sizes, _, chain_ptr = _chains(gold)
+    x = C(gold["train_x"])
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for cut, want in zip(gold["asd_cutoffs"], gold["asd_values"]):
+        cutoff = None if cut < 0 else float(cut)
+        per_chain = []
+        for c, n in enumerate(sizes):
+            if n < 2:
+                continue
+            got = compute_average_squared_distance(x[offs[c]:offs[c + 1]], cutoff)
+            assert abs(got - want[c]) <= 1e-5 * max(1.0, abs(want[c])), (cut, c, got, want[c])
+            per_chain.append(want[c])
+        # batched form: the mean over graphs (a single-atom graph contributes 0 pairs -> 0, as max(count, 1) in the kernel)
+        got_all = compute_average_squared_distance(x, cutoff, chain_ptr=chain_ptr)
+        assert abs(got_all - sum(per_chain) / len(sizes)) <= 1e-5

@@ -143,3 +143,24 @@ def test_noise_conditioning_and_embedding_equal_reference(gold):
                       edge_index=torch.zeros(2, 0, dtype=torch.long), **idx)
     with torch.no_grad():
         assert torch.equal(emb(b), T(gold["embed_out"]))
+
+
+def test_vocabulary_and_name_helpers_equal_reference(gold):
+    """jamun_b200.utils.residue_metadata (host logic of the product, not the oracle) against the reference's own tables and
+    helpers: the list order is the embedding-row order a released checkpoint learned."""
+    from jamun_b200.utils import residue_metadata as RM
+
+    M = RM.ResidueMetadata
+    assert M.ATOM_TYPES == list(gold["meta_atom_types"]) and M.ATOM_CODES == list(gold["meta_atom_codes"])
+    assert M.RESIDUE_CODES == list(gold["meta_residue_codes"])
+    assert list(M.AA_3CODES.keys()) == list(gold["meta_aa3_keys"]) and list(M.AA_3CODES.values()) == list(gold["meta_aa3_values"])
+    probes = [str(p) for p in gold["meta_probes"]]
+    assert [RM.encode_atom_type(p) for p in probes] == list(gold["meta_enc_type"])
+    assert [RM.encode_atom_code(p) for p in probes] == list(gold["meta_enc_code"])
+    assert [RM.encode_residue(p) for p in probes] == list(gold["meta_enc_res"])
+    peptides = [str(p) for p in gold["meta_peptides"]]
+    assert [RM.convert_to_three_letter_codes(p) for p in peptides] == list(gold["meta_three"])
+    assert [RM.convert_to_one_letter_codes(p) for p in peptides] == list(gold["meta_one"])
+    for bad in ("B", "XYZ", "ALAA"):
+        with pytest.raises(ValueError):
+            RM.convert_to_three_letter_code(bad)
