@@ -8,5 +8,5 @@ package at the repo root) resolves the reference's own ``jamun.*`` names to thes
 """
 __version__ = "0.1.0"
 
-from . import data, distributions, e3tools, irreps, model, sampling, synthetic, utils  # noqa: E402,F401
+from . import data, distributions, e3tools, irreps, lr_schedules, model, sampling, synthetic, utils  # noqa: E402,F401
 from .factory import default_arch, default_denoiser  # noqa: E402,F401

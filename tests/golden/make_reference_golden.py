@@ -18,6 +18,8 @@ What runs here is the unmodified code under /root/reference/src/jamun, loaded fi
     model/atom_embedding.py              AtomEmbeddingWithResidueInformation.forward
     utils/residue_metadata.py            vocabulary tables, encode_* and convert_* helpers (the embedding-row order of checkpoints)
     utils/average_squared_distance.py    compute_distance_matrix, compute_average_squared_distance (numpy)
+    distributions/_distributions.py      every sigma / measurement distribution (seeded samples)
+    lr_schedules/_lr_schedules.py        the three LambdaLR multipliers
 
 The reference's third-party dependencies are absent here (e3nn, torch_geometric, torch_scatter, torch_cluster, lightning),
 so the interpreter gets *stand-ins for the containers and primitives only* (listed in `install_stand_ins`): a Data/Batch
@@ -209,6 +211,8 @@ def load_reference():
         embed=load("jamun.model.atom_embedding", "model/atom_embedding.py"),
         meta=load("jamun.utils.residue_metadata", "utils/residue_metadata.py"),
         asd=load("jamun.utils.average_squared_distance", "utils/average_squared_distance.py"),
+        dist=load("jamun.distributions._distributions", "distributions/_distributions.py"),
+        lr=load("jamun.lr_schedules._lr_schedules", "lr_schedules/_lr_schedules.py"),
     )
     return ref
 
@@ -391,6 +395,26 @@ def main():
     out["asd_cutoffs"] = np.array([-1.0 if c is None else c for c in cuts])
     out["asd_values"] = np.array([[ref.asd.compute_average_squared_distance(xs[offs[c]:offs[c + 1]], cutoff=cut) if sizes[c] > 1 else np.nan
                                    for c in range(len(sizes))] for cut in cuts])
+
+    # ---- 9. sigma / measurement distributions (distributions/_distributions.py): samples under torch.manual_seed(123)
+    D = ref.dist
+    makers = {"constant": lambda m: m.ConstantSigma(0.04), "uniform": lambda m: m.UniformSigma(0.5, 0.01),
+              "exponential": lambda m: m.ExponentialSigma(50.0, 1e-2), "lognormal": lambda m: m.ClippedLogNormalSigma(-1.2, 1.5, 2.0),
+              "uniform_plus_normal": lambda m: m.UniformPlusNormal(0.3, (4, 3)),
+              "uniform_measurement": lambda m: m.UniformMeasurement(0.5, 4),
+              "weighted_measurement": lambda m: m.WeightedMeasurement(0.5, torch.tensor([0.1, 0.2, 0.3, 0.4]))}
+    for name, mk in makers.items():
+        torch.manual_seed(123)
+        d = mk(D)
+        out[f"dist_{name}"] = torch.stack([d.sample() for _ in range(5)] + [d.sample((3,))[i] for i in range(3)]).numpy()
+    out["dist_measurement_mean"] = D.WeightedMeasurement(0.5, torch.tensor([0.1, 0.2, 0.3, 0.4])).mean.numpy()
+
+    # ---- 10. LR multipliers (lr_schedules/_lr_schedules.py)
+    steps_lr = [0, 1, 10, 99, 100, 101, 500, 1000, 5000]
+    out["lr_steps"] = np.array(steps_lr)
+    out["lr_warmup_decay"] = np.array([ref.lr.linear_warmup_linear_decay_lr_lambda(s_, num_warmup_steps=100, num_training_steps=1000) for s_ in steps_lr])
+    out["lr_warmup_plateau"] = np.array([ref.lr.linear_warmup_plateau_lr_lambda(s_, num_warmup_steps=100, start_factor=0.1, end_factor=0.8) for s_ in steps_lr])
+    out["lr_linear"] = np.array([ref.lr.linear(s_, start_factor=0.2, slope=-1e-3) for s_ in steps_lr])
 
     path = os.path.join(HERE, "reference_exec.npz")
     np.savez_compressed(path, **out)

@@ -164,3 +164,27 @@ def test_vocabulary_and_name_helpers_equal_reference(gold):
     for bad in ("B", "XYZ", "ALAA"):
         with pytest.raises(ValueError):
             RM.convert_to_three_letter_code(bad)
+
+
+def test_sigma_distributions_and_lr_schedules_equal_reference(gold):
+    """jamun_b200.distributions / jamun_b200.lr_schedules (host logic of the product) against the reference's own classes run
+    under the same seed: every Hydra `sigma_distribution` target and the LambdaLR multipliers of `lr_scheduler_config`."""
+    from jamun_b200 import distributions as D
+    from jamun_b200 import lr_schedules as L
+
+    makers = {"constant": lambda: D.ConstantSigma(0.04), "uniform": lambda: D.UniformSigma(0.5, 0.01),
+              "exponential": lambda: D.ExponentialSigma(50.0, 1e-2), "lognormal": lambda: D.ClippedLogNormalSigma(-1.2, 1.5, 2.0),
+              "uniform_plus_normal": lambda: D.UniformPlusNormal(0.3, (4, 3)),
+              "uniform_measurement": lambda: D.UniformMeasurement(0.5, 4),
+              "weighted_measurement": lambda: D.WeightedMeasurement(0.5, torch.tensor([0.1, 0.2, 0.3, 0.4]))}
+    for name, mk in makers.items():
+        torch.manual_seed(123)
+        d = mk()
+        got = torch.stack([d.sample() for _ in range(5)] + [d.sample((3,))[i] for i in range(3)])
+        assert torch.equal(got, T(gold[f"dist_{name}"])), name
+    mean = D.WeightedMeasurement(0.5, torch.tensor([0.1, 0.2, 0.3, 0.4])).mean
+    assert torch.allclose(mean, T(gold["dist_measurement_mean"]), rtol=1e-6, atol=0)
+    steps = [int(s) for s in gold["lr_steps"]]
+    assert [L.linear_warmup_linear_decay_lr_lambda(s, num_warmup_steps=100, num_training_steps=1000) for s in steps] == list(gold["lr_warmup_decay"])
+    assert [L.linear_warmup_plateau_lr_lambda(s, num_warmup_steps=100, start_factor=0.1, end_factor=0.8) for s in steps] == list(gold["lr_warmup_plateau"])
+    assert [L.linear(s, start_factor=0.2, slope=-1e-3) for s in steps] == list(gold["lr_linear"])
