@@ -31,10 +31,9 @@ class EMA:
         if self.step % self.every_n_steps:
             return
         for e, p in zip(self._ema, self._params):
-            if p.is_cuda:
-                ops.ema_update(e, p.detach().contiguous(), self.decay)
-            else:  # host-side parameters (not on the product path)
-                e.mul_(self.decay).add_(p.detach(), alpha=1 - self.decay)
+            if not p.is_cuda:
+                raise RuntimeError("jamun_b200 EMA updates CUDA parameters only (no CPU fallback)")
+            ops.ema_update(e, p.detach().contiguous(), self.decay)
 
     def swap_model_weights(self) -> None:
         for e, p in zip(self._ema, self._params):
