@@ -20,16 +20,19 @@ from . import engine, ops
 T = torch.ops.jamun_b200
 
 
-_grids = {}  # (r_cut, device) -> (centres on the device, spacing): uploaded once (a per-step upload would drain the stream)
+_grids = {}  # (r_cut, device) -> (centres on the device, spacing)
 
 
 def _radial_grid(r_cut: float, device):
+    """Radial-basis centres for this cut-off (host linspace, as the sampling path's plan.radial_grid).  Cached per cut-off; a new
+    cut-off (sigma drawn from a continuous distribution: one per step) is uploaded from pinned memory without blocking -- a
+    pageable host-to-device copy would wait for the stream and stop the host from running ahead."""
     key = (r_cut, str(device))
     if key not in _grids:
         if len(_grids) > 64:
             _grids.clear()
         values = torch.linspace(0.0, r_cut, ops.NBASIS + 2, dtype=torch.float32)
-        _grids[key] = (values[1:-1].to(device).contiguous(), float(values[1] - values[0]))
+        _grids[key] = (values[1:-1].contiguous().pin_memory().to(device, non_blocking=True), float(values[1] - values[0]))
     return _grids[key]
 
 
