@@ -441,3 +441,37 @@ def test_rowmat_mul_shapes_vs_fp64(rows, a, b, trans, acc, live):
     scale = want.abs().max().item()
     assert (Y[:live, 3:3 + b].double() - want).abs().max().item() <= 2e-5 * scale
     assert torch.equal(Y[live:], Y0[live:]) and torch.equal(Y[:, :3], Y0[:, :3]) and torch.equal(Y[:, 3 + b:], Y0[:, 3 + b:])
+
+
+def test_training_step_has_no_host_synchronisation(models):
+    """After the first steps (Topology built, caches warm) a training step with sigma drawn from a continuous distribution --
+    a new cut-off, radial grid and loss weight every step -- issues no synchronising CUDA call: the host runs ahead of the GPU."""
+    import jamun_b200 as J
+    from jamun_b200 import data, distributions, synthetic
+
+    o32, _, _ = models
+    prod = J.default_denoiser(sigma_distribution=distributions.UniformSigma(0.08, 0.02))
+    prod.load_state_dict(o32.state_dict())
+    prod = prod.to("cuda").train()
+    batch = data.Batch.from_tensors(synthetic.make_tensors([20, 17, 9, 30])).to("cuda")
+    opt = torch.optim.Adam(prod.parameters(), lr=1e-4)
+    torch.manual_seed(3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = prod.training_step(batch, 0)
+        out["loss"].backward()
+        opt.step()
+        return out
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        outs = [step() for _ in range(3)]
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    sig = [float(o["sigma"]) for o in outs]
+    assert len(set(sig)) == 3 and all(0.02 <= s <= 0.08 for s in sig)
+    assert all(torch.isfinite(o["loss"]).item() for o in outs)
