@@ -475,3 +475,29 @@ def test_training_step_has_no_host_synchronisation(models):
     sig = [float(o["sigma"]) for o in outs]
     assert len(set(sig)) == 3 and all(0.02 <= s <= 0.08 for s in sig)
     assert all(torch.isfinite(o["loss"]).item() for o in outs)
+
+
+def test_atom_embedding_backward_with_many_atoms(models):
+    """The table gradients with the atoms split over several CTAs per table row (N > 1024: per-split partial rows summed in
+    order) against torch, and bit-reproducible."""
+    import jamun_b200.autograd_ops  # noqa: F401
+
+    T = torch.ops.jamun_b200
+    _, _, prod = models
+    g = prod.arch_module
+    gen = torch.Generator().manual_seed(17)
+    N = 5000 + 37
+    idx = [torch.randint(0, hi, (N,), generator=gen, dtype=torch.int32).cuda() for hi in (5, 7, 21, 1)]
+    tabs = [tb.detach() for tb in g.atom_embedder.tables()]
+    scale = (1 + 0.1 * torch.randn(56, generator=gen)).cuda()
+    dx0 = torch.randn(N, 56, generator=gen).cuda()
+    grads = []
+    for _ in range(2):
+        la = [_leaf(v) for v in (*tabs, scale)]
+        T.atom_embed(*idx, *la).backward(dx0)
+        grads.append([a.grad.clone() for a in la])
+    lb = [_leaf(v) for v in (*tabs, scale)]
+    (torch.cat([tb[i.long()] for tb, i in zip(lb[:4], idx)], dim=1) * lb[4]).backward(dx0)
+    for k, (a, b) in enumerate(zip(grads[0], lb)):
+        _close(a, b.grad, 1e-4, f"embed grad {k}")
+    assert all(torch.equal(a, b) for a, b in zip(*grads))
