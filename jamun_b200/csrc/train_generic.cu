@@ -391,7 +391,7 @@ extern "C" int jamun_rowmat_mul(const float* X, int ldx, const float* W, int ldw
 }
 
 // scratch: >= jamun_rowmat_dw_scratch(rows, a, b) floats
-inline int dw_splits(int rows) { return pick_splits(rows, 256, 2 * jb::kNumSMs); }
+inline int dw_splits(int rows) { return pick_splits(rows, 64, 2 * jb::kNumSMs); }  // >= 64 rows per CTA, at most two CTAs per SM
 
 extern "C" long long jamun_rowmat_dw_scratch(int rows, int a, int b) { return (long long)dw_splits(rows) * a * b; }
 
