@@ -328,9 +328,21 @@ colsum_kernel(const float* __restrict__ M, int ld, int rows, const int* __restri
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
     const int n_begin = blockIdx.y * rows_per_split, n_end = min(rows, n_begin + rows_per_split);
     float acc = 0.f;
-    if (c < cols)
-        for (int n = n_begin + ry; n < n_end; n += 8)
-            if (!flag || flag[n] == flag_value) acc += M[(size_t)n * ld + c];
+    if (c < cols) {
+        // four rows in flight per thread (independent partial sums, combined in a fixed order)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int n = n_begin + ry;
+        for (; n + 24 < n_end; n += 32) {
+            const float v0 = (!flag || flag[n] == flag_value) ? M[(size_t)n * ld + c] : 0.f;
+            const float v1 = (!flag || flag[n + 8] == flag_value) ? M[(size_t)(n + 8) * ld + c] : 0.f;
+            const float v2 = (!flag || flag[n + 16] == flag_value) ? M[(size_t)(n + 16) * ld + c] : 0.f;
+            const float v3 = (!flag || flag[n + 24] == flag_value) ? M[(size_t)(n + 24) * ld + c] : 0.f;
+            a0 += v0, a1 += v1, a2 += v2, a3 += v3;
+        }
+        for (; n < n_end; n += 8)
+            if (!flag || flag[n] == flag_value) a0 += M[(size_t)n * ld + c];
+        acc = (a0 + a1) + (a2 + a3);
+    }
     red[ry][threadIdx.x & 31] = acc;
     __syncthreads();
     if (ry == 0 && c < cols) {
