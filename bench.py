@@ -510,33 +510,40 @@ def run_native(args):
         torch.cuda.empty_cache()
         # ---- the other BASELINE configs, same process, same clocks
         configs = {}
+
+        def extra(name: str, fn):
+            """One of the other BASELINE configs.  On a single GPU a failure there (e.g. out of memory on a shared box) is recorded
+            in its entry instead of losing the headline line; with several ranks it must propagate (the others wait in collectives)."""
+            try:
+                configs[name] = fn()
+            except Exception as exc:  # noqa: BLE001
+                if cx.world > 1:
+                    raise
+                configs[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
+        def sampling_config(workload, n_chains, inner, steps, text):
+            c = measure_sampling(cx, model, workload, n_chains, inner, steps, 3, e2e=True)
+            c.pop("_state")
+            c["config"] = text
+            return c
+
+        def training_config(n_graphs, text):
+            c = measure_training(cx, n_graphs, 3, 3)
+            c["config"] = text
+            return c
+
         if not args.no_configs and args.workload == "2AA":
-            c3 = measure_sampling(cx, model, "4AA", 1024, 16, 3, 3, e2e=True)
-            c3.pop("_state")
-            c3["config"] = f"C3: uncapped 4AA, 1024 chains/GPU x {cx.world} GPU(s) = {1024 * cx.world} chains, 16 steps per bench " \
-                           f"step, samples gathered over NCCL"
-            configs["C3_4AA"] = c3
-            torch.cuda.empty_cache()
-            c5 = measure_training(cx, 1024, 3, 3)
-            c5["config"] = "C5: training step fwd+bwd on synthetic 4AA batches, 1024 graphs/GPU, DDP all-reduce at N>1"
-            configs["C5_train4AA"] = c5
-            torch.cuda.empty_cache()
+            extra("C3_4AA", lambda: sampling_config("4AA", 1024, 16, 3, f"C3: uncapped 4AA, 1024 chains/GPU x {cx.world} GPU(s) = "
+                                                    f"{1024 * cx.world} chains, 16 steps per bench step, samples gathered over NCCL"))
+            extra("C5_train4AA", lambda: training_config(1024, "C5: training step fwd+bwd on synthetic 4AA batches, 1024 graphs/GPU, DDP "
+                                                               "all-reduce at N>1"))
             if cx.world == 1:
-                c1 = measure_sampling(cx, model, "ala2_capped", 64, 100, 3, 3, e2e=True)
-                c1.pop("_state")
-                c1["config"] = "C1: capped ALA-ALA (22 atoms), 64 chains x 100 walk-jump steps per bench step"
-                configs["C1_ala2_capped"] = c1
-                torch.cuda.empty_cache()
-                c5s = measure_training(cx, 32, 3, 3)
-                c5s["config"] = "C5 (reference batch size): 32 graphs/GPU (data/md.yaml:3)"
-                configs["C5_train4AA_batch32"] = c5s
-                torch.cuda.empty_cache()
-                c4 = measure_sampling(cx, model, "protein1000", 512, 4, 2, 3, e2e=True)
-                c4.pop("_state")
-                c4["config"] = "C4: 1000-atom chains, 512 chains/GPU (512 k atoms, conv operand processed in row chunks), 4 steps " \
-                               "per bench step"
-                configs["C4_protein1000"] = c4
-                torch.cuda.empty_cache()
+                extra("C1_ala2_capped", lambda: sampling_config("ala2_capped", 64, 100, 3, "C1: capped ALA-ALA (22 atoms), 64 chains x 100 "
+                                                                "walk-jump steps per bench step"))
+                extra("C5_train4AA_batch32", lambda: training_config(32, "C5 (reference batch size): 32 graphs/GPU (data/md.yaml:3)"))
+                extra("C4_protein1000", lambda: sampling_config("protein1000", 512, 4, 2, "C4: 1000-atom chains, 512 chains/GPU (512 k atoms, "
+                                                                "conv operand processed in row chunks), 4 steps per bench step"))
         if cx.rank == 0:
             if configs:
                 line["configs"] = configs
@@ -544,7 +551,7 @@ def run_native(args):
                 o = oracle_from(model.state_dict())
                 line["cpu_baseline"] = cpu_baseline_block(args.workload, chains, args.cpu_sample_chains, o)
                 line["parity"] = parity_block(model, args.workload, chains, args.cpu_sample_chains, cx.dev, o)
-                if "C3_4AA" in configs:
+                if "e2e" in configs.get("C3_4AA", {}):
                     configs["C3_4AA"]["cpu_baseline"] = cpu_baseline_block("4AA", 1024, max(4, args.cpu_sample_chains // 2), o)
                     configs["C3_4AA"]["speedup_vs_cpu_like_for_like"] = \
                         configs["C3_4AA"]["e2e"]["value"] / configs["C3_4AA"]["cpu_baseline"]["value_without_redundant_jump"]
