@@ -261,10 +261,7 @@ class E3ConvPlan:
             self.w0r_all = up(torch.stack([b.pack(emb)["w0r"] for b in [gc.initial_projector, *gc.layers]]))      # [L, 32, 64]
             self.b0eff_all = up(torch.stack([b.pack(emb)["b0eff"] for b in [gc.initial_projector, *gc.layers]]))  # [L, 2, 64]
             self.w0r_frag = ops.radial_pack_frag(self.w0r_all) if RADIAL_IMPL == "mma" else None  # tensor-core weight images
-            f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
-            self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
-            self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
-            self.skips = [ops.noise_mlp(*map(f32, m.weights.mlp_operands()), self.c_noise, True) for m in g.skip_connections]
+            self.set_noise(g, self.c_noise, bump=False)
             blk, lin2 = gc.output_head[0], gc.output_head[1]
             self.head_w1s = up(blk.lin.packed(0))
             self.head_w1v = up(blk.lin.packed(1))
@@ -272,6 +269,20 @@ class E3ConvPlan:
             self.head_w2 = up(lin2.packed(1).reshape(-1) * gc.output_gain.detach())
         self.n_basis = ops.NBASIS
         self._grids: Dict[float, tuple] = {}  # r_cut -> (centres on the device, spacing); never evicted (see radial_grid)
+
+    def set_noise(self, g, c_noise: float, bump: bool = True) -> None:
+        """The only noise-level-dependent operands: the outputs of the 11 noise-conditioning MLPs (jamun_noise_mlp).  A new noise
+        level on an existing plan recomputes just these (the packed weight images are sigma-independent) into *fresh* tensors and
+        takes a new serial, so CUDA graphs and per-topology constants captured for the previous level are never reused."""
+        dev = self.device
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+        self.c_noise = float(c_noise)
+        with torch.no_grad():
+            self.s_init = ops.noise_mlp(*map(f32, g.initial_noise_scaling.mlp_operands()), self.c_noise, False)
+            self.scales = [ops.noise_mlp(*map(f32, m.mlp_operands()), self.c_noise, False) for m in g.noise_scalings]
+            self.skips = [ops.noise_mlp(*map(f32, m.weights.mlp_operands()), self.c_noise, True) for m in g.skip_connections]
+        if bump:
+            self.serial = next(E3ConvPlan._serials)
 
     def radial_grid(self, r_cut: float):
         """soft_one_hot_linspace(..., cutoff=True) grid: centres linspace(0, r, n+2)[1:-1] and their spacing.

@@ -52,11 +52,15 @@ class E3Conv(torch.nn.Module):
     def plan(self, c_noise: float, device) -> "engine.E3ConvPlan":
         import os
 
-        key = (float(c_noise), str(device), tuple(p._version for p in self.parameters()),
+        # everything but the noise level: a change here rebuilds the packed weight images; a new noise level alone only
+        # re-evaluates the noise-conditioning MLPs (validation / training draw sigma from a continuous distribution)
+        key = (str(device), tuple(p._version for p in self.parameters()),
                tuple(p.data_ptr() for p in self.parameters()), os.environ.get("JAMUN_B200_GEMM", engine.GEMM_KIND))
         if self._plan is None or self._plan_key != key:
             self._plan = engine.E3ConvPlan(self, float(c_noise), device)
             self._plan_key = key
+        elif self._plan.c_noise != float(c_noise):
+            self._plan.set_noise(self, float(c_noise))
         return self._plan
 
     def forward(self, data, c_noise: torch.Tensor, effective_radial_cutoff: float):

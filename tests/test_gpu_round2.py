@@ -241,3 +241,27 @@ def test_radial_hidden_tensor_core_kernel_matches_fp64_and_cuda_core_kernel():
         assert torch.allclose(got[:, :E].cpu(), want, rtol=2e-6, atol=2e-6), (got[:, :E].cpu() - want).abs().max()
         assert torch.all(got[:, E:] == -7.0)
     assert (h_mma[:, :E] - h_ffma[:, :E]).abs().max().item() < 4e-6
+
+
+def test_new_noise_level_reuses_the_packed_plan(models):
+    """a new sigma (validation / training draw it from a continuous distribution) must not re-pack the weight images --
+    only the 11 noise-conditioning MLP outputs are re-evaluated; results equal those of a freshly built plan, bit for bit."""
+    from jamun_b200 import data, ops, synthetic
+
+    _, _, prod = models
+    batch = data.Batch.from_tensors(synthetic.make_tensors([22, 15, 9])).to("cuda")
+    arch = prod.arch_module
+    xa = prod.xhat(batch, 0.04).pos.clone()
+    plan = arch._plan
+    imgs = [b["b0_img"].data_ptr() for b in plan.blocks]
+    n0 = ops.LAUNCHES
+    xb = prod.xhat(batch, 0.07).pos.clone()
+    launched = ops.LAUNCHES - n0
+    assert arch._plan is plan and [b["b0_img"].data_ptr() for b in plan.blocks] == imgs
+    assert launched < 11 + 80, launched  # 11 noise MLPs + one evaluation (~60 launches), no pack_b launches
+    xa2 = prod.xhat(batch, 0.04).pos.clone()
+    assert torch.equal(xa, xa2) and not torch.equal(xa, xb)
+    arch._plan = None  # fresh plans at both levels
+    assert torch.equal(prod.xhat(batch, 0.07).pos, xb)
+    arch._plan = None
+    assert torch.equal(prod.xhat(batch, 0.04).pos, xa)
